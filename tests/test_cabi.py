@@ -1,0 +1,38 @@
+"""CPU checks of the drop-in boundary: the library loads and exports every symbol
+that include/pfpn_b200.h declares; argument validation works without a GPU."""
+import ctypes as C
+
+from pfpn_b200 import _cabi
+
+
+def test_library_exports_every_declared_symbol():
+    names = _cabi.exported_symbols()
+    assert "pfpn_head_logprob" in names and len(names) >= 6
+    for n in names:
+        assert hasattr(_cabi.lib, n), n
+
+
+def test_abi_version_and_status_strings():
+    assert _cabi.pfpn_abi_version() == 1
+    assert _cabi.pfpn_status_string(0) == b"ok"
+    for code in (-1, -2, -3, -4):
+        assert _cabi.pfpn_status_string(code).startswith(b"pfpn:")
+
+
+def test_argument_errors_without_gpu():
+    n = C.c_size_t(0)
+    assert _cabi.pfpn_head_workspace_bytes(36, 35, C.byref(n)) == 0 and n.value > 0
+    assert _cabi.pfpn_head_workspace_bytes(0, 35, C.byref(n)) == -1
+    assert _cabi.pfpn_head_logprob(None, None, 0, None) == -1
+    a = _cabi.HeadArgs()
+    a.B, a.A, a.P = 4, 36, 35
+    assert _cabi.pfpn_head_logprob(C.byref(a), None, 0, None) == -1  # null pointers
+
+
+def test_head_args_layout_matches_header():
+    # 20 pointers/floats interleaved + 5 ints: catch accidental reordering
+    assert _cabi.HeadArgs.logits.offset == 0
+    assert _cabi.HeadArgs.g_ent.offset == 48 and _cabi.HeadArgs.adv.offset == 56
+    assert _cabi.HeadArgs.eps_clip.offset == 80 and _cabi.HeadArgs.loss_scale.offset == 84
+    assert _cabi.HeadArgs.lp.offset == 88 and _cabi.HeadArgs.loss.offset == 144
+    assert _cabi.HeadArgs.B.offset == 152 and C.sizeof(_cabi.HeadArgs) == 176
