@@ -55,17 +55,24 @@ __device__ __forceinline__ float softplusf_acc(float x) {
   return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));
 }
 
-template <int LPR, int EPL, int RPT, int NSTAGE, bool BWD, int MAXT, int NREG>
+template <int LPR, int EPL, int RPT, int NSTAGE, bool BWD, int MAXT, int NREG, int PT>
 __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const HeadKParams kp) {
   constexpr int EP2 = (EPL + 1) / 2;  // packed pairs per lane
   constexpr int DIST = NSTAGE - 2;    // load prefetch distance (tiles)
   static_assert(NSTAGE >= 3, "need >=3 stages: 1 computing, >=1 loading, 1 draining");
-  const pfpn_head_args& ar = kp.a;
-  const int A = ar.A, P = ar.P, B = ar.B;
+  // hot parameters into registers / uniform registers once
+  const int A = kp.a.A, B = kp.a.B;
+  const int P = PT > 0 ? PT : kp.a.P;  // PT > 0: particle count known at compile time
   const int AP = A * P;
   const int slots = kp.slots;
   const int TS = slots * RPT;
   const int tile_floats = TS * AP;
+  const uint32_t mode = kp.a.mode;
+  const float* __restrict__ g_logits = kp.a.logits;
+  const float* __restrict__ g_value = kp.a.value;
+  float* __restrict__ g_dlogits = kp.a.dlogits;
+  float* __restrict__ g_dvalue = kp.a.dvalue;
+  float* __restrict__ g_ent_ba = kp.a.ent_ba;
   const int tid = threadIdx.x;
   const int nthr = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
@@ -76,9 +83,10 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   unsigned char* tail = smem_raw + (size_t)NSTAGE * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
-  float2* rowbuf = reinterpret_cast<float2*>(tail + 8 * NSTAGE);  // [2][TS*A]
+  float2* rowbuf = reinterpret_cast<float2*>(tail + 8 * NSTAGE);    // [2][TS*A]
   float* statebuf = reinterpret_cast<float*>(rowbuf + 2 * TS * A);  // [TS]
-  float* lossbuf = statebuf + TS;                                   // [nwarps]
+  float* lossbuf = statebuf + TS;                                   // [kHeadMaxWarps]
+  float* dummy = lossbuf + kHeadMaxWarps;                           // [LPR*EPL] sink for masked rows
 
   if (tid == 0) {
 #pragma unroll
@@ -87,11 +95,16 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
   }
 
   // ---- fixed thread -> (slot, a, particle set) mapping ---------------------
+  // lane c of a row owns particles k = c + LPR*i, i = 0..EPL-1.  Slots i < nfull are
+  // valid for every lane, slot nfull only for c < P % LPR, later slots for nobody.
   const int row_in_cta = tid / LPR;
   const int c = tid % LPR;
   const int slot = row_in_cta / A;
   const int a = row_in_cta - slot * A;
   const bool active = slot < slots;
+  const int nfull = P / LPR;
+  const bool part_ok = c < P - nfull * LPR;
+  auto k_ok = [&](int i) -> bool { return (i < nfull) || (i == nfull && part_ok); };
 
   float2 isig[EP2], nmisig[EP2], cst[EP2];
   float2 acc1[EP2], acc2[EP2];
@@ -100,11 +113,12 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
     float v[2][3];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int k = c + LPR * (2 * i2 + h);
-      const bool ok = active && (2 * i2 + h < EPL) && (k < P);
-      float ls = ok ? __ldg(&ar.logstd[a * P + k]) : 0.f;
-      float mu = ok ? __ldg(&ar.loc[a * P + k]) : 0.f;
-      float is = ok ? expf(-ls) : 0.f;
+      const int i = 2 * i2 + h;
+      const bool ok = active && (i < EPL) && k_ok(i);
+      const int k = c + LPR * i;
+      const float ls = ok ? __ldg(&kp.a.logstd[a * P + k]) : 0.f;
+      const float mu = ok ? __ldg(&kp.a.loc[a * P + k]) : 0.f;
+      const float is = ok ? expf(-ls) : 0.f;
       v[h][0] = is;
       v[h][1] = -mu * is;
       v[h][2] = ok ? -(ls + kHalfLog2Pi) * kLog2e : 0.f;
@@ -115,14 +129,16 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
     acc1[i2] = make_float2(0.f, 0.f);
     acc2[i2] = make_float2(0.f, 0.f);
   }
-  const bool tanh_flag = (ar.flags & PFPN_HEAD_FLAG_TANH) != 0;
+  const bool tanh_flag = (kp.a.flags & PFPN_HEAD_FLAG_TANH) != 0;
   const bool tail_exists = (B % TS) != 0;
   const int tail_tile = kp.num_tiles - 1;
+  const bool has_ent_grad = kp.has_ent_grad != 0;
+  const float eps_clip = kp.a.eps_clip, loss_scale = kp.a.loss_scale;
 
   float adv_mean = 0.f, adv_rstd = 1.f;
-  if (ar.mode == PFPN_HEAD_PPO && ar.adv_stats != nullptr) {
-    adv_mean = __ldg(&ar.adv_stats[0]);
-    adv_rstd = __ldg(&ar.adv_stats[1]);
+  if (mode == PFPN_HEAD_PPO && kp.a.adv_stats != nullptr) {
+    adv_mean = __ldg(&kp.a.adv_stats[0]);
+    adv_rstd = __ldg(&kp.a.adv_stats[1]);
   }
   float loss_acc = 0.f;
 
@@ -140,7 +156,7 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
     const int st = it % NSTAGE;
     const uint32_t bar = smem_u32(&full_bar[st]);
     mbar_expect_tx(bar, (uint32_t)(tile_floats * 4));
-    bulk_g2s(smem_u32(stage_base) + st * stage_bytes, ar.logits + (size_t)tile * tile_floats,
+    bulk_g2s(smem_u32(stage_base) + st * stage_bytes, g_logits + (size_t)tile * tile_floats,
              (uint32_t)(tile_floats * 4), bar);
   };
   if (tid == 0) {
@@ -155,13 +171,17 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
       const int b = tile * TS + j * slots + slot;
-      dst[j] = (it < my_tiles && active && b < B) ? __ldg(&ar.value[(size_t)b * A + a]) : 0.f;
+      dst[j] = (it < my_tiles && active && b < B) ? __ldg(&g_value[(size_t)b * A + a]) : 0.f;
     }
   };
   load_values(0, v_nxt);
 
   int prev_tile = -1, prev_stage = 0;
   bool prev_was_tail = false;
+
+  const float2 L2 = splat2(kLog2e);
+  const float2 nhl = splat2(-0.5f * kLog2e);
+  const float2 neg1 = splat2(-1.f);
 
   for (int it = 0; it < my_tiles; ++it) {
     const int tile = first_tile + it * tile_step;
@@ -180,11 +200,11 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
     if (BWD && lane == 0 && warp < TS) {
       const int b = b0 + warp;
       if (b < B) {
-        if (ar.mode == PFPN_HEAD_PPO) {
-          pre_adv = __ldg(&ar.adv[b]);
-          pre_lpo = __ldg(&ar.lp_old[b]);
+        if (mode == PFPN_HEAD_PPO) {
+          pre_adv = __ldg(&kp.a.adv[b]);
+          pre_lpo = __ldg(&kp.a.lp_old[b]);
         } else {
-          pre_g = __ldg(&ar.g_lp[b]);
+          pre_g = __ldg(&kp.a.g_lp[b]);
         }
       }
     }
@@ -193,7 +213,7 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
       mbar_wait(smem_u32(&full_bar[st]), (uint32_t)((it / NSTAGE) & 1));
     } else {
       const int nvalid = (B - b0) * AP;
-      const float* src = ar.logits + (size_t)b0 * AP;
+      const float* src = g_logits + (size_t)b0 * AP;
       for (int idx = tid; idx < nvalid; idx += nthr) sbuf[idx] = __ldg(&src[idx]);
       __syncthreads();
     }
@@ -206,20 +226,20 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
     for (int j = 0; j < RPT; ++j) {
       const int srow_idx = (j * slots + slot) * A + a;
       const bool row_ok = active && (b0 + j * slots + slot < B);
-      const float* srow = sbuf + srow_idx * P + c;
+      // masked rows read state 0 of the tile (always valid, finite) and are discarded
+      const float* ld = sbuf + (row_ok ? srow_idx : a) * P + c;
       float2 l[EP2];
       float m = kNegBig;
 #pragma unroll
       for (int i2 = 0; i2 < EP2; ++i2) {
-        const int k0 = c + LPR * (2 * i2), k1 = k0 + LPR;
-        l[i2].x = (row_ok && k0 < P) ? srow[LPR * (2 * i2)] : kNegBig;
-        l[i2].y = (row_ok && (2 * i2 + 1 < EPL) && k1 < P) ? srow[LPR * (2 * i2 + 1)] : kNegBig;
+        const int i0 = 2 * i2, i1 = 2 * i2 + 1;
+        l[i2].x = (i0 < nfull) ? ld[LPR * i0] : ((i0 == nfull && part_ok) ? ld[LPR * i0] : kNegBig);
+        l[i2].y = (i1 >= EPL) ? kNegBig
+                              : ((i1 < nfull) ? ld[LPR * i1] : ((i1 == nfull && part_ok) ? ld[LPR * i1] : kNegBig));
         m = max3f(m, l[i2].x, l[i2].y);
       }
       m = row_max<LPR>(m);
       const float2 nmL = splat2(-m * kLog2e);
-      const float2 L2 = splat2(kLog2e);
-      const float2 nhl = splat2(-0.5f * kLog2e);
       const float2 v2 = splat2(v_cur[j]);
       float2 s1 = make_float2(0.f, 0.f), s2 = s1, h = s1;
 #pragma unroll
@@ -258,7 +278,7 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
       l2s1[j] = lg1;
       if (row_ok && c == 0) {
         rb[srow_idx] = make_float2(lnp, Hval);
-        if (ar.ent_ba != nullptr) ar.ent_ba[(size_t)(b0 + j * slots + slot) * A + a] = Hval;
+        if (g_ent_ba != nullptr) g_ent_ba[(size_t)(b0 + j * slots + slot) * A + a] = Hval;
       }
     }
     __syncthreads();  // B1: rowbuf complete; previous tile's gradient stores fenced
@@ -266,8 +286,8 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
     // ---------------- thread 0: drain previous tile, prefetch ----------------
     if (tid == 0) {
       if (BWD && prev_tile >= 0) {
-        bulk_s2g(ar.dlogits + (size_t)prev_tile * tile_floats,
-                 smem_u32(stage_base) + prev_stage * stage_bytes, (uint32_t)(tile_floats * 4));
+        bulk_s2g(g_dlogits + (size_t)prev_tile * tile_floats, smem_u32(stage_base) + prev_stage * stage_bytes,
+                 (uint32_t)(tile_floats * 4));
         bulk_commit();
         bulk_wait_read<1>();
       }
@@ -286,22 +306,22 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
       lp = row_sum<32>(lp);
       en = row_sum<32>(en);
       if (lane == 0 && b < B) {
-        ar.lp[b] = lp;
-        if (ar.ent != nullptr) ar.ent[b] = en;
+        kp.a.lp[b] = lp;
+        if (kp.a.ent != nullptr) kp.a.ent[b] = en;
         if (BWD) {
           float g;
-          if (ar.mode == PFPN_HEAD_PPO) {
+          if (mode == PFPN_HEAD_PPO) {
             // (s == warp always holds while TS <= nwarps; otherwise re-read)
-            const float adv_raw = (s == warp) ? pre_adv : __ldg(&ar.adv[b]);
-            const float lpo = (s == warp) ? pre_lpo : __ldg(&ar.lp_old[b]);
+            const float adv_raw = (s == warp) ? pre_adv : __ldg(&kp.a.adv[b]);
+            const float lpo = (s == warp) ? pre_lpo : __ldg(&kp.a.lp_old[b]);
             const float an = (adv_raw - adv_mean) * adv_rstd;
             const float ratio = expf(lp - lpo);
             const float surr = ratio * an;
-            const float clipped = fminf(fmaxf(ratio, 1.f - ar.eps_clip), 1.f + ar.eps_clip) * an;
-            loss_acc -= fminf(surr, clipped) * ar.loss_scale;
-            g = (surr <= clipped) ? -ar.loss_scale * ratio * an : 0.f;  // TF Minimum: ties -> x
+            const float clipped = fminf(fmaxf(ratio, 1.f - eps_clip), 1.f + eps_clip) * an;
+            loss_acc -= fminf(surr, clipped) * loss_scale;
+            g = (surr <= clipped) ? -loss_scale * ratio * an : 0.f;  // TF Minimum: ties -> x
           } else {
-            g = (s == warp) ? pre_g : __ldg(&ar.g_lp[b]);
+            g = (s == warp) ? pre_g : __ldg(&kp.a.g_lp[b]);
           }
           statebuf[s] = g;
         }
@@ -317,7 +337,7 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
         const int srow_idx = sidx * A + a;
         const int b = b0 + sidx;
         const bool row_ok = active && (b < B);
-        float* srow = sbuf + srow_idx * P + c;
+        float* stp = row_ok ? (sbuf + srow_idx * P + c) : (dummy + c);
         const float g = row_ok ? statebuf[sidx] : 0.f;
         const bool p_ok = s2r[j] > 0.f;
         // guard of utils.py:109-117: dL/dp is Inf/NaN when p == 0 -> zeroed
@@ -325,62 +345,55 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
         const float gs2 = p_ok ? g_row * rcpf(s2r[j]) : 0.f;
         const float2 v2 = splat2(v_cur[j]);
         const float2 gs2v = splat2(gs2);
-        float dv = 0.f;
-        if (!kp.has_ent_grad) {
-          const float2 nc0 = splat2(-g_row * inv_s1[j]);
-#pragma unroll
-          for (int i2 = 0; i2 < EP2; ++i2) {
-            const float2 rr = mul2(e2[j][i2], gs2v);  // g * r_k
-            const float2 d = fma2(e1[j][i2], nc0, rr);
-            const float2 z = fma2(v2, isig[i2], nmisig[i2]);
-            const float2 q1 = fma2(z, z, splat2(-1.f));
-            acc1[i2] = fma2(rr, z, acc1[i2]);
-            acc2[i2] = fma2(rr, q1, acc2[i2]);
-            if (ar.dvalue != nullptr) {
-              const float2 w = mul2(mul2(rr, z), isig[i2]);
-              dv += w.x + w.y;
-            }
-            const int k0 = c + LPR * (2 * i2), k1 = k0 + LPR;
-            if (row_ok && k0 < P) srow[LPR * (2 * i2)] = d.x;
-            if (row_ok && (2 * i2 + 1 < EPL) && k1 < P) srow[LPR * (2 * i2 + 1)] = d.y;
-          }
+        float2 nc0, nc1;
+        if (!has_ent_grad) {
+          nc0 = splat2(-g_row * inv_s1[j]);
+          nc1 = splat2(0.f);
         } else {
-          float ge = ar.g_ent;
-          if (ar.g_ent_ba != nullptr && row_ok) ge += __ldg(&ar.g_ent_ba[(size_t)b * A + a]);
+          float ge = kp.a.g_ent;
+          if (kp.a.g_ent_ba != nullptr && row_ok) ge += __ldg(&kp.a.g_ent_ba[(size_t)b * A + a]);
           // dH/dl_k = -pi_k (ln pi_k + H),  ln pi_k = ln2*(t_k - log2 s1)
-          const float c0 = (g_row + ge * (Hrow[j] - kLn2 * l2s1[j])) * inv_s1[j];
-          const float2 nc0 = splat2(-c0);
-          const float2 nc1 = splat2(-ge * kLn2 * inv_s1[j]);
+          nc0 = splat2(-(g_row + ge * (Hrow[j] - kLn2 * l2s1[j])) * inv_s1[j]);
+          nc1 = splat2(-ge * kLn2 * inv_s1[j]);
+        }
 #pragma unroll
-          for (int i2 = 0; i2 < EP2; ++i2) {
-            const float2 rr = mul2(e2[j][i2], gs2v);
-            // t_k = log2(e1_k) would cost a MUFU; recover it from e1 is lossy, so
-            // re-read the logit (still in smem) and recompute t = (l - m)*log2e via
-            // t = log2(e1) only when e1 > 0 is not safe -> use lg2 of e1 guarded.
+        for (int i2 = 0; i2 < EP2; ++i2) {
+          const float2 rr = mul2(e2[j][i2], gs2v);  // g * r_k
+          float2 coef = nc0;
+          if (has_ent_grad) {
+            // t_k = (l_k - m) log2e recovered as log2(e1_k); e1 == 0 contributes nothing
             float2 t;
             t.x = lg2f(fmaxf(e1[j][i2].x, 1e-37f));
             t.y = lg2f(fmaxf(e1[j][i2].y, 1e-37f));
-            const float2 inner = fma2(t, nc1, nc0);
-            const float2 d = fma2(e1[j][i2], inner, rr);
-            const float2 z = fma2(v2, isig[i2], nmisig[i2]);
-            const float2 q1 = fma2(z, z, splat2(-1.f));
-            acc1[i2] = fma2(rr, z, acc1[i2]);
-            acc2[i2] = fma2(rr, q1, acc2[i2]);
-            if (ar.dvalue != nullptr) {
-              const float2 w = mul2(mul2(rr, z), isig[i2]);
-              dv += w.x + w.y;
-            }
-            const int k0 = c + LPR * (2 * i2), k1 = k0 + LPR;
-            if (row_ok && k0 < P) srow[LPR * (2 * i2)] = d.x;
-            if (row_ok && (2 * i2 + 1 < EPL) && k1 < P) srow[LPR * (2 * i2 + 1)] = d.y;
+            coef = fma2(t, nc1, nc0);
+          }
+          const float2 d = fma2(e1[j][i2], coef, rr);
+          const float2 z = fma2(v2, isig[i2], nmisig[i2]);
+          const float2 q1 = fma2(z, z, neg1);
+          acc1[i2] = fma2(rr, z, acc1[i2]);
+          acc2[i2] = fma2(rr, q1, acc2[i2]);
+          const int i0 = 2 * i2, i1 = 2 * i2 + 1;
+          if (i0 < nfull) stp[LPR * i0] = d.x;
+          else if (i0 == nfull && part_ok) stp[LPR * i0] = d.x;
+          if (i1 < EPL) {
+            if (i1 < nfull) stp[LPR * i1] = d.y;
+            else if (i1 == nfull && part_ok) stp[LPR * i1] = d.y;
           }
         }
-        if (ar.dvalue != nullptr) {
+        if (g_dvalue != nullptr) {
+          float dv = 0.f;
+#pragma unroll
+          for (int i2 = 0; i2 < EP2; ++i2) {
+            const float2 rr = mul2(e2[j][i2], gs2v);
+            const float2 z = fma2(v2, isig[i2], nmisig[i2]);
+            const float2 w = mul2(mul2(rr, z), isig[i2]);
+            dv += w.x + w.y;
+          }
           dv = row_sum<LPR>(dv);
           if (row_ok && c == 0) {
             float out = -dv;
             if (tanh_flag) out += g_row * 2.f * tanhf(v_cur[j]);
-            ar.dvalue[(size_t)b * A + a] = out;
+            g_dvalue[(size_t)b * A + a] = out;
           }
         }
       }
@@ -396,15 +409,15 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
   if (BWD && prev_tile >= 0) {
     if (!prev_was_tail) {
       if (tid == 0) {
-        bulk_s2g(ar.dlogits + (size_t)prev_tile * tile_floats,
-                 smem_u32(stage_base) + prev_stage * stage_bytes, (uint32_t)(tile_floats * 4));
+        bulk_s2g(g_dlogits + (size_t)prev_tile * tile_floats, smem_u32(stage_base) + prev_stage * stage_bytes,
+                 (uint32_t)(tile_floats * 4));
         bulk_commit();
       }
     } else {
       const int b0 = prev_tile * TS;
       const int nvalid = (B - b0) * AP;
       const float* sb = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(stage_base) + (size_t)prev_stage * stage_bytes);
-      float* dst = ar.dlogits + (size_t)b0 * AP;
+      float* dst = g_dlogits + (size_t)b0 * AP;
       for (int idx = tid; idx < nvalid; idx += nthr) dst[idx] = sb[idx];
     }
   }
@@ -416,14 +429,14 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
     if (active) {
 #pragma unroll
       for (int i2 = 0; i2 < EP2; ++i2) {
-        const int k0 = c + LPR * (2 * i2), k1 = k0 + LPR;
-        if (k0 < P) {
-          red[(slot * 2 + 0) * AP + a * P + k0] = acc1[i2].x;
-          red[(slot * 2 + 1) * AP + a * P + k0] = acc2[i2].x;
-        }
-        if ((2 * i2 + 1 < EPL) && k1 < P) {
-          red[(slot * 2 + 0) * AP + a * P + k1] = acc1[i2].y;
-          red[(slot * 2 + 1) * AP + a * P + k1] = acc2[i2].y;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = 2 * i2 + h;
+          if (i < EPL && k_ok(i)) {
+            const int k = c + LPR * i;
+            red[(slot * 2 + 0) * AP + a * P + k] = h ? acc1[i2].y : acc1[i2].x;
+            red[(slot * 2 + 1) * AP + a * P + k] = h ? acc2[i2].y : acc2[i2].x;
+          }
         }
       }
     }
@@ -505,24 +518,30 @@ typedef void (*head_kernel_t)(const HeadKParams);
 // first entry whose pmax >= P is the default, PFPN_HEAD_VARIANT=<n> picks the
 // n-th matching entry instead (tuning aid, read once per process).
 struct HeadVariant {
-  int pmax, lpr, epl, rpt, nstage, maxt, nreg;
+  int pmin, pmax, lpr, epl, rpt, nstage, maxt, nreg, pt;
   head_kernel_t fwd, bwd;
 };
-#define PFPN_HEAD_VARIANT_ENTRY(PMAX, LPR, EPL, RPT, NST, MAXT, NREG)                                   \
-  {                                                                                                     \
-    PMAX, LPR, EPL, RPT, NST, MAXT, NREG, head_kernel<LPR, EPL, RPT, NST, false, MAXT, NREG>,           \
-        head_kernel<LPR, EPL, RPT, NST, true, MAXT, NREG>                                               \
+#define PFPN_HEAD_VARIANT_ENTRY(PMIN, PMAX, LPR, EPL, RPT, NST, MAXT, NREG, PT)                            \
+  {                                                                                                        \
+    PMIN, PMAX, LPR, EPL, RPT, NST, MAXT, NREG, PT, head_kernel<LPR, EPL, RPT, NST, false, MAXT, NREG, PT>, \
+        head_kernel<LPR, EPL, RPT, NST, true, MAXT, NREG, PT>                                              \
   }
+// [pmin, pmax] = particle counts an entry serves; PT > 0 entries are specialised for
+// exactly P == PT (the shapes BASELINE.json names), PT == 0 entries take P at run time.
 static const HeadVariant kHeadVariants[] = {
-    PFPN_HEAD_VARIANT_ENTRY(12, 4, 3, 2, 4, 320, 96),
-    PFPN_HEAD_VARIANT_ENTRY(36, 4, 9, 2, 4, 288, 112),
-    PFPN_HEAD_VARIANT_ENTRY(36, 4, 9, 1, 4, 288, 72),
-    PFPN_HEAD_VARIANT_ENTRY(36, 4, 9, 1, 4, 288, 112),
-    PFPN_HEAD_VARIANT_ENTRY(36, 4, 9, 2, 3, 288, 112),
-    PFPN_HEAD_VARIANT_ENTRY(64, 8, 8, 2, 4, 320, 96),
-    PFPN_HEAD_VARIANT_ENTRY(104, 8, 13, 1, 4, 288, 112),
-    PFPN_HEAD_VARIANT_ENTRY(104, 8, 13, 1, 3, 288, 72),
-    PFPN_HEAD_VARIANT_ENTRY(256, 16, 16, 1, 3, 384, 168),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 4, 288, 72, 35),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 6, 288, 72, 35),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 2, 4, 288, 96, 35),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 4, 288, 96, 35),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 2, 3, 288, 72, 35),
+    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 4, 288, 96, 100),
+    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 3, 288, 72, 100),
+    PFPN_HEAD_VARIANT_ENTRY(10, 10, 4, 3, 2, 4, 320, 72, 10),
+    PFPN_HEAD_VARIANT_ENTRY(1, 12, 4, 3, 2, 4, 320, 96, 0),
+    PFPN_HEAD_VARIANT_ENTRY(13, 36, 4, 9, 1, 4, 288, 96, 0),
+    PFPN_HEAD_VARIANT_ENTRY(37, 64, 8, 8, 1, 4, 320, 96, 0),
+    PFPN_HEAD_VARIANT_ENTRY(65, 104, 8, 13, 1, 4, 288, 96, 0),
+    PFPN_HEAD_VARIANT_ENTRY(105, 256, 16, 16, 1, 3, 384, 168, 0),
 };
 
 static const HeadVariant* pick_variant(int P) {
@@ -533,9 +552,9 @@ static const HeadVariant* pick_variant(int P) {
   const HeadVariant* first = nullptr;
   int seen = 0;
   for (const HeadVariant& v : kHeadVariants) {
-    if (v.pmax < P) continue;
+    if (P < v.pmin || P > v.pmax) continue;
     if (first == nullptr) first = &v;
-    if (v.pmax != first->pmax) break;
+    if (v.pt != first->pt) break;
     if (seen == want) return &v;
     ++seen;
   }
@@ -563,7 +582,8 @@ static int plan_head(int A, int P, bool bwd, HeadLaunch* L) {
   L->ts = slots * v.rpt;
   L->threads = (slots * per_slot + 31) & ~31;
   const int stage_bytes = (L->ts * A * P * 4 + 127) & ~127;
-  L->smem_bytes = v.nstage * stage_bytes + 8 * v.nstage + 2 * L->ts * A * 8 + L->ts * 4 + kHeadMaxWarps * 4 + 16;
+  L->smem_bytes = v.nstage * stage_bytes + 8 * v.nstage + 2 * L->ts * A * 8 + L->ts * 4 + kHeadMaxWarps * 4 +
+                  v.lpr * v.epl * 4 + 16;
   L->fn = bwd ? v.bwd : v.fwd;
   int dev = 0;
   PFPN_CUDA_OK(cudaGetDevice(&dev));

@@ -45,7 +45,11 @@ def test_ppo_fused_matches_oracle(cuda_dev, B, A, P):
     assert rel(out["dlogits"], ref["dlogits"]) < TOL
     assert rel(out["dloc"], ref["dloc"]) < TOL
     assert rel(out["dlogstd"], ref["dlogstd"]) < TOL
-    assert rel(out["loss"], ref["loss"].reshape(1)) < TOL
+    # the loss is a mean of B signed terms: bound the error by the mean |term| (norm-wise)
+    an = oh.normalize_advantage(d["adv"].double())
+    ratio = torch.exp(ref["lp"] - d["lp_old"].double())
+    scale = torch.minimum(ratio * an, ratio.clamp(0.8, 1.2) * an).abs().mean()
+    assert abs(float(out["loss"].cpu()) - float(ref["loss"])) < TOL * float(scale)
 
 
 @pytest.mark.parametrize("tanh", [False, True])
