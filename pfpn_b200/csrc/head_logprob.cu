@@ -18,8 +18,9 @@
 //    registers for the whole kernel because a thread's (a, k-set) never changes;
 //  * element math is packed fp32x2 (FFMA2/FMUL2/FADD2) with 2 MUFU.EX2 per
 //    particle; everything is computed in the log2 domain;
-//  * sum over a (log_prob of the state) and the PPO dL/dlp go through a tiny
-//    smem exchange: 2 block barriers per tile.
+//  * sum over a (log_prob of the state) goes through a tiny smem exchange; every
+//    lane re-derives the state's sum and the PPO dL/dlp redundantly, so there is
+//    exactly ONE block barrier per tile.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -55,24 +56,40 @@ __device__ __forceinline__ float softplusf_acc(float x) {
   return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));
 }
 
-template <int LPR, int EPL, int RPT, int NSTAGE, bool BWD, int MAXT, int NREG, int PT>
+// KM (kernel mode): 0 = forward only; 1 = backward, every feature decided at run time;
+// 2 / 3 = lean PPO / GRAD backward (no tanh, no entropy gradient, no dvalue, no ent_ba:
+// the DPPO train step) with those branches compiled out.
+// CSM: per-(a,k) constants live in shared memory instead of registers.
+template <int LPR, int EPL, int RPT, int NSTAGE, int KM, int MAXT, int NREG, int PT, int AT, bool CSM>
 __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const HeadKParams kp) {
+  constexpr bool BWD = KM != 0;
+  constexpr bool LEAN = KM >= 2;
   constexpr int EP2 = (EPL + 1) / 2;  // packed pairs per lane
-  constexpr int DIST = NSTAGE - 2;    // load prefetch distance (tiles)
-  static_assert(NSTAGE >= 3, "need >=3 stages: 1 computing, >=1 loading, 1 draining");
+  // Software pipeline: iteration `it` runs pass A/B of tile it and pass C of tile it-1; the
+  // gradient tile it-2 leaves with a bulk store.  A stage is therefore busy for 3 iterations
+  // after its load completes, plus DIST iterations of prefetch.
+  constexpr int DIST = NSTAGE - 3;
+  static_assert(NSTAGE >= 4, "need >= 4 stages: load-ahead, A/B, C, draining store");
   // hot parameters into registers / uniform registers once
-  const int A = kp.a.A, B = kp.a.B;
-  const int P = PT > 0 ? PT : kp.a.P;  // PT > 0: particle count known at compile time
+  // PT/AT > 0: particle count / action dims known at compile time (the BASELINE shapes);
+  // every index expression below then folds to constants.
+  const int B = kp.a.B;
+  const int A = AT > 0 ? AT : kp.a.A;
+  const int P = PT > 0 ? PT : kp.a.P;
   const int AP = A * P;
-  const int slots = kp.slots;
+  const int slots = AT > 0 ? MAXT / (AT * LPR) : kp.slots;
+  // SEG: a state's rows end on a 16-lane boundary, so the sum over a can be done with
+  // half-warp partials (4 rows each) + one 16-lane butterfly instead of A/LPR strided reads.
+  constexpr bool SEG = AT > 0 && ((AT * LPR) % 16 == 0) && (AT * LPR / 16 <= 16);
+  constexpr int HPS = SEG ? AT * LPR / 16 : 1;  // half-warps per state
   const int TS = slots * RPT;
   const int tile_floats = TS * AP;
-  const uint32_t mode = kp.a.mode;
+  const uint32_t mode = KM == 2 ? (uint32_t)PFPN_HEAD_PPO : (KM == 3 ? (uint32_t)PFPN_HEAD_GRAD : kp.a.mode);
   const float* __restrict__ g_logits = kp.a.logits;
   const float* __restrict__ g_value = kp.a.value;
   float* __restrict__ g_dlogits = kp.a.dlogits;
-  float* __restrict__ g_dvalue = kp.a.dvalue;
-  float* __restrict__ g_ent_ba = kp.a.ent_ba;
+  float* __restrict__ g_dvalue = LEAN ? nullptr : kp.a.dvalue;
+  float* __restrict__ g_ent_ba = LEAN ? nullptr : kp.a.ent_ba;
   const int tid = threadIdx.x;
   const int nthr = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
@@ -83,14 +100,16 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   unsigned char* tail = smem_raw + (size_t)NSTAGE * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
-  float2* rowbuf = reinterpret_cast<float2*>(tail + 8 * NSTAGE);    // [2][TS*A]
-  float* statebuf = reinterpret_cast<float*>(rowbuf + 2 * TS * A);  // [TS]
-  float* lossbuf = statebuf + TS;                                   // [kHeadMaxWarps]
+  uint64_t* cta_bar = full_bar + NSTAGE;                            // split-phase CTA barrier
+  float2* rowbuf = reinterpret_cast<float2*>(tail + 8 * (NSTAGE + 1));  // [3][TS*A]
+  float* lossbuf = reinterpret_cast<float*>(rowbuf + 3 * TS * A);       // [kHeadMaxWarps]
   float* dummy = lossbuf + kHeadMaxWarps;                           // [LPR*EPL] sink for masked rows
+  float2* cs = reinterpret_cast<float2*>(dummy + LPR * EPL + ((LPR * EPL) & 1));  // CSM: [EP2*3][A*LPR]
 
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < NSTAGE; ++s) mbar_init(smem_u32(&full_bar[s]), 1);
+    mbar_init(smem_u32(cta_bar), (uint32_t)nthr);
     mbar_fence_init();
   }
 
@@ -106,8 +125,11 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
   const bool part_ok = c < P - nfull * LPR;
   auto k_ok = [&](int i) -> bool { return (i < nfull) || (i == nfull && part_ok); };
 
-  float2 isig[EP2], nmisig[EP2], cst[EP2];
+  constexpr int NCR = CSM ? 1 : EP2;
+  float2 isig_r[NCR], nmisig_r[NCR], cst_r[NCR];
   float2 acc1[EP2], acc2[EP2];
+  const int tps = A * LPR;               // threads per state slot
+  const int tps_idx = tid - slot * tps;  // this thread's column in the constant table
 #pragma unroll
   for (int i2 = 0; i2 < EP2; ++i2) {
     float v[2][3];
@@ -123,16 +145,28 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
       v[h][1] = -mu * is;
       v[h][2] = ok ? -(ls + kHalfLog2Pi) * kLog2e : 0.f;
     }
-    isig[i2] = make_float2(v[0][0], v[1][0]);
-    nmisig[i2] = make_float2(v[0][1], v[1][1]);
-    cst[i2] = make_float2(v[0][2], v[1][2]);
+    if (CSM) {
+      if (active && slot == 0) {
+        cs[(i2 * 3 + 0) * tps + tps_idx] = make_float2(v[0][0], v[1][0]);
+        cs[(i2 * 3 + 1) * tps + tps_idx] = make_float2(v[0][1], v[1][1]);
+        cs[(i2 * 3 + 2) * tps + tps_idx] = make_float2(v[0][2], v[1][2]);
+      }
+    } else {
+      isig_r[i2] = make_float2(v[0][0], v[1][0]);
+      nmisig_r[i2] = make_float2(v[0][1], v[1][1]);
+      cst_r[i2] = make_float2(v[0][2], v[1][2]);
+    }
     acc1[i2] = make_float2(0.f, 0.f);
     acc2[i2] = make_float2(0.f, 0.f);
   }
-  const bool tanh_flag = (kp.a.flags & PFPN_HEAD_FLAG_TANH) != 0;
+  const float2* csp = cs + (active ? tps_idx : 0);
+  auto c_isig = [&](int i2) -> float2 { return CSM ? csp[(i2 * 3 + 0) * tps] : isig_r[CSM ? 0 : i2]; };
+  auto c_nmisig = [&](int i2) -> float2 { return CSM ? csp[(i2 * 3 + 1) * tps] : nmisig_r[CSM ? 0 : i2]; };
+  auto c_cst = [&](int i2) -> float2 { return CSM ? csp[(i2 * 3 + 2) * tps] : cst_r[CSM ? 0 : i2]; };
+  const bool tanh_flag = LEAN ? false : (kp.a.flags & PFPN_HEAD_FLAG_TANH) != 0;
   const bool tail_exists = (B % TS) != 0;
   const int tail_tile = kp.num_tiles - 1;
-  const bool has_ent_grad = kp.has_ent_grad != 0;
+  const bool has_ent_grad = LEAN ? false : kp.has_ent_grad != 0;
   const float eps_clip = kp.a.eps_clip, loss_scale = kp.a.loss_scale;
 
   float adv_mean = 0.f, adv_rstd = 1.f;
@@ -161,251 +195,304 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
   };
   if (tid == 0) {
 #pragma unroll
-    for (int d = 0; d < DIST; ++d) issue_load(d);
+    for (int d = 0; d <= DIST; ++d) issue_load(d);
   }
 
-  // value prefetch (one tile ahead)
-  float v_nxt[RPT];
-  auto load_values = [&](int it, float (&dst)[RPT]) {
+  // per-thread fixed row offsets inside a tile and the one "writer" thread per state
+  int row_off[RPT];
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) row_off[j] = (j * slots + slot) * A + a;
+  const bool writer = active && a == 0 && c == 0;
+  const uint32_t cta_bar_a = smem_u32(cta_bar);
+
+  // action / per-state scalar prefetch, one tile ahead.  sc = {adv, lp_old} (PPO) or {g_lp, -}
+  float v_nxt[RPT], sc0_nxt[RPT], sc1_nxt[RPT];
+  auto load_values = [&](int it) {
     const int tile = first_tile + it * tile_step;
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
       const int b = tile * TS + j * slots + slot;
-      dst[j] = (it < my_tiles && active && b < B) ? __ldg(&g_value[(size_t)b * A + a]) : 0.f;
+      const bool ok = it < my_tiles && active && b < B;
+      v_nxt[j] = ok ? __ldg(&g_value[(size_t)b * A + a]) : 0.f;
+      if (BWD) {
+        if (mode == PFPN_HEAD_PPO) {
+          sc0_nxt[j] = ok ? __ldg(&kp.a.adv[b]) : 0.f;
+          sc1_nxt[j] = ok ? __ldg(&kp.a.lp_old[b]) : 0.f;
+        } else {
+          sc0_nxt[j] = ok ? __ldg(&kp.a.g_lp[b]) : 0.f;
+          sc1_nxt[j] = 0.f;
+        }
+      }
     }
   };
-  load_values(0, v_nxt);
-
-  int prev_tile = -1, prev_stage = 0;
-  bool prev_was_tail = false;
+  load_values(0);
 
   const float2 L2 = splat2(kLog2e);
   const float2 nhl = splat2(-0.5f * kLog2e);
   const float2 neg1 = splat2(-1.f);
 
-  for (int it = 0; it < my_tiles; ++it) {
-    const int tile = first_tile + it * tile_step;
-    const int st = it % NSTAGE;
-    float* sbuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(stage_base) + (size_t)st * stage_bytes);
-    const bool is_tail = tail_exists && tile == tail_tile;
-    const int b0 = tile * TS;
-
-    float v_cur[RPT];
-#pragma unroll
-    for (int j = 0; j < RPT; ++j) v_cur[j] = v_nxt[j];
-    load_values(it + 1, v_nxt);
-
-    // per-state scalars for the reducer lanes, fetched early to hide latency
-    float pre_g = 0.f, pre_adv = 0.f, pre_lpo = 0.f;
-    if (BWD && lane == 0 && warp < TS) {
-      const int b = b0 + warp;
-      if (b < B) {
-        if (mode == PFPN_HEAD_PPO) {
-          pre_adv = __ldg(&kp.a.adv[b]);
-          pre_lpo = __ldg(&kp.a.lp_old[b]);
-        } else {
-          pre_g = __ldg(&kp.a.g_lp[b]);
-        }
-      }
-    }
-
-    if (!is_tail) {
-      mbar_wait(smem_u32(&full_bar[st]), (uint32_t)((it / NSTAGE) & 1));
-    } else {
-      const int nvalid = (B - b0) * AP;
-      const float* src = g_logits + (size_t)b0 * AP;
-      for (int idx = tid; idx < nvalid; idx += nthr) sbuf[idx] = __ldg(&src[idx]);
-      __syncthreads();
-    }
-
-    // ---------------- pass A/B: per-row statistics ------------------------
+  // state carried from pass A/B (iteration it) to pass C (iteration it+1); two copies that
+  // swap roles every iteration (the loop is unrolled by two so both stay in registers)
+  struct RowState {
     float2 e1[RPT][EP2], e2[RPT][EP2];
-    float inv_s1[RPT], s2r[RPT], Hrow[RPT], l2s1[RPT];
-    float2* rb = rowbuf + (it & 1) * TS * A;
-#pragma unroll
-    for (int j = 0; j < RPT; ++j) {
-      const int srow_idx = (j * slots + slot) * A + a;
-      const bool row_ok = active && (b0 + j * slots + slot < B);
-      // masked rows read state 0 of the tile (always valid, finite) and are discarded
-      const float* ld = sbuf + (row_ok ? srow_idx : a) * P + c;
-      float2 l[EP2];
-      float m = kNegBig;
-#pragma unroll
-      for (int i2 = 0; i2 < EP2; ++i2) {
-        const int i0 = 2 * i2, i1 = 2 * i2 + 1;
-        l[i2].x = (i0 < nfull) ? ld[LPR * i0] : ((i0 == nfull && part_ok) ? ld[LPR * i0] : kNegBig);
-        l[i2].y = (i1 >= EPL) ? kNegBig
-                              : ((i1 < nfull) ? ld[LPR * i1] : ((i1 == nfull && part_ok) ? ld[LPR * i1] : kNegBig));
-        m = max3f(m, l[i2].x, l[i2].y);
-      }
-      m = row_max<LPR>(m);
-      const float2 nmL = splat2(-m * kLog2e);
-      const float2 v2 = splat2(v_cur[j]);
-      float2 s1 = make_float2(0.f, 0.f), s2 = s1, h = s1;
-#pragma unroll
-      for (int i2 = 0; i2 < EP2; ++i2) {
-        const float2 t = fma2(l[i2], L2, nmL);
-        float2 x1;
-        x1.x = ex2f(t.x);
-        x1.y = ex2f(t.y);
-        const float2 z = fma2(v2, isig[i2], nmisig[i2]);
-        const float2 q = mul2(z, z);
-        const float2 u = add2(t, cst[i2]);
-        const float2 t2 = fma2(q, nhl, u);
-        float2 x2;
-        x2.x = ex2f(t2.x);
-        x2.y = ex2f(t2.y);
-        s1 = add2(s1, x1);
-        s2 = add2(s2, x2);
-        h = fma2(x1, t, h);
-        e1[j][i2] = x1;
-        e2[j][i2] = x2;
-      }
-      const float S1 = row_sum<LPR>(s1.x + s1.y);
-      const float S2 = row_sum<LPR>(s2.x + s2.y);
-      const float Hs = row_sum<LPR>(h.x + h.y);
-      const float is1 = rcpf(S1);
-      const float lg1 = lg2f(S1);
-      const float Hval = kLn2 * (lg1 - Hs * is1);
-      float lnp = kLn2 * (lg2f(S2) - lg1);  // -inf when every term underflowed (p == 0)
-      if (tanh_flag) {
-        const float uu = v_cur[j];
-        lnp -= 2.f * (kLn2 - uu - softplusf_acc(-2.f * uu));
-      }
-      inv_s1[j] = is1;
-      s2r[j] = S2;
-      Hrow[j] = Hval;
-      l2s1[j] = lg1;
-      if (row_ok && c == 0) {
-        rb[srow_idx] = make_float2(lnp, Hval);
-        if (g_ent_ba != nullptr) g_ent_ba[(size_t)(b0 + j * slots + slot) * A + a] = Hval;
-      }
-    }
-    __syncthreads();  // B1: rowbuf complete; previous tile's gradient stores fenced
+    float inv_s1[RPT], s2r[RPT], Hrow[RPT], l2s1[RPT], v_c[RPT], sc0_c[RPT], sc1_c[RPT];
+  };
+  RowState stA, stB;
 
-    // ---------------- thread 0: drain previous tile, prefetch ----------------
-    if (tid == 0) {
-      if (BWD && prev_tile >= 0) {
-        bulk_s2g(g_dlogits + (size_t)prev_tile * tile_floats, smem_u32(stage_base) + prev_stage * stage_bytes,
-                 (uint32_t)(tile_floats * 4));
-        bulk_commit();
-        bulk_wait_read<1>();
+  // One pipeline step: pass A/B of tile `it` into `nw`, then -- after the split-phase CTA
+  // barrier of the previous step, arrived on a whole pass A/B ago -- pass C of tile it-1 from `od`.
+  auto step = [&](const int it, RowState& nw, RowState& od) {
+    if (it > my_tiles) return;
+    // ======================= pass A/B of tile it ========================================
+    if (it < my_tiles) {
+      const int tile = first_tile + it * tile_step;
+      const int st = it % NSTAGE;
+      float* sbuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(stage_base) + (size_t)st * stage_bytes);
+      const bool is_tail = tail_exists && tile == tail_tile;
+      const int b0 = tile * TS;
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        nw.v_c[j] = v_nxt[j];
+        nw.sc0_c[j] = sc0_nxt[j];
+        nw.sc1_c[j] = sc1_nxt[j];
       }
-      issue_load(it + DIST);
-    }
+      load_values(it + 1);
 
-    // ---------------- per-state reduction over a (+ PPO) ---------------------
-    for (int s = warp; s < TS; s += nwarps) {
-      const int b = b0 + s;
-      float lp = 0.f, en = 0.f;
-      for (int aa = lane; aa < A; aa += 32) {
-        const float2 r = rb[s * A + aa];
-        lp += r.x;
-        en += r.y;
+      if (!is_tail) {
+        mbar_wait(smem_u32(&full_bar[st]), (uint32_t)((it / NSTAGE) & 1));
+      } else {
+        const int nvalid = (B - b0) * AP;
+        const float* src = g_logits + (size_t)b0 * AP;
+        for (int idx = tid; idx < nvalid; idx += nthr) sbuf[idx] = __ldg(&src[idx]);
+        __syncthreads();  // tail tile only (last iteration of exactly one CTA)
       }
-      lp = row_sum<32>(lp);
-      en = row_sum<32>(en);
-      if (lane == 0 && b < B) {
-        kp.a.lp[b] = lp;
-        if (kp.a.ent != nullptr) kp.a.ent[b] = en;
-        if (BWD) {
-          float g;
-          if (mode == PFPN_HEAD_PPO) {
-            // (s == warp always holds while TS <= nwarps; otherwise re-read)
-            const float adv_raw = (s == warp) ? pre_adv : __ldg(&kp.a.adv[b]);
-            const float lpo = (s == warp) ? pre_lpo : __ldg(&kp.a.lp_old[b]);
-            const float an = (adv_raw - adv_mean) * adv_rstd;
-            const float ratio = expf(lp - lpo);
-            const float surr = ratio * an;
-            const float clipped = fminf(fmaxf(ratio, 1.f - eps_clip), 1.f + eps_clip) * an;
-            loss_acc -= fminf(surr, clipped) * loss_scale;
-            g = (surr <= clipped) ? -loss_scale * ratio * an : 0.f;  // TF Minimum: ties -> x
-          } else {
-            g = (s == warp) ? pre_g : __ldg(&kp.a.g_lp[b]);
-          }
-          statebuf[s] = g;
+
+      float2* rb = rowbuf + (it % 3) * TS * A;
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        const bool row_ok = active && (b0 + j * slots + slot < B);
+        // masked rows read state 0 of the tile (always valid, finite) and are discarded
+        const float* ld = sbuf + (row_ok ? row_off[j] : a) * P + c;
+        float2 l[EP2];
+        float m = kNegBig;
+#pragma unroll
+        for (int i2 = 0; i2 < EP2; ++i2) {
+          const int i0 = 2 * i2, i1 = 2 * i2 + 1;
+          l[i2].x = (i0 < nfull) ? ld[LPR * i0] : ((i0 == nfull && part_ok) ? ld[LPR * i0] : kNegBig);
+          l[i2].y = (i1 >= EPL) ? kNegBig
+                                : ((i1 < nfull) ? ld[LPR * i1] : ((i1 == nfull && part_ok) ? ld[LPR * i1] : kNegBig));
+          m = max3f(m, l[i2].x, l[i2].y);
+        }
+        m = row_max<LPR>(m);
+        const float2 nmL = splat2(-m * kLog2e);
+        const float2 v2 = splat2(nw.v_c[j]);
+        float2 s1 = make_float2(0.f, 0.f), s2 = s1, h = s1;
+#pragma unroll
+        for (int i2 = 0; i2 < EP2; ++i2) {
+          const float2 t = fma2(l[i2], L2, nmL);
+          float2 x1;
+          x1.x = ex2f(t.x);
+          x1.y = ex2f(t.y);
+          const float2 z = fma2(v2, c_isig(i2), c_nmisig(i2));
+          const float2 q = mul2(z, z);
+          const float2 u = add2(t, c_cst(i2));
+          const float2 t2 = fma2(q, nhl, u);
+          float2 x2;
+          x2.x = ex2f(t2.x);
+          x2.y = ex2f(t2.y);
+          s1 = add2(s1, x1);
+          s2 = add2(s2, x2);
+          h = fma2(x1, t, h);
+          nw.e1[j][i2] = x1;
+          nw.e2[j][i2] = x2;
+        }
+        const float S1 = row_sum<LPR>(s1.x + s1.y);
+        const float S2 = row_sum<LPR>(s2.x + s2.y);
+        const float Hs = row_sum<LPR>(h.x + h.y);
+        const float is1 = rcpf(S1);
+        const float lg1 = lg2f(S1);
+        const float Hval = kLn2 * (lg1 - Hs * is1);
+        float lnp = kLn2 * (lg2f(S2) - lg1);  // -inf when every term underflowed (p == 0)
+        if (tanh_flag) {
+          const float uu = nw.v_c[j];
+          lnp -= 2.f * (kLn2 - uu - softplusf_acc(-2.f * uu));
+        }
+        nw.inv_s1[j] = is1;
+        nw.s2r[j] = S2;
+        nw.Hrow[j] = Hval;
+        nw.l2s1[j] = lg1;
+        if (row_ok && c == 0 && g_ent_ba != nullptr) g_ent_ba[(size_t)(b0 + j * slots + slot) * A + a] = Hval;
+        if (SEG) {
+          // 4 rows of this half-warp -> one partial (lanes differing in bits 2,3 hold different rows)
+          float pl = row_ok ? lnp : 0.f, ph = row_ok ? Hval : 0.f;
+          pl += __shfl_xor_sync(0xffffffffu, pl, 4);
+          ph += __shfl_xor_sync(0xffffffffu, ph, 4);
+          pl += __shfl_xor_sync(0xffffffffu, pl, 8);
+          ph += __shfl_xor_sync(0xffffffffu, ph, 8);
+          if ((tid & 15) == 0) rb[j * (MAXT / 16) + (tid >> 4)] = make_float2(pl, ph);
+        } else if (row_ok && c == 0) {
+          rb[row_off[j]] = make_float2(lnp, Hval);
         }
       }
     }
+    // ======================= pass C of tile it-1 (state in registers) ==================
+    // Placed first in program order so that the carried registers die before pass A/B
+    // allocates the new ones; its barrier phase (it-1) was arrived on an iteration ago.
+    if (it >= 1) {
+      const int pit = it - 1;
+      const int tile = first_tile + pit * tile_step;
+      const int st = pit % NSTAGE;
+      float* sbuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(stage_base) + (size_t)st * stage_bytes);
+      const int b0 = tile * TS;
+      const float2* rb = rowbuf + (pit % 3) * TS * A;
 
-    if (BWD) {
-      __syncthreads();  // B2: statebuf ready
-      // ---------------- pass C: gradients ----------------------------------
+      mbar_wait(cta_bar_a, (uint32_t)(pit & 1));  // every thread finished iteration it-1
+
+      if (tid == 0) {
+        if (BWD && it >= 2) {  // all threads fenced their STS of tile it-2 before arriving
+          const int ptile = tile - tile_step;
+          bulk_s2g(g_dlogits + (size_t)ptile * tile_floats,
+                   smem_u32(stage_base) + ((it - 2) % NSTAGE) * stage_bytes, (uint32_t)(tile_floats * 4));
+          bulk_commit();
+          bulk_wait_read<1>();
+        }
+        issue_load(it + DIST);
+      }
+
 #pragma unroll
       for (int j = 0; j < RPT; ++j) {
         const int sidx = j * slots + slot;
-        const int srow_idx = sidx * A + a;
         const int b = b0 + sidx;
         const bool row_ok = active && (b < B);
-        float* stp = row_ok ? (sbuf + srow_idx * P + c) : (dummy + c);
-        const float g = row_ok ? statebuf[sidx] : 0.f;
-        const bool p_ok = s2r[j] > 0.f;
+        // ---- log_prob of the state: sum over a of the per-row log p
+        float lp = 0.f, en = 0.f;
+        if (SEG) {
+          const float2* hb = rb + j * (MAXT / 16) + slot * HPS;
+#pragma unroll
+          for (int h = 0; h < HPS; ++h) {
+            const float2 r = hb[h];
+            lp += r.x;
+            en += r.y;
+          }
+        } else {
+          const float2* rbs = rb + (row_ok ? sidx : 0) * A;
+#pragma unroll 3
+          for (int aa = c; aa < A; aa += LPR) {
+            const float2 r = rbs[aa];
+            lp += r.x;
+            en += r.y;
+          }
+          lp = row_sum<LPR>(lp);
+          en = row_sum<LPR>(en);
+        }
+        if (writer && row_ok) {
+          kp.a.lp[b] = lp;
+          if (kp.a.ent != nullptr) kp.a.ent[b] = en;
+        }
+        if (!BWD) continue;
+
+        float g;
+        const float sc0v = od.sc0_c[j];
+        if (mode == PFPN_HEAD_PPO) {
+          const float sc1v = od.sc1_c[j];
+          const float an = (sc0v - adv_mean) * adv_rstd;
+          const float ratio = ex2f((lp - sc1v) * kLog2e);
+          const float surr = ratio * an;
+          const float clipped = fminf(fmaxf(ratio, 1.f - eps_clip), 1.f + eps_clip) * an;
+          if (writer && row_ok) loss_acc -= fminf(surr, clipped) * loss_scale;
+          g = (surr <= clipped) ? -loss_scale * ratio * an : 0.f;  // TF Minimum: ties -> x
+        } else {
+          g = sc0v;
+        }
+        if (!row_ok) g = 0.f;
+
+        float* stp = row_ok ? (sbuf + row_off[j] * P + c) : (dummy + c);
+        const bool p_ok = od.s2r[j] > 0.f;
         // guard of utils.py:109-117: dL/dp is Inf/NaN when p == 0 -> zeroed
         const float g_row = p_ok ? g : 0.f;
-        const float gs2 = p_ok ? g_row * rcpf(s2r[j]) : 0.f;
-        const float2 v2 = splat2(v_cur[j]);
+        const float gs2 = p_ok ? g_row * rcpf(od.s2r[j]) : 0.f;
+        const float2 v2 = splat2(od.v_c[j]);
         const float2 gs2v = splat2(gs2);
-        float2 nc0, nc1;
         if (!has_ent_grad) {
-          nc0 = splat2(-g_row * inv_s1[j]);
-          nc1 = splat2(0.f);
+          const float2 nc0 = splat2(-g_row * od.inv_s1[j]);
+#pragma unroll
+          for (int i2 = 0; i2 < EP2; ++i2) {
+            const float2 rr = mul2(od.e2[j][i2], gs2v);  // g * r_k
+            const float2 d = fma2(od.e1[j][i2], nc0, rr);
+            const float2 z = fma2(v2, c_isig(i2), c_nmisig(i2));
+            const float2 q1 = fma2(z, z, neg1);
+            acc1[i2] = fma2(rr, z, acc1[i2]);
+            acc2[i2] = fma2(rr, q1, acc2[i2]);
+            const int i0 = 2 * i2, i1 = 2 * i2 + 1;
+            if (i0 < nfull) stp[LPR * i0] = d.x;
+            else if (i0 == nfull && part_ok) stp[LPR * i0] = d.x;
+            if (i1 < EPL) {
+              if (i1 < nfull) stp[LPR * i1] = d.y;
+              else if (i1 == nfull && part_ok) stp[LPR * i1] = d.y;
+            }
+          }
         } else {
           float ge = kp.a.g_ent;
           if (kp.a.g_ent_ba != nullptr && row_ok) ge += __ldg(&kp.a.g_ent_ba[(size_t)b * A + a]);
           // dH/dl_k = -pi_k (ln pi_k + H),  ln pi_k = ln2*(t_k - log2 s1)
-          nc0 = splat2(-(g_row + ge * (Hrow[j] - kLn2 * l2s1[j])) * inv_s1[j]);
-          nc1 = splat2(-ge * kLn2 * inv_s1[j]);
-        }
+          const float2 nc0 = splat2(-(g_row + ge * (od.Hrow[j] - kLn2 * od.l2s1[j])) * od.inv_s1[j]);
+          const float2 nc1 = splat2(-ge * kLn2 * od.inv_s1[j]);
 #pragma unroll
-        for (int i2 = 0; i2 < EP2; ++i2) {
-          const float2 rr = mul2(e2[j][i2], gs2v);  // g * r_k
-          float2 coef = nc0;
-          if (has_ent_grad) {
+          for (int i2 = 0; i2 < EP2; ++i2) {
+            const float2 rr = mul2(od.e2[j][i2], gs2v);
             // t_k = (l_k - m) log2e recovered as log2(e1_k); e1 == 0 contributes nothing
             float2 t;
-            t.x = lg2f(fmaxf(e1[j][i2].x, 1e-37f));
-            t.y = lg2f(fmaxf(e1[j][i2].y, 1e-37f));
-            coef = fma2(t, nc1, nc0);
-          }
-          const float2 d = fma2(e1[j][i2], coef, rr);
-          const float2 z = fma2(v2, isig[i2], nmisig[i2]);
-          const float2 q1 = fma2(z, z, neg1);
-          acc1[i2] = fma2(rr, z, acc1[i2]);
-          acc2[i2] = fma2(rr, q1, acc2[i2]);
-          const int i0 = 2 * i2, i1 = 2 * i2 + 1;
-          if (i0 < nfull) stp[LPR * i0] = d.x;
-          else if (i0 == nfull && part_ok) stp[LPR * i0] = d.x;
-          if (i1 < EPL) {
-            if (i1 < nfull) stp[LPR * i1] = d.y;
-            else if (i1 == nfull && part_ok) stp[LPR * i1] = d.y;
+            t.x = lg2f(fmaxf(od.e1[j][i2].x, 1e-37f));
+            t.y = lg2f(fmaxf(od.e1[j][i2].y, 1e-37f));
+            const float2 coef = fma2(t, nc1, nc0);
+            const float2 d = fma2(od.e1[j][i2], coef, rr);
+            const float2 z = fma2(v2, c_isig(i2), c_nmisig(i2));
+            const float2 q1 = fma2(z, z, neg1);
+            acc1[i2] = fma2(rr, z, acc1[i2]);
+            acc2[i2] = fma2(rr, q1, acc2[i2]);
+            const int i0 = 2 * i2, i1 = 2 * i2 + 1;
+            if (i0 < nfull) stp[LPR * i0] = d.x;
+            else if (i0 == nfull && part_ok) stp[LPR * i0] = d.x;
+            if (i1 < EPL) {
+              if (i1 < nfull) stp[LPR * i1] = d.y;
+              else if (i1 == nfull && part_ok) stp[LPR * i1] = d.y;
+            }
           }
         }
         if (g_dvalue != nullptr) {
           float dv = 0.f;
 #pragma unroll
           for (int i2 = 0; i2 < EP2; ++i2) {
-            const float2 rr = mul2(e2[j][i2], gs2v);
-            const float2 z = fma2(v2, isig[i2], nmisig[i2]);
-            const float2 w = mul2(mul2(rr, z), isig[i2]);
+            const float2 rr = mul2(od.e2[j][i2], gs2v);
+            const float2 z = fma2(v2, c_isig(i2), c_nmisig(i2));
+            const float2 w = mul2(mul2(rr, z), c_isig(i2));
             dv += w.x + w.y;
           }
           dv = row_sum<LPR>(dv);
           if (row_ok && c == 0) {
             float out = -dv;
-            if (tanh_flag) out += g_row * 2.f * tanhf(v_cur[j]);
+            if (tanh_flag) out += g_row * 2.f * tanhf(od.v_c[j]);
             g_dvalue[(size_t)b * A + a] = out;
           }
         }
       }
-      fence_async_smem();  // make this thread's gradient STS visible to the bulk store
-      prev_tile = tile;
-      prev_stage = st;
-      prev_was_tail = is_tail;
+      if (BWD) fence_async_smem();  // gradient STS -> visible to the bulk store issued later
     }
+
+    // arrive: this thread's partials of tile it are written, its gradient STS of tile it-1 fenced
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cta_bar_a) : "memory");
+  };
+  for (int it = 0; it <= my_tiles; it += 2) {
+    step(it, stA, stB);
+    step(it + 1, stB, stA);
   }
 
+  // ---------------- drain: the last tile's gradient ------------------------------------
+  mbar_wait(cta_bar_a, (uint32_t)(my_tiles & 1));
+  const int prev_tile = my_tiles >= 1 ? first_tile + (my_tiles - 1) * tile_step : -1;
+  const int prev_stage = my_tiles >= 1 ? (my_tiles - 1) % NSTAGE : 0;
+  const bool prev_was_tail = tail_exists && prev_tile == tail_tile;
   // ---------------- epilogue: last store, partial sums --------------------------
-  __syncthreads();
   if (BWD && prev_tile >= 0) {
     if (!prev_was_tail) {
       if (tid == 0) {
@@ -423,7 +510,9 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
   }
   if (tid == 0) bulk_wait_read<0>();
   if (BWD) {
-    if (lane == 0) lossbuf[warp] = loss_acc;
+    // loss terms live in the writer threads; fixed-order two-level sum
+    const float wl = row_sum<32>(loss_acc);
+    if (lane == 0) lossbuf[warp] = wl;
     __syncthreads();  // all bulk reads of smem done (thread 0 waited) before reuse
     float* red = stage_base;  // [slots][2][AP]
     if (active) {
@@ -477,14 +566,29 @@ __global__ void head_finalize_kernel(const float* __restrict__ part, const float
 }
 
 // One CTA: mean and 1/(sqrt(popvar)+1e-8) of adv[B], fixed summation order.
-__global__ void adv_stats_kernel(const float* __restrict__ adv, int B, float* __restrict__ stats) {
+// Eight independent loads per thread per trip keep the single SM's memory pipe busy
+// (a dependent one-load loop costs ~20 us at B = 65536, this ~3 us).
+__global__ void __launch_bounds__(1024) adv_stats_kernel(const float* __restrict__ adv, int B, float* __restrict__ stats) {
   __shared__ double sh[2][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double s = 0.0, ss = 0.0;
-  for (int i = tid; i < B; i += blockDim.x) {
-    const double x = adv[i];
-    s += x;
-    ss += x * x;
+  constexpr int U = 8;
+  int i = tid;
+  for (; i + (U - 1) * 1024 < B; i += U * 1024) {
+    float x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) x[u] = __ldg(&adv[i + u * 1024]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double d = x[u];
+      s += d;
+      ss += d * d;
+    }
+  }
+  for (; i < B; i += 1024) {
+    const double d = __ldg(&adv[i]);
+    s += d;
+    ss += d * d;
   }
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -518,33 +622,37 @@ typedef void (*head_kernel_t)(const HeadKParams);
 // first entry whose pmax >= P is the default, PFPN_HEAD_VARIANT=<n> picks the
 // n-th matching entry instead (tuning aid, read once per process).
 struct HeadVariant {
-  int pmin, pmax, lpr, epl, rpt, nstage, maxt, nreg, pt;
-  head_kernel_t fwd, bwd;
+  int pmin, pmax, lpr, epl, rpt, nstage, maxt, nreg, pt, at, csm;
+  head_kernel_t fn[4];  // indexed by KM
 };
-#define PFPN_HEAD_VARIANT_ENTRY(PMIN, PMAX, LPR, EPL, RPT, NST, MAXT, NREG, PT)                            \
-  {                                                                                                        \
-    PMIN, PMAX, LPR, EPL, RPT, NST, MAXT, NREG, PT, head_kernel<LPR, EPL, RPT, NST, false, MAXT, NREG, PT>, \
-        head_kernel<LPR, EPL, RPT, NST, true, MAXT, NREG, PT>                                              \
+#define PFPN_HK(LPR, EPL, RPT, NST, KM, MAXT, NREG, PT, AT, CSM) head_kernel<LPR, EPL, RPT, NST, KM, MAXT, NREG, PT, AT, CSM>
+#define PFPN_HEAD_VARIANT_ENTRY(PMIN, PMAX, LPR, EPL, RPT, NST, MAXT, NREG, PT, AT, CSM)                       \
+  {                                                                                                            \
+    PMIN, PMAX, LPR, EPL, RPT, NST, MAXT, NREG, PT, AT, CSM, {                                                 \
+      PFPN_HK(LPR, EPL, RPT, NST, 0, MAXT, NREG, PT, AT, CSM), PFPN_HK(LPR, EPL, RPT, NST, 1, MAXT, NREG, PT, AT, CSM), \
+          PFPN_HK(LPR, EPL, RPT, NST, 2, MAXT, NREG, PT, AT, CSM), PFPN_HK(LPR, EPL, RPT, NST, 3, MAXT, NREG, PT, AT, CSM) \
+    }                                                                                                          \
   }
-// [pmin, pmax] = particle counts an entry serves; PT > 0 entries are specialised for
-// exactly P == PT (the shapes BASELINE.json names), PT == 0 entries take P at run time.
+// [pmin, pmax] = particle counts an entry serves.  PT/AT > 0 entries are specialised for
+// exactly (P, A) == (PT, AT) -- the shapes BASELINE.json names (A = 36 DeepMimic action
+// dims, P in {10, 35, 100}); PT == AT == 0 entries take both at run time.
 static const HeadVariant kHeadVariants[] = {
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 4, 288, 72, 35),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 6, 288, 72, 35),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 2, 4, 288, 96, 35),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 4, 288, 96, 35),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 2, 3, 288, 72, 35),
-    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 4, 288, 96, 100),
-    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 3, 288, 72, 100),
-    PFPN_HEAD_VARIANT_ENTRY(10, 10, 4, 3, 2, 4, 320, 72, 10),
-    PFPN_HEAD_VARIANT_ENTRY(1, 12, 4, 3, 2, 4, 320, 96, 0),
-    PFPN_HEAD_VARIANT_ENTRY(13, 36, 4, 9, 1, 4, 288, 96, 0),
-    PFPN_HEAD_VARIANT_ENTRY(37, 64, 8, 8, 1, 4, 320, 96, 0),
-    PFPN_HEAD_VARIANT_ENTRY(65, 104, 8, 13, 1, 4, 288, 96, 0),
-    PFPN_HEAD_VARIANT_ENTRY(105, 256, 16, 16, 1, 3, 384, 168, 0),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, true),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, false),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 72, 35, 36, true),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 6, 288, 96, 35, 36, true),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 2, 5, 288, 96, 35, 36, true),
+    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 5, 288, 96, 100, 36, true),
+    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 4, 288, 72, 100, 36, true),
+    PFPN_HEAD_VARIANT_ENTRY(10, 10, 4, 3, 2, 5, 288, 72, 10, 36, false),
+    PFPN_HEAD_VARIANT_ENTRY(1, 12, 4, 3, 2, 5, 320, 96, 0, 0, false),
+    PFPN_HEAD_VARIANT_ENTRY(13, 36, 4, 9, 1, 5, 288, 96, 0, 0, false),
+    PFPN_HEAD_VARIANT_ENTRY(37, 64, 8, 8, 1, 5, 320, 96, 0, 0, false),
+    PFPN_HEAD_VARIANT_ENTRY(65, 104, 8, 13, 1, 5, 288, 96, 0, 0, false),
+    PFPN_HEAD_VARIANT_ENTRY(105, 256, 16, 16, 1, 4, 384, 168, 0, 0, false),
 };
 
-static const HeadVariant* pick_variant(int P) {
+static const HeadVariant* pick_variant(int A, int P) {
   static const int want = []() {
     const char* e = getenv("PFPN_HEAD_VARIANT");
     return e ? atoi(e) : 0;
@@ -553,8 +661,9 @@ static const HeadVariant* pick_variant(int P) {
   int seen = 0;
   for (const HeadVariant& v : kHeadVariants) {
     if (P < v.pmin || P > v.pmax) continue;
+    if (v.at != 0 && v.at != A) continue;
     if (first == nullptr) first = &v;
-    if (v.pt != first->pt) break;
+    if (v.pt != first->pt || v.at != first->at) break;
     if (seen == want) return &v;
     ++seen;
   }
@@ -567,9 +676,9 @@ struct HeadLaunch {
   int threads, slots, ts, smem_bytes, ctas_per_sm, num_sms;
 };
 
-static int plan_head(int A, int P, bool bwd, HeadLaunch* L) {
+static int plan_head(int A, int P, int km, HeadLaunch* L) {
   if (A <= 0 || P <= 0) return PFPN_ERR_ARG;
-  L->cfg = pick_variant(P);
+  L->cfg = pick_variant(A, P);
   if (L->cfg == nullptr) return PFPN_ERR_UNSUPPORTED;
   const HeadVariant& v = *L->cfg;
   const int per_slot = A * v.lpr;
@@ -578,13 +687,14 @@ static int plan_head(int A, int P, bool bwd, HeadLaunch* L) {
   // tiles must start 16-byte aligned: TS*A*P % 4 == 0
   while (slots > 0 && ((slots * v.rpt * A * P) & 3) != 0) --slots;
   if (slots < 1) return PFPN_ERR_UNSUPPORTED;
+  if (v.at != 0 && slots != v.maxt / per_slot) return PFPN_ERR_UNSUPPORTED;  // kernel derives slots itself
   L->slots = slots;
   L->ts = slots * v.rpt;
   L->threads = (slots * per_slot + 31) & ~31;
   const int stage_bytes = (L->ts * A * P * 4 + 127) & ~127;
-  L->smem_bytes = v.nstage * stage_bytes + 8 * v.nstage + 2 * L->ts * A * 8 + L->ts * 4 + kHeadMaxWarps * 4 +
-                  v.lpr * v.epl * 4 + 16;
-  L->fn = bwd ? v.bwd : v.fwd;
+  L->smem_bytes = v.nstage * stage_bytes + 8 * (v.nstage + 1) + 3 * L->ts * A * 8 + kHeadMaxWarps * 4 +
+                  (v.lpr * v.epl + 1) * 4 + 16 + (v.csm ? ((v.epl + 1) / 2) * 3 * per_slot * 8 : 0);
+  L->fn = v.fn[km];
   int dev = 0;
   PFPN_CUDA_OK(cudaGetDevice(&dev));
   int max_optin = 0;
@@ -613,7 +723,7 @@ extern "C" int pfpn_head_workspace_bytes(int32_t A, int32_t P, size_t* bytes) {
 extern "C" int pfpn_head_launch_info(int32_t A, int32_t P, uint32_t mode, int32_t* out) {
   if (out == nullptr) return PFPN_ERR_ARG;
   HeadLaunch L;
-  int rc = plan_head(A, P, mode != PFPN_HEAD_FWD, &L);
+  int rc = plan_head(A, P, mode == PFPN_HEAD_FWD ? 0 : (mode == PFPN_HEAD_PPO ? 2 : 3), &L);
   if (rc != PFPN_OK) return rc;
   out[0] = L.num_sms;
   out[1] = L.ctas_per_sm;
@@ -640,7 +750,10 @@ extern "C" int pfpn_head_logprob(const pfpn_head_args* args, void* workspace, si
   if (!aligned16(a.logits) || (bwd && !aligned16(a.dlogits))) return PFPN_ERR_ALIGN;
 
   HeadLaunch L;
-  int rc = plan_head(a.A, a.P, bwd, &L);
+  const bool has_ent_grad = (a.g_ent != 0.f || a.g_ent_ba != nullptr);
+  const bool lean = !has_ent_grad && !a.dvalue && !a.ent_ba && !(a.flags & PFPN_HEAD_FLAG_TANH);
+  const int km = !bwd ? 0 : (!lean ? 1 : (a.mode == PFPN_HEAD_PPO ? 2 : 3));
+  int rc = plan_head(a.A, a.P, km, &L);
   if (rc != PFPN_OK) return rc;
   const int num_tiles = (a.B + L.ts - 1) / L.ts;
   int grid = L.num_sms * L.ctas_per_sm;
@@ -651,7 +764,7 @@ extern "C" int pfpn_head_logprob(const pfpn_head_args* args, void* workspace, si
   kp.a = a;
   kp.num_tiles = num_tiles;
   kp.slots = L.slots;
-  kp.has_ent_grad = (a.g_ent != 0.f || a.g_ent_ba != nullptr) ? 1 : 0;
+  kp.has_ent_grad = has_ent_grad ? 1 : 0;
   kp.part = nullptr;
   kp.loss_part = nullptr;
   const size_t AP = (size_t)a.A * a.P;
