@@ -98,6 +98,109 @@ int pfpn_adv_stats(const float* adv, int32_t B, float* stats, pfpn_stream_t stre
  * states per tile the K1 launch for (A,P,mode) uses.  out[4]. */
 int pfpn_head_launch_info(int32_t A, int32_t P, uint32_t mode, int32_t* out);
 
+/* ------------------------------------------------------------------------
+ * K2  plain particle sampling (rollouts).
+ * Replaces: MixtureGaussianDistribution.sample, plain branch   networks/utils.py:187-194
+ *           (Categorical.sample -> TF Multinomial; Normal.sample; one_hot gather).
+ * idx follows the TF-1.14 CPU Multinomial functor (fp64 CDF + upper_bound): with
+ * ext_uniform supplied the particle indices are bit-exact against the oracle.
+ * ---------------------------------------------------------------------- */
+typedef struct pfpn_sample_args {
+  const float* logits;      /* [B, A, P]                                            */
+  const float* loc;         /* [A, P]                                               */
+  const float* logstd;      /* [A, P]                                               */
+  const double* ext_uniform;/* [B, A] fp64 in [0,1), or NULL = Philox                */
+  const float* ext_normal;  /* [B, A, P] standard normals (read at [b,a,idx]) or NULL */
+  float* action;            /* [B, A]   out                                          */
+  int32_t* idx;             /* [B, A]   out: chosen particle ("dis_action")          */
+  uint64_t seed, offset;    /* Philox key / call counter (production mode)           */
+  int32_t B, A, P;
+} pfpn_sample_args;
+int pfpn_head_sample(const pfpn_sample_args* args, pfpn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * K3  reparameterised sampling (SAC, normalize_output=True) forward / backward.
+ * Replaces: MixtureGaussianDistribution.sample, rsample branch  networks/utils.py:156-186
+ *           incl. the custom gradients mask2 (:164-171) and mask (:176-183), and TFP 0.7
+ *           RelaxedOneHotCategorical(1.0, logits).sample (Gumbel-softmax).
+ * fwd: sample = tanh(s_pre), s_pre = (loc + scale*eps)[argmax softmax(logits + Gumbel(U))].
+ * bwd: given dL/dsample and dL/ds_pre writes dlogits (overwritten) and ADDS into
+ *      dloc / dlogstd (caller zeroes them).  The same (seed, offset) or the same ext_* arrays
+ *      must be passed to fwd and bwd: the draws are regenerated, not stored.
+ * ---------------------------------------------------------------------- */
+typedef struct pfpn_rsample_args {
+  const float* logits;      /* [B, A, P]                                            */
+  const float* loc;         /* [A, P]                                               */
+  const float* logstd;      /* [A, P]                                               */
+  const float* ext_uniform; /* [B, A, P] in [tiny, 1) or NULL = Philox               */
+  const float* ext_normal;  /* [B, A, P] or NULL (both or neither)                   */
+  float* sample;            /* [B, A]  fwd out: tanh(s_pre)                          */
+  float* s_pre;             /* [B, A]  fwd out: pre-tanh value                       */
+  int32_t* idx;             /* [B, A]  fwd out: argmax particle ("dis_action")       */
+  const float* g_sample;    /* [B, A]  bwd in                                        */
+  const float* g_s_pre;     /* [B, A]  bwd in, may be NULL (= 0)                     */
+  float* dlogits;           /* [B, A, P] bwd out                                     */
+  float* dloc;              /* [A, P]  bwd in/out (accumulated)                      */
+  float* dlogstd;           /* [A, P]  bwd in/out (accumulated)                      */
+  uint64_t seed, offset;
+  int32_t B, A, P;
+} pfpn_rsample_args;
+int pfpn_head_rsample_fwd(const pfpn_rsample_args* args, pfpn_stream_t stream);
+int pfpn_head_rsample_bwd(const pfpn_rsample_args* args, pfpn_stream_t stream);
+
+/* Deterministic action (evaluator): MixtureGaussianDistribution.mean  networks/utils.py:202-236.
+ * action[b,a] = loc[a, argmax_k logits[b,a,k]]  (tanh of it with PFPN_HEAD_FLAG_TANH). idx may be NULL. */
+int pfpn_head_mean(const float* logits, const float* loc, float* action, int32_t* idx, int32_t B, int32_t A,
+                   int32_t P, uint32_t flags, pfpn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * K4  running activity statistics.
+ * Replaces: ParticleFilteringA2CNetwork.init, `resample` scope   networks/actor_critic/a2c.py:346-365
+ *   max_active = max(max_active, max_b softmax(logits)); sum_active += sum_b softmax(logits).
+ * probs [B,A,P] may be NULL (only needed when the caller wants `dis_dist.probs`).
+ * ---------------------------------------------------------------------- */
+int pfpn_stats_update(const float* logits, float* probs, float* max_active, float* sum_active, int32_t B,
+                      int32_t A, int32_t P, pfpn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * K5  dead-particle resampling.
+ * Replaces: ParticleFilteringA2CNetwork.build_resample_ops      networks/actor_critic/a2c.py:385-474
+ *           and the statistics reset of `update()`               a2c.py:370-378.
+ * All tensors are updated in place.  The out_* pointers are optional verification outputs
+ * (bit-exact integers against the oracle when the ext_* draws are supplied).
+ * ---------------------------------------------------------------------- */
+#define PFPN_RESAMPLE_FLAG_TANH 1u /* normalize_policy_output_: atanh(clip(loc)) (a2c.py:448-450) */
+typedef struct pfpn_resample_args {
+  float* max_active;         /* [A, P] in; zeroed on return                           */
+  float* sum_active;         /* [A, P] in; zeroed on return                           */
+  float* loc;                /* [A, P] in/out  ("samples")                            */
+  float* logstd;             /* [A, P] in/out  ("samples_std")                        */
+  float* bias;               /* [A*P]  in/out  (fc_policy/bias)                       */
+  float* weight;             /* [H, A*P] in/out (fc_policy/weight), NULL iff H == 0   */
+  const double* ext_cat_u;   /* [A, P] fp64 draws of tf.random.categorical, or NULL   */
+  const int32_t* ext_choice; /* [A*P]  draws of uniform{0..k-1} (resample > 0), or NULL */
+  const float* ext_noise_u;  /* [A*P]  draws of uniform(-1,1), or NULL                */
+  int32_t* out_M;            /* [1]    number of dead particles                       */
+  int32_t* out_nuniq;        /* [1]    number of distinct source columns              */
+  int32_t* out_invalid;      /* [A*P, 2] (a_m, j_m) row-major                         */
+  int32_t* out_cand;         /* [A, k] candidate table                                */
+  int32_t* out_src;          /* [A*P]                                                 */
+  int32_t* out_col;          /* [A*P]  a_m*P + j_m                                    */
+  int32_t* out_tcol;         /* [A*P]  a_m*P + src_m                                  */
+  int32_t* out_uniq;         /* [A*P]  unique_with_counts: values, first-occurrence order */
+  int32_t* out_idx;          /* [A*P]  unique_with_counts: index of tcol_m in uniq    */
+  int32_t* out_count;        /* [A*P]  unique_with_counts: counts                     */
+  int32_t* out_delta;        /* [A*P]  1 iff uniq_u is itself a dead column           */
+  uint64_t seed, offset;     /* Philox key / call counter (production mode)           */
+  float threshold;           /* <= 0: 0.05 / P (a2c.py:391)                           */
+  int32_t A, P, H;
+  int32_t resample;          /* -1: categorical candidates (shipped); r > 0: top-r    */
+  uint32_t flags;
+} pfpn_resample_args;
+int pfpn_resample_workspace_bytes(int32_t A, int32_t P, int32_t H, size_t* bytes);
+int pfpn_resample(const pfpn_resample_args* args, void* workspace, size_t workspace_bytes,
+                  pfpn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

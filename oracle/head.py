@@ -132,7 +132,9 @@ def tf_multinomial_cpu(logits: np.ndarray, uniforms: np.ndarray) -> np.ndarray:
         e = np.where(finite, np.exp(row.astype(np.float64) - mx), 0.0)
         cdf = np.cumsum(e)  # sequential fp64 running total
         total = cdf[-1]
-        out[r] = np.searchsorted(cdf, uniforms[r] * total, side="right").astype(np.int32)
+        # (u * total can round up to total; TF would then emit the out-of-range class `classes`,
+        #  the oracle and the kernels clamp to the last class)
+        out[r] = np.minimum(np.searchsorted(cdf, uniforms[r] * total, side="right"), classes - 1).astype(np.int32)
     return out
 
 

@@ -75,3 +75,56 @@ def exported_symbols():
     import re
     hdr = (Path(__file__).resolve().parent.parent / "include" / "pfpn_b200.h").read_text()
     return sorted(set(re.findall(r"\b(pfpn_[a-z0-9_]+)\s*\(", hdr)))
+
+
+# ---- K2 / K3 / K4 / K5 ------------------------------------------------------------------------
+RESAMPLE_FLAG_TANH = 1
+
+
+class SampleArgs(C.Structure):
+    """Mirror of ``pfpn_sample_args``."""
+    _fields_ = [
+        ("logits", _f32p), ("loc", _f32p), ("logstd", _f32p), ("ext_uniform", C.c_void_p),
+        ("ext_normal", _f32p), ("action", _f32p), ("idx", C.c_void_p),
+        ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("B", C.c_int32), ("A", C.c_int32), ("P", C.c_int32),
+    ]
+
+
+class RSampleArgs(C.Structure):
+    """Mirror of ``pfpn_rsample_args``."""
+    _fields_ = [
+        ("logits", _f32p), ("loc", _f32p), ("logstd", _f32p), ("ext_uniform", _f32p), ("ext_normal", _f32p),
+        ("sample", _f32p), ("s_pre", _f32p), ("idx", C.c_void_p),
+        ("g_sample", _f32p), ("g_s_pre", _f32p), ("dlogits", _f32p), ("dloc", _f32p), ("dlogstd", _f32p),
+        ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("B", C.c_int32), ("A", C.c_int32), ("P", C.c_int32),
+    ]
+
+
+class ResampleArgs(C.Structure):
+    """Mirror of ``pfpn_resample_args``."""
+    _fields_ = [
+        ("max_active", _f32p), ("sum_active", _f32p), ("loc", _f32p), ("logstd", _f32p),
+        ("bias", _f32p), ("weight", _f32p),
+        ("ext_cat_u", C.c_void_p), ("ext_choice", C.c_void_p), ("ext_noise_u", _f32p),
+        ("out_M", C.c_void_p), ("out_nuniq", C.c_void_p), ("out_invalid", C.c_void_p), ("out_cand", C.c_void_p),
+        ("out_src", C.c_void_p), ("out_col", C.c_void_p), ("out_tcol", C.c_void_p), ("out_uniq", C.c_void_p),
+        ("out_idx", C.c_void_p), ("out_count", C.c_void_p), ("out_delta", C.c_void_p),
+        ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("threshold", C.c_float),
+        ("A", C.c_int32), ("P", C.c_int32), ("H", C.c_int32),
+        ("resample", C.c_int32), ("flags", C.c_uint32),
+    ]
+
+
+pfpn_head_sample = _sig("pfpn_head_sample", C.c_int, [C.POINTER(SampleArgs), C.c_void_p])
+pfpn_head_rsample_fwd = _sig("pfpn_head_rsample_fwd", C.c_int, [C.POINTER(RSampleArgs), C.c_void_p])
+pfpn_head_rsample_bwd = _sig("pfpn_head_rsample_bwd", C.c_int, [C.POINTER(RSampleArgs), C.c_void_p])
+pfpn_head_mean = _sig("pfpn_head_mean", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                                  C.c_int32, C.c_int32, C.c_uint32, C.c_void_p])
+pfpn_stats_update = _sig("pfpn_stats_update", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p])
+pfpn_resample_workspace_bytes = _sig("pfpn_resample_workspace_bytes", C.c_int,
+                                     [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)])
+pfpn_resample = _sig("pfpn_resample", C.c_int, [C.POINTER(ResampleArgs), C.c_void_p, C.c_size_t, C.c_void_p])

@@ -22,3 +22,7 @@ static_assert(sizeof(pfpn_head_args) == 176, "pfpn_head_args layout changed: upd
 static_assert(offsetof(pfpn_head_args, g_ent) == 48 && offsetof(pfpn_head_args, adv) == 56, "layout");
 static_assert(offsetof(pfpn_head_args, eps_clip) == 80 && offsetof(pfpn_head_args, lp) == 88, "layout");
 static_assert(offsetof(pfpn_head_args, loss) == 144 && offsetof(pfpn_head_args, B) == 152, "layout");
+static_assert(sizeof(pfpn_sample_args) == 88, "pfpn_sample_args layout changed: update _cabi.SampleArgs");
+static_assert(sizeof(pfpn_rsample_args) == 136, "pfpn_rsample_args layout changed: update _cabi.RSampleArgs");
+static_assert(sizeof(pfpn_resample_args) == 200, "pfpn_resample_args layout changed: update _cabi.ResampleArgs");
+static_assert(offsetof(pfpn_resample_args, seed) == 160 && offsetof(pfpn_resample_args, threshold) == 176, "layout");

@@ -1,0 +1,386 @@
+// K5 -- dead-particle resampling, and K4 -- running activity statistics.
+//
+// Replaces the ~120-node `cond/*` sub-graph that
+// /root/reference/networks/actor_critic/a2c.py:385-474 builds (Where, Multinomial,
+// GatherNd, UniqueWithCounts, map/while, ScatterNdUpdate ...) with three launches:
+//   1. resample_plan_kernel  (one CTA): stable row-major compaction of the dead particles,
+//      fp64-CDF categorical draw of the candidate table (TF-1.14 CPU Multinomial semantics),
+//      per-dead-particle gathers, noise, logit split  b -= log(count + 1 - delta), and the
+//      [A,P]-sized scatters;
+//   2. resample_gather_w / 3. resample_scatter_w: fc_policy weight columns W[:, col_m] =
+//      W_pre[:, tcol_m] through a snapshot, so a dead particle that is itself a source is
+//      copied from its PRE-update value as the reference's gather-before-scatter does.
+// Integer results (M, (a_m, j_m), cand, src, col, tcol, uniq/idx/count/delta) are bit-exact
+// against oracle/resample.py; M is only known on the device, launches 2/3 size for A*P.
+#include "common.cuh"
+
+namespace pfpn {
+
+struct ResampleWs {
+  int* M;          // [1]
+  int* nuniq;      // [1]
+  int* invalid;    // [AP][2]
+  int* cand;       // [A][P]
+  int* src;        // [AP]
+  int* col;        // [AP]
+  int* tcol;       // [AP]
+  int* count_by;   // [AP]  #m with tcol_m == column
+  int* first_m;    // [AP]  smallest m with tcol_m == column
+  int* is_dead;    // [AP]
+  int* uniq_rank;  // [AP]  rank of a column among first occurrences
+  float* tloc;     // [AP]
+  float* tlogstd;  // [AP]
+  float* tb;       // [AP]
+  float* logit;    // [AP]
+  double* cdf;     // [AP]
+  double* total;   // [A]
+  float* tW;       // [H][AP]
+};
+
+__device__ __forceinline__ int block_exclusive_scan(int flag, int* warp_sums, int* total_out) {
+  // returns exclusive prefix of `flag` over the CTA in thread order; *total_out = CTA total
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, flag != 0);
+  const int pre = __popc(bal & ((1u << lane) - 1u));
+  if (lane == 0) warp_sums[warp] = __popc(bal);
+  __syncthreads();
+  int base = 0, tot = 0;
+  for (int w = 0; w < nw; ++w) {
+    const int v = warp_sums[w];
+    if (w < warp) base += v;
+    tot += v;
+  }
+  __syncthreads();
+  *total_out = tot;
+  return base + pre;
+}
+
+__global__ void __launch_bounds__(1024) resample_plan_kernel(const pfpn_resample_args ar, const ResampleWs ws) {
+  __shared__ int warp_sums[32];
+  const int A = ar.A, P = ar.P, AP = A * P;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const float thr = ar.threshold > 0.f ? ar.threshold : 0.05f / (float)P;  // a2c.py:391
+  const bool tanh_flag = (ar.flags & PFPN_RESAMPLE_FLAG_TANH) != 0;
+  const int K = ar.resample < 0 ? P : min(P, ar.resample);
+  const Philox rng(ar.seed);
+
+  // ---- 1. avg = sum_active / rowsum (sequential fp32 row sum), logits = log(avg) ------------
+  for (int a = tid; a < A; a += nthr) {
+    float rs = 0.f;
+    for (int k = 0; k < P; ++k) rs = __fadd_rn(rs, ar.sum_active[a * P + k]);
+    double run = 0.0;
+    float mx = -3.402823466e38f;
+    for (int k = 0; k < P; ++k) {
+      const float avg = __fdiv_rn(ar.sum_active[a * P + k], rs);
+      const float lg = (float)log((double)avg);  // fp64 log rounded to fp32 (see oracle/resample.py)
+      ws.logit[a * P + k] = ar.resample < 0 ? lg : avg;
+      if (isfinite(lg)) mx = fmaxf(mx, lg);
+    }
+    if (ar.resample < 0) {  // TF CPU Multinomial: fp64 running CDF over the finite logits
+      for (int k = 0; k < P; ++k) {
+        const float lg = ws.logit[a * P + k];
+        if (isfinite(lg)) run += exp((double)lg - (double)mx);
+        ws.cdf[a * P + k] = run;
+      }
+      ws.total[a] = run;
+    }
+  }
+  for (int i = tid; i < AP; i += nthr) {
+    ws.count_by[i] = 0;
+    ws.first_m[i] = 0x7fffffff;
+    ws.is_dead[i] = 0;
+  }
+  __syncthreads();
+
+  // ---- 2. candidate table ------------------------------------------------------------------
+  if (ar.resample < 0) {
+    for (int i = tid; i < A * P; i += nthr) {  // (a, s): s-th draw of row a
+      const int a = i / P;
+      double u;
+      if (ar.ext_cat_u != nullptr) {
+        u = ar.ext_cat_u[i];
+      } else {
+        const uint4 r = rng(ar.offset, (uint64_t)i);
+        u = u64_to_unit_double(r.x, r.y);
+      }
+      const double to_find = u * ws.total[a];
+      const double* cdf = ws.cdf + a * P;
+      int lo = 0, hi = P;  // upper_bound: first index with cdf[idx] > to_find
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cdf[mid] > to_find) hi = mid;
+        else lo = mid + 1;
+      }
+      ws.cand[i] = lo;
+    }
+  } else {
+    for (int i = tid; i < AP; i += nthr) {  // descending rank, ties -> lower index
+      const int a = i / P, k = i - a * P;
+      const float v = ws.logit[i];
+      int rank = 0;
+      for (int j = 0; j < P; ++j) {
+        const float w = ws.logit[a * P + j];
+        rank += (w > v) || (w == v && j < k);
+      }
+      if (rank < K) ws.cand[a * K + rank] = k;
+    }
+  }
+
+  // ---- 3. stable row-major compaction of dead particles (tf.where order) --------------------
+  int M = 0;
+  for (int base = 0; base < AP; base += nthr) {
+    const int i = base + tid;
+    const int flag = (i < AP) && (ar.max_active[i] < thr);
+    int tot;
+    const int pos = block_exclusive_scan(flag, warp_sums, &tot);
+    if (flag) {
+      const int m = M + pos;
+      ws.invalid[2 * m] = i / P;
+      ws.invalid[2 * m + 1] = i % P;
+      ws.is_dead[i] = 1;
+    }
+    M += tot;
+  }
+  if (tid == 0) *ws.M = M;
+  __syncthreads();
+
+  // ---- 4. per dead particle: source, gathers of PRE-update values, noise ---------------------
+  for (int m = tid; m < M; m += nthr) {
+    const int a = ws.invalid[2 * m], j = ws.invalid[2 * m + 1];
+    int ch;
+    if (ar.resample < 0) {
+      ch = j;  // a2c.py:403
+    } else if (ar.ext_choice != nullptr) {
+      ch = ar.ext_choice[m];
+    } else {
+      const uint4 r = rng(ar.offset + 1, (uint64_t)m);
+      ch = (int)(r.x % (uint32_t)K);
+    }
+    const int s = ws.cand[a * K + ch];
+    const int col = a * P + j, tcol = a * P + s;
+    ws.src[m] = s;
+    ws.col[m] = col;
+    ws.tcol[m] = tcol;
+    atomicAdd(&ws.count_by[tcol], 1);
+    atomicMin(&ws.first_m[tcol], m);
+    float tloc = ar.loc[tcol];
+    const float tls = ar.logstd[tcol];
+    const float tstd = expf(tls);
+    float u;
+    if (ar.ext_noise_u != nullptr) {
+      u = ar.ext_noise_u[m];
+    } else {
+      const uint4 r = rng(ar.offset + 2, (uint64_t)m);
+      u = 2.f * u32_to_unit_open(r.x) - 1.f;
+    }
+    float noise = __fmul_rn(tstd, u);
+    noise = __fadd_rn(noise, noise < 0.f ? -1e-4f : 1e-4f);  // a2c.py:442-444
+    tloc = __fadd_rn(tloc, noise);
+    if (tanh_flag) {  // a2c.py:448-450
+      const float eps = 1e-6f;
+      tloc = atanhf(fminf(fmaxf(tloc, eps - 1.f), 1.f - eps));
+    }
+    ws.tloc[m] = tloc;
+    ws.tlogstd[m] = fminf(fmaxf(tls, -20.f), 2.f);  // a2c.py:451
+    ws.tb[m] = ar.bias[tcol];
+  }
+  __syncthreads();
+
+  // ---- 5. unique_with_counts bookkeeping (first-occurrence order) + logit split -------------
+  int nuniq = 0;
+  for (int base = 0; base < M; base += nthr) {
+    const int m = base + tid;
+    const int flag = (m < M) && (ws.first_m[ws.tcol[m]] == m);
+    int tot;
+    const int pos = block_exclusive_scan(flag, warp_sums, &tot);
+    if (flag) {
+      const int u = nuniq + pos;
+      const int tc = ws.tcol[m];
+      ws.uniq_rank[tc] = u;
+      if (ar.out_uniq) ar.out_uniq[u] = tc;
+      if (ar.out_count) ar.out_count[u] = ws.count_by[tc];
+      if (ar.out_delta) ar.out_delta[u] = ws.is_dead[tc];
+    }
+    nuniq += tot;
+  }
+  if (tid == 0) *ws.nuniq = nuniq;
+  __syncthreads();
+  for (int m = tid; m < M; m += nthr) {
+    const int tc = ws.tcol[m];
+    // a2c.py:458: b -= log(count + 1 - delta); delta = 1 iff the source column is itself dead
+    const float denom = __fsub_rn(__fadd_rn((float)ws.count_by[tc], 1.f), (float)ws.is_dead[tc]);
+    ws.tb[m] = __fsub_rn(ws.tb[m], logf(denom));
+    if (ar.out_idx) ar.out_idx[m] = ws.uniq_rank[tc];
+    if (ar.out_src) ar.out_src[m] = ws.src[m];
+    if (ar.out_col) ar.out_col[m] = ws.col[m];
+    if (ar.out_tcol) ar.out_tcol[m] = tc;
+    if (ar.out_invalid) {
+      ar.out_invalid[2 * m] = ws.invalid[2 * m];
+      ar.out_invalid[2 * m + 1] = ws.invalid[2 * m + 1];
+    }
+  }
+  if (ar.out_cand) {
+    for (int i = tid; i < A * K; i += nthr) ar.out_cand[i] = ws.cand[i];
+  }
+  if (tid == 0) {
+    if (ar.out_M) *ar.out_M = M;
+    if (ar.out_nuniq) *ar.out_nuniq = nuniq;
+  }
+  __syncthreads();
+
+  // ---- 6. [A,P]-sized scatters (a2c.py:460-466), then zero the statistics (a2c.py:372-378) ---
+  for (int m = tid; m < M; m += nthr) {
+    ar.loc[ws.col[m]] = ws.tloc[m];
+    ar.logstd[ws.col[m]] = ws.tlogstd[m];
+    ar.bias[ws.tcol[m]] = ws.tb[m];  // duplicates carry equal values
+  }
+  __syncthreads();
+  for (int m = tid; m < M; m += nthr) ar.bias[ws.col[m]] = ws.tb[m];  // control-dependent second scatter
+  for (int i = tid; i < AP; i += nthr) {
+    ar.max_active[i] = 0.f;
+    ar.sum_active[i] = 0.f;
+  }
+}
+
+// tW[h][m] = W[h][tcol_m]   (snapshot of the source columns)
+__global__ void resample_gather_w(const float* __restrict__ W, float* __restrict__ tW, const int* __restrict__ Mp,
+                                  const int* __restrict__ tcol, int H, int AP) {
+  const int M = *Mp;
+  const int h = blockIdx.y;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x)
+    tW[(size_t)h * AP + m] = W[(size_t)h * AP + tcol[m]];
+}
+// W[h][col_m] = tW[h][m]
+__global__ void resample_scatter_w(float* __restrict__ W, const float* __restrict__ tW, const int* __restrict__ Mp,
+                                   const int* __restrict__ col, int H, int AP) {
+  const int M = *Mp;
+  const int h = blockIdx.y;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x)
+    W[(size_t)h * AP + col[m]] = tW[(size_t)h * AP + m];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: max_active = max(max_active, max_b softmax(logits)), sum_active += sum_b softmax(logits)
+// (a2c.py:356-360).  One warp per mixture row; per-CTA column partials in shared memory, then one
+// atomicMax (values are non-negative, so the int ordering equals the float ordering) and one
+// float atomicAdd per column per CTA.  Optionally writes the probabilities.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stats_kernel(const float* __restrict__ logits, float* __restrict__ probs,
+                                                    float* __restrict__ max_active, float* __restrict__ sum_active,
+                                                    int B, int A, int P) {
+  extern __shared__ float sm[];  // [2][A*P]
+  const int AP = A * P;
+  float* smax = sm;
+  float* ssum = sm + AP;
+  for (int i = threadIdx.x; i < 2 * AP; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long rows = (long long)B * A;
+  for (long long r = (long long)blockIdx.x * nw + warp; r < rows; r += (long long)gridDim.x * nw) {
+    const int a = (int)(r % A);
+    const float* x = logits + r * P;
+    float m = -3.402823466e38f;
+    for (int k = lane; k < P; k += 32) m = fmaxf(m, x[k]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int k = lane; k < P; k += 32) s += expf(x[k] - m);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float inv = 1.f / s;
+    for (int k = lane; k < P; k += 32) {
+      const float p = expf(x[k] - m) * inv;
+      if (probs != nullptr) probs[r * P + k] = p;
+      atomicMax(reinterpret_cast<int*>(&smax[a * P + k]), __float_as_int(p));
+      atomicAdd(&ssum[a * P + k], p);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < AP; i += blockDim.x) {
+    atomicMax(reinterpret_cast<int*>(&max_active[i]), __float_as_int(smax[i]));
+    atomicAdd(&sum_active[i], ssum[i]);
+  }
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static size_t carve(ResampleWs* ws, unsigned char* base, int A, int P, int H) {
+  const size_t AP = (size_t)A * P;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    unsigned char* p = base ? base + off : nullptr;
+    off = align_up(off + bytes, 16);
+    return p;
+  };
+  ws->cdf = reinterpret_cast<double*>(take(AP * 8));
+  ws->total = reinterpret_cast<double*>(take((size_t)A * 8));
+  ws->M = reinterpret_cast<int*>(take(16));
+  ws->nuniq = reinterpret_cast<int*>(take(16));
+  ws->invalid = reinterpret_cast<int*>(take(AP * 8));
+  ws->cand = reinterpret_cast<int*>(take(AP * 4));
+  ws->src = reinterpret_cast<int*>(take(AP * 4));
+  ws->col = reinterpret_cast<int*>(take(AP * 4));
+  ws->tcol = reinterpret_cast<int*>(take(AP * 4));
+  ws->count_by = reinterpret_cast<int*>(take(AP * 4));
+  ws->first_m = reinterpret_cast<int*>(take(AP * 4));
+  ws->is_dead = reinterpret_cast<int*>(take(AP * 4));
+  ws->uniq_rank = reinterpret_cast<int*>(take(AP * 4));
+  ws->tloc = reinterpret_cast<float*>(take(AP * 4));
+  ws->tlogstd = reinterpret_cast<float*>(take(AP * 4));
+  ws->tb = reinterpret_cast<float*>(take(AP * 4));
+  ws->logit = reinterpret_cast<float*>(take(AP * 4));
+  ws->tW = reinterpret_cast<float*>(take((size_t)H * AP * 4));
+  return off;
+}
+
+}  // namespace pfpn
+
+using namespace pfpn;
+
+extern "C" int pfpn_resample_workspace_bytes(int32_t A, int32_t P, int32_t H, size_t* bytes) {
+  if (!bytes || A <= 0 || P <= 0 || H < 0) return PFPN_ERR_ARG;
+  ResampleWs ws;
+  *bytes = carve(&ws, nullptr, A, P, H);
+  return PFPN_OK;
+}
+
+extern "C" int pfpn_resample(const pfpn_resample_args* args, void* workspace, size_t workspace_bytes,
+                             pfpn_stream_t stream_) {
+  if (!args) return PFPN_ERR_ARG;
+  const pfpn_resample_args& a = *args;
+  if (a.A <= 0 || a.P <= 0 || a.H < 0) return PFPN_ERR_ARG;
+  if (!a.max_active || !a.sum_active || !a.loc || !a.logstd || !a.bias || (a.H > 0 && !a.weight)) return PFPN_ERR_ARG;
+  if (a.resample == 0 || a.resample < -1) return PFPN_ERR_ARG;
+  if (a.resample > a.P) return PFPN_ERR_ARG;  // reference asserts n >= resample (a2c.py:390)
+  ResampleWs ws;
+  const size_t need = carve(&ws, nullptr, a.A, a.P, a.H);
+  if (!workspace || workspace_bytes < need) return PFPN_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) & 15u) return PFPN_ERR_ALIGN;
+  carve(&ws, reinterpret_cast<unsigned char*>(workspace), a.A, a.P, a.H);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  resample_plan_kernel<<<1, 1024, 0, stream>>>(a, ws);
+  PFPN_CUDA_OK(cudaGetLastError());
+  if (a.H > 0) {
+    const int AP = a.A * a.P;
+    dim3 grid((AP + 255) / 256, a.H);
+    resample_gather_w<<<grid, 256, 0, stream>>>(a.weight, ws.tW, ws.M, ws.tcol, a.H, AP);
+    PFPN_CUDA_OK(cudaGetLastError());
+    resample_scatter_w<<<grid, 256, 0, stream>>>(a.weight, ws.tW, ws.M, ws.col, a.H, AP);
+    PFPN_CUDA_OK(cudaGetLastError());
+  }
+  return PFPN_OK;
+}
+
+extern "C" int pfpn_stats_update(const float* logits, float* probs, float* max_active, float* sum_active, int32_t B,
+                                 int32_t A, int32_t P, pfpn_stream_t stream_) {
+  if (!logits || !max_active || !sum_active || B < 0 || A <= 0 || P <= 0) return PFPN_ERR_ARG;
+  if (B == 0) return PFPN_OK;
+  const size_t smem = 2 * (size_t)A * P * sizeof(float);
+  if (smem > 200 * 1024) return PFPN_ERR_UNSUPPORTED;
+  PFPN_CUDA_OK(cudaFuncSetAttribute((const void*)stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long rows = (long long)B * A;
+  long long want = (rows + 7) / 8;
+  int grid = (int)(want < 148 * 4 ? want : 148 * 4);
+  if (grid < 1) grid = 1;
+  stats_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(logits, probs, max_active, sum_active, B, A, P);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}

@@ -13,6 +13,7 @@ import torch
 
 from . import _cabi
 from . import head as _head
+from . import sampling as _sampling
 
 
 class _LogProbFn(torch.autograd.Function):
@@ -55,6 +56,30 @@ class _EntropyFn(torch.autograd.Function):
         return out["dlogits"], None, None
 
 
+class _RSampleFn(torch.autograd.Function):
+    """(sample, s_) of utils.py:156-186 with the mask / mask2 custom gradients."""
+
+    @staticmethod
+    def forward(ctx, logits, loc, logstd, seed, offset, ext_uniform, ext_normal):
+        sample, s_pre, idx = _sampling.rsample_fwd(logits, loc, logstd, seed=seed, offset=offset,
+                                                   ext_uniform=ext_uniform, ext_normal=ext_normal)
+        ctx.save_for_backward(logits, loc, logstd)
+        ctx.rng = (seed, offset, ext_uniform, ext_normal)
+        ctx.mark_non_differentiable(idx)
+        return sample, s_pre, idx
+
+    @staticmethod
+    def backward(ctx, g_sample, g_s_pre, _g_idx):
+        logits, loc, logstd = ctx.saved_tensors
+        seed, offset, eu, en = ctx.rng
+        if g_sample is None:
+            g_sample = torch.zeros(logits.shape[:2], dtype=torch.float32, device=logits.device)
+        dlogits, dloc, dlogstd = _sampling.rsample_bwd(logits, loc, logstd, g_sample.contiguous(),
+                                                       None if g_s_pre is None else g_s_pre.contiguous(),
+                                                       seed=seed, offset=offset, ext_uniform=eu, ext_normal=en)
+        return dlogits, dloc, dlogstd, None, None, None, None
+
+
 class _DisDist:
     """Stand-in for ``dis_dist`` (utils.py:96-98): callers read ``.probs`` / ``.logits``."""
 
@@ -65,10 +90,11 @@ class _DisDist:
     @property
     def probs(self):
         if self._probs is None:
-            # consumed only by the running activity statistics (a2c.py:348-360),
-            # for which `pfpn_b200.stats` has a fused kernel; this materialised
-            # form exists for API parity.
-            self._probs = torch.softmax(self.logits, dim=-1)
+            # the only consumer is the running activity statistics (a2c.py:348-360); the K4 kernel
+            # produces the probabilities as a by-product (statistics go to scratch here).
+            _, A, P = self.logits.shape
+            scratch = torch.zeros(2, A, P, dtype=torch.float32, device=self.logits.device)
+            self._probs = _sampling.stats_update(self.logits.detach(), scratch[0], scratch[1], want_probs=True)
         return self._probs
 
 
@@ -102,3 +128,28 @@ class MixtureGaussianDistribution:
     # utils.py:146-151
     def entropy(self, name="entropy"):
         return _EntropyFn.apply(self.logits, self.loc, self.logstd)
+
+    # utils.py:153-200
+    def sample(self, n, *, seed: int = 0, offset: int = 0, ext_uniform=None, ext_normal=None):
+        """``n`` must be 1 (utils.py:154).  Plain branch -> [1, B, A]; rsample branch
+        (normalize_output) -> tuple (sample [1,B,A], value_before_tanh [1,B,A]).
+        Draws come from Philox(seed, offset) unless ext_* arrays are supplied."""
+        assert n == 1
+        B, A, _ = self.logits.shape
+        if self.normalize_output:
+            sample, s_pre, idx = _RSampleFn.apply(self.logits, self.loc, self.logstd, seed, offset, ext_uniform,
+                                                  ext_normal)
+            self.dis_action = idx
+            return sample.reshape(n, B, A), s_pre.reshape(n, B, A)
+        action, idx = _sampling.sample_plain(self.logits.detach(), self.loc.detach(), self.logstd.detach(), seed=seed,
+                                             offset=offset, ext_uniform=ext_uniform, ext_normal=ext_normal)
+        self.dis_action = idx
+        return action.reshape(n, B, A)
+
+    # utils.py:202-236 (forward; the reference only evaluates it on non-trainable evaluator nets)
+    def mean(self):
+        if not hasattr(self, "_determinstic_action"):
+            action, idx = _sampling.mean_action(self.logits.detach(), self.loc.detach(), tanh=self.normalize_output)
+            self.dis_action = idx
+            self._determinstic_action = action
+        return self._determinstic_action

@@ -1,0 +1,117 @@
+"""Wrappers over K2 (plain sample), K3 (reparameterised sample fwd/bwd), the deterministic
+action and K4 (activity statistics).  torch tensors carry device memory only."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _cabi
+from .head import _f32c, _stream_ptr
+
+
+def _i32(*shape, device):
+    return torch.empty(*shape, dtype=torch.int32, device=device)
+
+
+def sample_plain(logits, loc, logstd, *, seed: int = 0, offset: int = 0, ext_uniform: Optional[torch.Tensor] = None,
+                 ext_normal: Optional[torch.Tensor] = None):
+    """utils.py:187-194.  Returns (action [B,A] f32, idx [B,A] int32)."""
+    logits, loc, logstd = _f32c(logits, "logits"), _f32c(loc, "loc"), _f32c(logstd, "logstd")
+    B, A, P = logits.shape
+    a = _cabi.SampleArgs()
+    a.logits, a.loc, a.logstd = logits.data_ptr(), loc.data_ptr(), logstd.data_ptr()
+    keep = []
+    if ext_uniform is not None:
+        if ext_uniform.dtype != torch.float64 or ext_uniform.shape != (B, A):
+            raise ValueError("ext_uniform must be float64 [B, A]")
+        ext_uniform = ext_uniform.contiguous()
+        keep.append(ext_uniform)
+        a.ext_uniform = ext_uniform.data_ptr()
+    if ext_normal is not None:
+        ext_normal = _f32c(ext_normal, "ext_normal")
+        if ext_normal.shape != (B, A, P):
+            raise ValueError("ext_normal must be float32 [B, A, P]")
+        keep.append(ext_normal)
+        a.ext_normal = ext_normal.data_ptr()
+    action = torch.empty(B, A, dtype=torch.float32, device=logits.device)
+    idx = _i32(B, A, device=logits.device)
+    a.action, a.idx = action.data_ptr(), idx.data_ptr()
+    a.seed, a.offset, a.B, a.A, a.P = seed, offset, B, A, P
+    with torch.cuda.device(logits.device):
+        _cabi.check(_cabi.pfpn_head_sample(C.byref(a), _stream_ptr()))
+    return action, idx
+
+
+def _rsample_args(logits, loc, logstd, seed, offset, ext_uniform, ext_normal):
+    logits, loc, logstd = _f32c(logits, "logits"), _f32c(loc, "loc"), _f32c(logstd, "logstd")
+    B, A, P = logits.shape
+    a = _cabi.RSampleArgs()
+    a.logits, a.loc, a.logstd = logits.data_ptr(), loc.data_ptr(), logstd.data_ptr()
+    keep = [logits, loc, logstd]
+    if (ext_uniform is None) != (ext_normal is None):
+        raise ValueError("pass both ext_uniform and ext_normal or neither")
+    if ext_uniform is not None:
+        ext_uniform, ext_normal = _f32c(ext_uniform, "ext_uniform"), _f32c(ext_normal, "ext_normal")
+        keep += [ext_uniform, ext_normal]
+        a.ext_uniform, a.ext_normal = ext_uniform.data_ptr(), ext_normal.data_ptr()
+    a.seed, a.offset, a.B, a.A, a.P = seed, offset, B, A, P
+    return a, keep
+
+
+def rsample_fwd(logits, loc, logstd, *, seed=0, offset=0, ext_uniform=None, ext_normal=None):
+    """utils.py:156-186 forward.  Returns (sample = tanh(s_), s_, idx)."""
+    a, keep = _rsample_args(logits, loc, logstd, seed, offset, ext_uniform, ext_normal)
+    dev = logits.device
+    sample = torch.empty(a.B, a.A, dtype=torch.float32, device=dev)
+    s_pre = torch.empty_like(sample)
+    idx = _i32(a.B, a.A, device=dev)
+    a.sample, a.s_pre, a.idx = sample.data_ptr(), s_pre.data_ptr(), idx.data_ptr()
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.pfpn_head_rsample_fwd(C.byref(a), _stream_ptr()))
+    return sample, s_pre, idx
+
+
+def rsample_bwd(logits, loc, logstd, g_sample, g_s_pre, *, seed=0, offset=0, ext_uniform=None, ext_normal=None):
+    """Straight-through backward (mask / mask2, utils.py:164-183).  Returns (dlogits, dloc, dlogstd)."""
+    a, keep = _rsample_args(logits, loc, logstd, seed, offset, ext_uniform, ext_normal)
+    dev = logits.device
+    g_sample = _f32c(g_sample, "g_sample")
+    a.g_sample = g_sample.data_ptr()
+    if g_s_pre is not None:
+        g_s_pre = _f32c(g_s_pre, "g_s_pre")
+        a.g_s_pre = g_s_pre.data_ptr()
+    dlogits = torch.empty(a.B, a.A, a.P, dtype=torch.float32, device=dev)
+    dloc = torch.zeros(a.A, a.P, dtype=torch.float32, device=dev)
+    dlogstd = torch.zeros_like(dloc)
+    a.dlogits, a.dloc, a.dlogstd = dlogits.data_ptr(), dloc.data_ptr(), dlogstd.data_ptr()
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.pfpn_head_rsample_bwd(C.byref(a), _stream_ptr()))
+    return dlogits, dloc, dlogstd
+
+
+def mean_action(logits, loc, tanh: bool = False):
+    """utils.py:202-236 (forward).  Returns (action [B,A], idx [B,A])."""
+    logits, loc = _f32c(logits, "logits"), _f32c(loc, "loc")
+    B, A, P = logits.shape
+    action = torch.empty(B, A, dtype=torch.float32, device=logits.device)
+    idx = _i32(B, A, device=logits.device)
+    with torch.cuda.device(logits.device):
+        _cabi.check(_cabi.pfpn_head_mean(logits.data_ptr(), loc.data_ptr(), action.data_ptr(), idx.data_ptr(), B, A, P,
+                                         _cabi.HEAD_FLAG_TANH if tanh else 0, _stream_ptr()))
+    return action, idx
+
+
+def stats_update(logits, max_active, sum_active, want_probs: bool = False):
+    """a2c.py:356-360, in place on max_active / sum_active.  Returns probs [B,A,P] or None."""
+    logits = _f32c(logits, "logits")
+    B, A, P = logits.shape
+    for t, n in ((max_active, "max_active"), (sum_active, "sum_active")):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape == (A, P)):
+            raise ValueError(f"{n}: expected contiguous float32 CUDA [A, P]")
+    probs = torch.empty_like(logits) if want_probs else None
+    with torch.cuda.device(logits.device):
+        _cabi.check(_cabi.pfpn_stats_update(logits.data_ptr(), None if probs is None else probs.data_ptr(),
+                                            max_active.data_ptr(), sum_active.data_ptr(), B, A, P, _stream_ptr()))
+    return probs

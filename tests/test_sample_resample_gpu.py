@@ -1,0 +1,203 @@
+"""K2 / K3 / K4 / K5 parity through the C ABI against the oracle, with externally supplied draws.
+Integers (particle indices, dead-particle bookkeeping) must be bit-exact; floats within 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import head as oh
+from oracle import resample as orr
+from pfpn_b200 import resampling, sampling, synth
+from pfpn_b200.distribution import MixtureGaussianDistribution
+from tests.test_oracle_resample import synth as rs_synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("B,A,P", [(2048, 36, 35), (300, 36, 100), (257, 36, 10), (5, 3, 7)])
+def test_plain_sample_indices_bit_exact(cuda_dev, B, A, P):
+    d = synth.head_inputs(B, A, P, seed=34114, far_frac=0.0)
+    g = torch.Generator().manual_seed(1)
+    u = torch.rand(B, A, dtype=torch.float64, generator=g)
+    eps = torch.randn(B, A, P, generator=g)
+    d["logits"][0, 0, :3] = float("-inf")  # non-finite logits carry no mass in TF's kernel
+    dist = oh.MixtureGaussianOracle(d["logits"], d["loc"], d["logstd"].exp(), False)
+    ref = dist.sample(1, uniform=u, normal=eps)[0]
+    cu = lambda t: t.to(cuda_dev)
+    act, idx = sampling.sample_plain(cu(d["logits"]), cu(d["loc"]), cu(d["logstd"]), ext_uniform=cu(u), ext_normal=cu(eps))
+    assert torch.equal(idx.cpu().long(), dist.dis_action)
+    assert rel(act, ref) < 1e-6
+    # the reference-facing object
+    gd = MixtureGaussianDistribution(cu(d["logits"]), cu(d["loc"]), cu(d["logstd"]).exp(), False, logstd=cu(d["logstd"]))
+    s = gd.sample(1, ext_uniform=cu(u), ext_normal=cu(eps))
+    assert s.shape == (1, B, A) and torch.equal(s[0], act) and torch.equal(gd.dis_action, idx)
+
+
+def test_plain_sample_philox_is_distributed_like_the_mixture(cuda_dev):
+    B, A, P = 200000, 2, 5
+    logits = torch.tensor([[0.0, 1.0, 2.0, -1.0, 0.5], [3.0, 0.0, 0.0, 0.0, -2.0]]).repeat(B, 1, 1).contiguous()
+    loc, logstd = synth.particle_grid(A, P, torch.Generator().manual_seed(0))
+    cu = lambda t: t.to(cuda_dev)
+    act, idx = sampling.sample_plain(cu(logits), cu(loc), cu(logstd), seed=123, offset=7)
+    act2, idx2 = sampling.sample_plain(cu(logits), cu(loc), cu(logstd), seed=123, offset=7)
+    assert torch.equal(idx, idx2) and torch.equal(act, act2)  # counter-based: reproducible
+    _, idx3 = sampling.sample_plain(cu(logits), cu(loc), cu(logstd), seed=123, offset=8)
+    assert not torch.equal(idx, idx3)
+    freq = torch.stack([torch.bincount(idx[:, a].long().cpu(), minlength=P) for a in range(A)]).double() / B
+    assert (freq - torch.softmax(logits[0].double(), -1)).abs().max() < 5e-3
+    z = (act.cpu() - loc.expand(B, A, P).gather(2, idx.cpu().long()[..., None])[..., 0]) / \
+        logstd.exp().expand(B, A, P).gather(2, idx.cpu().long()[..., None])[..., 0]
+    assert abs(float(z.mean())) < 1e-2 and abs(float(z.std()) - 1) < 1e-2
+
+
+@pytest.mark.parametrize("B,A,P", [(1024, 36, 100), (300, 36, 35), (7, 4, 10)])
+def test_rsample_forward_backward(cuda_dev, B, A, P):
+    g = torch.Generator().manual_seed(12831)
+    logits = torch.randn(B, A, P, generator=g) * 2
+    loc_np, logstd_np = oh.init_particles(A, P, tanh=True)
+    loc = torch.tensor(loc_np, dtype=torch.float32)
+    logstd = torch.tensor(logstd_np, dtype=torch.float32)
+    U = torch.rand(B, A, P, generator=g).clamp_min(oh.F32_TINY)
+    eps = torch.randn(B, A, P, generator=g)
+    g_a = torch.randn(B, A, generator=g)
+    g_u = torch.randn(B, A, generator=g) * 0.3
+    lg = logits.double().requires_grad_(True)
+    lc = loc.double().requires_grad_(True)
+    ls = logstd.double().requires_grad_(True)
+    dist = oh.MixtureGaussianOracle(lg, lc, ls.exp(), True)
+    sample, s_ = dist.sample(1, uniform=U.double(), normal=eps.double())
+    (sample[0] * g_a.double()).sum().backward(retain_graph=True)
+    (s_[0] * g_u.double()).sum().backward()
+    cu = lambda t: t.to(cuda_dev)
+    ext = dict(ext_uniform=cu(U), ext_normal=cu(eps))
+    smp, spre, idx = sampling.rsample_fwd(cu(logits), cu(loc), cu(logstd), **ext)
+    assert torch.equal(idx.cpu().long(), dist.dis_action)
+    assert rel(smp, sample[0]) < TOL and rel(spre, s_[0]) < TOL
+    dl, dc, ds = sampling.rsample_bwd(cu(logits), cu(loc), cu(logstd), cu(g_a), cu(g_u), **ext)
+    assert rel(dl, lg.grad) < TOL and rel(dc, lc.grad) < TOL and rel(ds, ls.grad) < TOL
+
+
+def test_sac_policy_gradient_through_the_distribution_object(cuda_dev):
+    """sample -> log_prob((sample, s_)) -> alpha*logp - q(sample): the composition of sac.py:128-130,166-173."""
+    B, A, P = 256, 36, 35
+    g = torch.Generator().manual_seed(5)
+    logits = torch.randn(B, A, P, generator=g) * 2
+    loc_np, logstd_np = oh.init_particles(A, P, tanh=True)
+    loc, logstd = torch.tensor(loc_np, dtype=torch.float32), torch.tensor(logstd_np, dtype=torch.float32)
+    U = torch.rand(B, A, P, generator=g).clamp_min(oh.F32_TINY)
+    eps = torch.randn(B, A, P, generator=g)
+    qw = torch.randn(A, generator=g)
+
+    def run(mod, lg, lc, ls, to):
+        if mod is oh.MixtureGaussianOracle:
+            dist = mod(lg, lc, ls.exp(), True)
+            smp, s_ = dist.sample(1, uniform=to(U), normal=to(eps))
+        else:
+            dist = mod(lg, lc, ls.exp(), True, logstd=ls)
+            smp, s_ = dist.sample(1, ext_uniform=to(U), ext_normal=to(eps))
+        smp, s_ = smp[0], s_[0]
+        logp = dist.log_prob((smp, s_))
+        loss = (0.2 * logp - (smp * to(qw)).sum(1)).mean()
+        loss.backward()
+        return logp
+
+    a64 = [t.double().requires_grad_(True) for t in (logits, loc, logstd)]
+    lp_ref = run(oh.MixtureGaussianOracle, *a64, lambda t: t.double())
+    agpu = [t.to(cuda_dev).requires_grad_(True) for t in (logits, loc, logstd)]
+    lp = run(MixtureGaussianDistribution, *agpu, lambda t: t.to(cuda_dev))
+    assert rel(lp, lp_ref) < TOL
+    for x, r in zip(agpu, a64):
+        assert rel(x.grad, r.grad) < TOL
+
+
+def test_mean_action(cuda_dev):
+    d = synth.head_inputs(500, 36, 35, seed=3, far_frac=0.0)
+    cu = lambda t: t.to(cuda_dev)
+    for tanh in (False, True):
+        ref = oh.MixtureGaussianOracle(d["logits"], d["loc"], d["logstd"].exp(), tanh).mean()
+        act, idx = sampling.mean_action(cu(d["logits"]), cu(d["loc"]), tanh=tanh)
+        assert torch.equal(idx.cpu().long(), d["logits"].argmax(-1))
+        assert rel(act, ref) < 1e-6
+
+
+def test_activity_statistics(cuda_dev):
+    d = synth.head_inputs(4096, 36, 35, seed=9, far_frac=0.0)
+    probs = torch.softmax(d["logits"].double(), -1)
+    mx0 = torch.rand(36, 35) * 0.05
+    sm0 = torch.rand(36, 35)
+    ref_max, ref_sum = orr.activity_stats(probs.numpy(), mx0.numpy(), sm0.numpy())
+    mx, sm = mx0.to(cuda_dev), sm0.to(cuda_dev)
+    p = sampling.stats_update(d["logits"].to(cuda_dev), mx, sm, want_probs=True)
+    assert rel(p, probs) < 1e-6
+    assert rel(mx, torch.maximum(mx0.double(), probs.max(0).values)) < 1e-6
+    assert rel(sm, sm0.double() + probs.sum(0)) < 1e-5
+    assert rel(mx, ref_max) < 1e-6 and rel(sm, ref_sum) < 1e-4
+    gd = MixtureGaussianDistribution(d["logits"].to(cuda_dev), d["loc"].to(cuda_dev), d["logstd"].exp().to(cuda_dev), False)
+    assert rel(gd.dis_dist.probs, probs) < 1e-6
+
+
+INT_KEYS = ("invalid", "src", "col", "tcol", "idx")
+
+
+def _run_resample(cuda_dev, t, d, **kw):
+    ref, ints = orr.resample(**t, **d, **kw)
+    g = {k: torch.tensor(v).to(cuda_dev) for k, v in t.items()}
+    out = resampling.resample_(g["max_active"], g["sum_active"], g["loc"], g["logstd"], g["bias"], g["weight"],
+                               ext_cat_u=torch.tensor(d["cat_u"]).to(cuda_dev),
+                               ext_choice=torch.tensor(d["choice"]).to(cuda_dev),
+                               ext_noise_u=torch.tensor(d["noise_u"]).to(cuda_dev), verify=True, **kw)
+    M = int(out["M"].item())
+    assert M == ints["M"]
+    assert np.array_equal(out["cand"].cpu().numpy(), ints["cand"])
+    for k in INT_KEYS:
+        assert np.array_equal(out[k].cpu().numpy()[:M], ints[k]), k
+    nu = int(out["nuniq"].item())
+    assert nu == len(ints["uniq"])
+    for k in ("uniq", "count", "delta"):
+        assert np.array_equal(out[k].cpu().numpy()[:nu], ints[k]), k
+    for k in ("loc", "logstd", "bias", "weight", "max_active", "sum_active"):
+        assert np.allclose(g[k].cpu().numpy(), ref[k], rtol=1e-5, atol=1e-6), k  # floats: tolerance; ints above: exact
+    return M
+
+
+@pytest.mark.parametrize("P", [10, 35, 100])
+@pytest.mark.parametrize("dead_frac,all_but_one", [(0.0, False), (0.03, False), (0.1, False), (0.5, False), (1.0, True)])
+def test_resample_sweep_bit_exact(cuda_dev, P, dead_frac, all_but_one):
+    """BASELINE config c3: P = 10/35/100, A = 36, dead fraction sweep."""
+    t, d, dead = rs_synth(A=36, P=P, H=512, dead_frac=dead_frac, all_but_one=all_but_one, seed=33406 + P)
+    M = _run_resample(cuda_dev, t, d, resample=-1)
+    assert M == int(dead.sum())
+
+
+def test_resample_tanh_and_topk(cuda_dev):
+    t, d, _ = rs_synth(A=36, P=35, H=64, dead_frac=0.2)
+    _run_resample(cuda_dev, t, d, resample=-1, tanh=True)
+    _run_resample(cuda_dev, t, d, resample=3)
+
+
+def test_resample_dead_source_case(cuda_dev):
+    t, d, _ = rs_synth(A=2, P=6, H=4, dead_frac=0.0)
+    t["max_active"][0, 1] = 1e-6
+    t["max_active"][0, 4] = 1e-6
+    t["sum_active"][0, :] = np.array([0, 1, 0, 0, 0, 0], np.float32) + 1e-12
+    assert _run_resample(cuda_dev, t, d, resample=-1) == 2
+
+
+def test_resample_philox_mode_is_replica_deterministic(cuda_dev):
+    """every rank runs the resampler redundantly from the same seed -> identical results."""
+    t, d, _ = rs_synth(A=36, P=35, H=512, dead_frac=0.2)
+    outs = []
+    for _ in range(2):
+        g = {k: torch.tensor(v).to(cuda_dev) for k, v in t.items()}
+        o = resampling.resample_(g["max_active"], g["sum_active"], g["loc"], g["logstd"], g["bias"], g["weight"],
+                                 seed=33407, offset=368, verify=True)
+        outs.append((g, o))
+    for k in ("loc", "logstd", "bias", "weight"):
+        assert torch.equal(outs[0][0][k], outs[1][0][k])
+    assert torch.equal(outs[0][1]["src"], outs[1][1]["src"])
