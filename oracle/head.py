@@ -275,6 +275,15 @@ def ppo_policy_loss(lp, lp_old, adv_n, eps=0.2):
     return -torch.mean(torch.minimum(surrogate, clipped))
 
 
+def sac_policy_loss(logp, q_min, log_alpha, A):
+    """sac.py:166-173: mean(alpha*logp - min(Q1,Q2) - log_alpha * sg(logp + target_entropy)),
+    alpha = sg(exp(log_alpha)) (sac.py:38), target_entropy = -A (sac.py:170)."""
+    alpha = torch.exp(log_alpha).detach()
+    l = alpha * logp - q_min
+    l = l - log_alpha * (logp + (-A)).detach()
+    return torch.mean(l)
+
+
 def ppo_head_fwd_bwd(logits, loc, logstd, action, adv, lp_old, *, eps=0.2,
                      entropy_beta=0.0, normalize_adv=True, tanh=False, dtype=torch.float64):
     """One fused-K1 worth of reference work: log_prob, entropy, PPO surrogate
