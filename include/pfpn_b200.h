@@ -201,6 +201,52 @@ int pfpn_resample_workspace_bytes(int32_t A, int32_t P, int32_t H, size_t* bytes
 int pfpn_resample(const pfpn_resample_args* args, void* workspace, size_t workspace_bytes,
                   pfpn_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * K6  dense layers of the 1024-512 trunk (fp32 FFMA anchor path).
+ * Replaces: fc_layer                         networks/ops.py:82-118
+ *           build_conv_fc_net                networks/utils.py:17-43
+ *           and the MatMul_grad / Relu6Grad nodes tf.gradients derives from them.
+ * Row-major fp32; every leading dimension and every contiguous extent (K, N) must be a
+ * multiple of 4, except N == 1 (critic/fc3) which has dedicated paths.
+ * ---------------------------------------------------------------------- */
+/* Y[M,N] = act(X[M,K] W[K,N] + b[N]), act = relu6 if `relu6` else identity */
+int pfpn_mlp_linear_fwd(const float* X, int32_t ldx, const float* W, const float* b, float* Y, int32_t ldy,
+                        int32_t M, int32_t K, int32_t N, int32_t relu6, pfpn_stream_t stream);
+/* dX[M,K] = (dY[M,N] W[K,N]^T) .* 1[0 < Hin < 6]   (Hin = forward output of the previous layer, NULL: no mask) */
+int pfpn_mlp_linear_bwd_input(const float* dY, int32_t ldy, const float* W, const float* Hin, float* dX,
+                              int32_t ldx, int32_t M, int32_t K, int32_t N, pfpn_stream_t stream);
+/* dW[K,N] = X[M,K]^T dY[M,N], db[N] = column sums of dY; deterministic split-K over the batch */
+int pfpn_mlp_wgrad_workspace_bytes(int32_t M, int32_t K, int32_t N, size_t* bytes);
+int pfpn_mlp_linear_bwd_weight(const float* X, int32_t ldx, const float* dY, int32_t ldy, float* dW, float* db,
+                               int32_t M, int32_t K, int32_t N, void* workspace, size_t workspace_bytes,
+                               pfpn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Learner-update element-wise pieces and K7 (clip + Adam).
+ * ---------------------------------------------------------------------- */
+/* out[B, ldo] = clip((state - mean) / std, +-clip), zero padded beyond S.
+ * Replaces: build_state_normalizer_op        networks/actor_critic/actor_critic.py:223-244 */
+int pfpn_state_normalize(const float* state, const float* mean, const float* std, float* out, int32_t B,
+                         int32_t S, int32_t ldo, float clip, int32_t normalize, pfpn_stream_t stream);
+/* Moving-average update of the state statistics over a minibatch; scratch = 2*S floats.
+ * Replaces: online_normalizer(moving_average=True)   networks/utils.py:60-68 */
+int pfpn_normalizer_update(const float* state, float* mean, float* std, int32_t B, int32_t S, float step,
+                           float* scratch, pfpn_stream_t stream);
+/* loss[0] = scale * sum((v - (adv + v_old))^2); dv = coef * 2 (v - target) * scale  (scale = 1/B).
+ * Replaces: ClipPPONetwork.build_value_loss / setup_value_target_tensor   ppo.py:31-42 */
+int pfpn_value_loss(const float* v, const float* adv, const float* v_old, float* dv, float* loss, int32_t B,
+                    float coef, float scale, pfpn_stream_t stream);
+/* grads *= clip * min(1/||grads||, 1/clip) (NaN if the norm is not finite); norm_scale = {norm, scale};
+ * clip <= 0 only computes the norm.  scratch >= 296 doubles.
+ * Replaces: clip_grads -> tf.clip_by_global_norm      models/workers/base_worker.py:97-102 */
+int pfpn_clip_by_global_norm(float* grads, size_t n, float clip, float* norm_scale, void* scratch,
+                             size_t scratch_bytes, pfpn_stream_t stream);
+/* TF AdamOptimizer step `step` (1-based) on a flat parameter buffer; the gradient is read as
+ * grads * grad_scale (1/N after a sum all-reduce over N ranks).
+ * Replaces: build_optimizer -> tf.train.AdamOptimizer  models/workers/base_worker.py:64-70 */
+int pfpn_adam_step(float* params, const float* grads, float* m, float* v, size_t n, float lr, float beta1,
+                   float beta2, float eps, int64_t step, float grad_scale, pfpn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,3 +128,19 @@ pfpn_stats_update = _sig("pfpn_stats_update", C.c_int, [C.c_void_p, C.c_void_p, 
 pfpn_resample_workspace_bytes = _sig("pfpn_resample_workspace_bytes", C.c_int,
                                      [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)])
 pfpn_resample = _sig("pfpn_resample", C.c_int, [C.POINTER(ResampleArgs), C.c_void_p, C.c_size_t, C.c_void_p])
+
+
+# ---- K6 / K7 ---------------------------------------------------------------------------------------
+_vp, _i32, _f = C.c_void_p, C.c_int32, C.c_float
+pfpn_mlp_linear_fwd = _sig("pfpn_mlp_linear_fwd", C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp])
+pfpn_mlp_linear_bwd_input = _sig("pfpn_mlp_linear_bwd_input", C.c_int,
+                                 [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp])
+pfpn_mlp_wgrad_workspace_bytes = _sig("pfpn_mlp_wgrad_workspace_bytes", C.c_int,
+                                      [_i32, _i32, _i32, C.POINTER(C.c_size_t)])
+pfpn_mlp_linear_bwd_weight = _sig("pfpn_mlp_linear_bwd_weight", C.c_int,
+                                  [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, C.c_size_t, _vp])
+pfpn_state_normalize = _sig("pfpn_state_normalize", C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _f, _i32, _vp])
+pfpn_normalizer_update = _sig("pfpn_normalizer_update", C.c_int, [_vp, _vp, _vp, _i32, _i32, _f, _vp, _vp])
+pfpn_value_loss = _sig("pfpn_value_loss", C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _f, _f, _vp])
+pfpn_clip_by_global_norm = _sig("pfpn_clip_by_global_norm", C.c_int, [_vp, C.c_size_t, _f, _vp, _vp, C.c_size_t, _vp])
+pfpn_adam_step = _sig("pfpn_adam_step", C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _f, _f, _f, _f, C.c_int64, _f, _vp])

@@ -1,0 +1,198 @@
+// K7 and the small element-wise pieces of the learner update.
+//
+//  * state normaliser + clip              actor_critic.py:223-244  ((s - mean) / std, clip +-5)
+//  * moving-average statistics update     networks/utils.py:60-68
+//  * PPO value loss and its gradient      ppo.py:31-42, actor_critic.py:128-136
+//  * clip_by_global_norm                  workers/base_worker.py:97-102 (TF semantics, [graph])
+//  * Adam                                 workers/base_worker.py:64-70  (TF AdamOptimizer)
+// Every reduction is two-stage with a fixed order, so the update is bit-reproducible.
+#include "common.cuh"
+
+namespace pfpn {
+
+// x[b, 0:S] = clip((s - mean) / std, -c, c); columns S..ldo-1 are zero padding (GEMM K % 4 == 0)
+__global__ void state_normalize_kernel(const float* __restrict__ s, const float* __restrict__ mean,
+                                       const float* __restrict__ std, float* __restrict__ out, int B, int S, int ldo,
+                                       float clip, int normalize) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * ldo) return;
+  const int b = (int)(i / ldo), k = (int)(i % ldo);
+  float v = 0.f;
+  if (k < S) {
+    v = s[(size_t)b * S + k];
+    if (normalize) v = (v - mean[k]) / std[k];
+    if (clip > 0.f) v = fminf(fmaxf(v, -clip), clip);
+  }
+  out[i] = v;
+}
+
+// column mean / population variance of X[B,S] (tf.nn.moments: mean, then mean of squared differences)
+__global__ void __launch_bounds__(256) col_moments_kernel(const float* __restrict__ X, int B, int S,
+                                                          float* __restrict__ mean_out, float* __restrict__ var_out) {
+  const int k = blockIdx.x;
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int b = threadIdx.x; b < B; b += 256) s += X[(size_t)b * S + k];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double mean = sh[0] / B;
+  __syncthreads();
+  double q = 0.0;
+  for (int b = threadIdx.x; b < B; b += 256) {
+    const double d = X[(size_t)b * S + k] - mean;
+    q += d * d;
+  }
+  sh[threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    mean_out[k] = (float)mean;
+    var_out[k] = (float)(sh[0] / B);
+  }
+}
+// utils.py:60-68: decay = min(0.9999, (1+step)/(10+step)); mean/std moving averages, std >= 1e-6
+__global__ void normalizer_update_kernel(float* __restrict__ mean, float* __restrict__ std, const float* __restrict__ m,
+                                         const float* __restrict__ v, int S, float step) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= S) return;
+  const float decay = fminf(0.9999f, (1.f + step) / (10.f + step));
+  mean[k] = decay * mean[k] + (1.f - decay) * m[k];
+  std[k] = fmaxf(1e-6f, decay * std[k] + (1.f - decay) * sqrtf(v[k]));
+}
+
+// value loss: mean((v - sg(adv + v_old))^2); dv = coef * 2 (v - target) * scale; one CTA
+__global__ void __launch_bounds__(1024) value_loss_kernel(const float* __restrict__ v, const float* __restrict__ adv,
+                                                          const float* __restrict__ v_old, float* __restrict__ dv,
+                                                          float* __restrict__ loss, int B, float coef, float scale) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < B; i += 1024) {
+    const float d = v[i] - (adv[i] + v_old[i]);
+    s += (double)d * d;
+    dv[i] = coef * 2.f * d * scale;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 32; ++w) t += sh[w];
+    *loss = (float)(t * scale);  // un-weighted value loss (the reference reports it before * coef)
+  }
+}
+
+constexpr int kNormBlocks = 296;
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, size_t n, double* __restrict__ part) {
+  __shared__ double sh[8];
+  double s = 0.0;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const double x = g[i];
+    s += x * x;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    part[blockIdx.x] = t;
+  }
+}
+// out[0] = global norm, out[1] = scale = clip * min(1/norm, 1/clip), NaN when the norm is not finite
+__global__ void norm_finalize_kernel(const double* __restrict__ part, int nparts, float clip, float* __restrict__ out) {
+  double t = 0.0;
+  for (int i = 0; i < nparts; ++i) t += part[i];
+  const float norm = (float)sqrt(t);
+  out[0] = norm;
+  float scale = 1.f;
+  if (clip > 0.f) scale = isfinite(norm) ? clip * fminf(1.f / norm, 1.f / clip) : __int_as_float(0x7fc00000);
+  out[1] = scale;
+}
+__global__ void scale_kernel(float* __restrict__ g, size_t n, const float* __restrict__ norm_scale) {
+  const float s = norm_scale[1];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) g[i] *= s;
+}
+// TF AdamOptimizer: lr_t = lr sqrt(1-b2^t)/(1-b1^t); m,v moving averages; p -= lr_t m / (sqrt(v) + eps)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            size_t n, float lr_t, float b1, float b2, float eps, float gscale) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+}  // namespace pfpn
+
+using namespace pfpn;
+
+extern "C" int pfpn_state_normalize(const float* state, const float* mean, const float* std, float* out, int32_t B,
+                                    int32_t S, int32_t ldo, float clip, int32_t normalize, pfpn_stream_t stream_) {
+  if (!state || !out || B < 0 || S <= 0 || ldo < S) return PFPN_ERR_ARG;
+  if (normalize && (!mean || !std)) return PFPN_ERR_ARG;
+  if (B == 0) return PFPN_OK;
+  const size_t n = (size_t)B * ldo;
+  state_normalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      state, mean, std, out, B, S, ldo, clip, normalize);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}
+
+// scratch: 2*S floats
+extern "C" int pfpn_normalizer_update(const float* state, float* mean, float* std, int32_t B, int32_t S, float step,
+                                      float* scratch, pfpn_stream_t stream_) {
+  if (!state || !mean || !std || !scratch || B <= 0 || S <= 0) return PFPN_ERR_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  col_moments_kernel<<<S, 256, 0, st>>>(state, B, S, scratch, scratch + S);
+  PFPN_CUDA_OK(cudaGetLastError());
+  normalizer_update_kernel<<<(S + 255) / 256, 256, 0, st>>>(mean, std, scratch, scratch + S, S, step);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}
+
+extern "C" int pfpn_value_loss(const float* v, const float* adv, const float* v_old, float* dv, float* loss, int32_t B,
+                               float coef, float scale, pfpn_stream_t stream_) {
+  if (!v || !adv || !v_old || !dv || !loss || B <= 0) return PFPN_ERR_ARG;
+  value_loss_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(v, adv, v_old, dv, loss, B, coef, scale);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}
+
+// norm_scale[2] = {global norm, applied scale}; scratch: kNormBlocks doubles.  In place on `grads`.
+extern "C" int pfpn_clip_by_global_norm(float* grads, size_t n, float clip, float* norm_scale, void* scratch,
+                                        size_t scratch_bytes, pfpn_stream_t stream_) {
+  if (!grads || !norm_scale || !scratch || n == 0) return PFPN_ERR_ARG;
+  if (scratch_bytes < kNormBlocks * sizeof(double)) return PFPN_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(scratch) & 7u) return PFPN_ERR_ALIGN;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  double* part = reinterpret_cast<double*>(scratch);
+  sumsq_partial_kernel<<<kNormBlocks, 256, 0, st>>>(grads, n, part);
+  PFPN_CUDA_OK(cudaGetLastError());
+  norm_finalize_kernel<<<1, 1, 0, st>>>(part, kNormBlocks, clip, norm_scale);
+  PFPN_CUDA_OK(cudaGetLastError());
+  if (clip > 0.f) {
+    scale_kernel<<<kNormBlocks, 256, 0, st>>>(grads, n, norm_scale);
+    PFPN_CUDA_OK(cudaGetLastError());
+  }
+  return PFPN_OK;
+}
+
+extern "C" int pfpn_adam_step(float* params, const float* grads, float* m, float* v, size_t n, float lr, float beta1,
+                              float beta2, float eps, int64_t step, float grad_scale, pfpn_stream_t stream_) {
+  if (!params || !grads || !m || !v || n == 0 || step < 1) return PFPN_ERR_ARG;
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
+  adam_kernel<<<kNormBlocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(params, grads, m, v, n, (float)lr_t, beta1,
+                                                                                 beta2, eps, grad_scale);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}

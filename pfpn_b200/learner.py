@@ -1,0 +1,116 @@
+"""Data-parallel learner update: the B200 replacement of the reference's synchronous
+parameter-server step (/root/reference/models/sync_model.py:60-101 +
+models/workers/base_worker.py:25-120).
+
+Reference order of operations ([graph]): per worker tf.gradients -> LOCAL
+clip_by_global_norm -> accumulator MEAN over workers of the clipped gradients and of the pushed
+statistics (state mean/std, max/sum_active: averaged, not max-reduced) -> assign statistics ->
+Adam -> train_flag tick / resample.  Here the weights are replicated on every GPU, one process per
+GPU, and the accumulator is ONE NCCL all-reduce over NVLink of the flat bucket
+[gradients | statistics]; Adam then runs identically on every rank, so no broadcast is needed.
+
+The collective plumbing below is device-agnostic torch.distributed code (covered by world-size-2
+gloo tests on CPU); the arithmetic is CUDA kernels behind the C ABI.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+from .head import _stream_ptr
+
+
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous, balanced split of n minibatch rows (B/N rows per rank)."""
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_mean_(bucket: torch.Tensor, group=None) -> float:
+    """Sum all-reduce of the flat bucket in place; returns the 1/N factor the caller still has to
+    apply (the Adam kernel folds it into its gradient read)."""
+    _, n = world()
+    if n > 1:
+        dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / n
+
+
+class SyncReplicasAdam:
+    """`SyncReplicasOptimizer(AdamOptimizer(lr), replicas_to_aggregate=N)` + clip_grads, for one
+    network whose parameters / gradients are flat buffers (pfpn_b200.network)."""
+
+    def __init__(self, lr: float = 1e-4, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
+                 norm_clip: Optional[float] = 1.0, group=None):
+        self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
+        self.norm_clip = float(norm_clip) if norm_clip else 0.0
+        self.group = group
+        self.step = 0
+        self.m = self.v = None
+        self.norm_scale = None
+        self._scratch = None
+
+    def _lazy(self, net):
+        if self.m is None:
+            self.m = torch.zeros_like(net.params)
+            self.v = torch.zeros_like(net.params)
+            self.norm_scale = torch.zeros(2, dtype=torch.float32, device=net.params.device)
+            self._scratch = torch.empty(296 * 8, dtype=torch.uint8, device=net.params.device)
+
+    def pack_stats(self, net):
+        """Statistics pushed through the same accumulators as the gradients (sync_model.py:37-45)."""
+        n, S, AP = net.n_params, net.S, net.A * net.P
+        tail = net.bucket[n:]
+        if net.normalize_state:
+            tail[0:S].copy_(net._new_mean)
+            tail[S:2 * S].copy_(net._new_std)
+        tail[2 * S:2 * S + AP].copy_(net.max_active.reshape(-1))
+        tail[2 * S + AP:2 * S + 2 * AP].copy_(net.sum_active.reshape(-1))
+
+    def unpack_stats(self, net, inv_n: float):
+        n, S, AP = net.n_params, net.S, net.A * net.P
+        tail = net.bucket[n:]
+        if inv_n != 1.0:
+            tail.mul_(inv_n)
+        if net.normalize_state:
+            net.state_mean.copy_(tail[0:S])
+            net.state_std.copy_(tail[S:2 * S])
+        net.max_active.copy_(tail[2 * S:2 * S + AP].view_as(net.max_active))
+        net.sum_active.copy_(tail[2 * S + AP:2 * S + 2 * AP].view_as(net.sum_active))
+
+    def apply_gradients(self, net):
+        self._lazy(net)
+        st = _stream_ptr()
+        # 1. local clip (before aggregation: optimizer/clip_by_global_norm/mul_* feed the accumulators)
+        _cabi.check(_cabi.pfpn_clip_by_global_norm(net.grads.data_ptr(), net.n_params, self.norm_clip,
+                                                   self.norm_scale.data_ptr(), self._scratch.data_ptr(),
+                                                   self._scratch.numel(), st))
+        # 2-4. one all-reduce of [clipped gradients | statistics], mean, assign statistics
+        self.pack_stats(net)
+        inv_n = allreduce_mean_(net.bucket, self.group)
+        self.unpack_stats(net, inv_n)
+        # 5. Adam (identical on every rank -> replicas stay bit-identical)
+        self.step += 1
+        _cabi.check(_cabi.pfpn_adam_step(net.params.data_ptr(), net.grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                         net.n_params, self.lr, self.beta1, self.beta2, self.eps, self.step, inv_n, st))
+        net.global_step += 1
+        # 6. train_ops chained after the optimizer step (sync_model.py:79-81): resample tick
+        for op in net.train_ops:
+            op()
+
+    def state_dict(self):
+        return dict(step=self.step, m=None if self.m is None else self.m.clone(), v=None if self.v is None else self.v.clone())
+
+    def load_state_dict(self, sd):
+        self.step = int(sd["step"])
+        if sd["m"] is not None:
+            self.m, self.v = sd["m"].clone(), sd["v"].clone()

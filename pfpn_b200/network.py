@@ -1,0 +1,354 @@
+"""Drop-in for the reference's ``ParticleFilteringClipPPONetwork`` on the learner-update path
+(/root/reference/networks/actor_critic/{actor_critic,a2c,ppo}.py), eager instead of a TF graph.
+
+Same constructor keywords, ``init()``, ``run`` / ``evaluate`` / ``train`` signatures and return
+conventions (``sess`` / ``ops`` are ignorable handles; ``optimizer`` is a
+``pfpn_b200.learner.SyncReplicasAdam``).  All parameters live in ONE flat fp32 buffer in the
+reference's variable order, all gradients in one flat bucket that also carries the pushed
+statistics, so the data-parallel exchange is a single all-reduce.
+
+Compute = hand-written CUDA behind the C ABI (K1 head, K2 sampling, K4 statistics, K5 resampling,
+K6 trunk GEMMs); torch is the allocator and the stream provider.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+from . import head as _head
+from . import resampling as _resampling
+from . import sampling as _sampling
+from .head import _stream_ptr
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+class _Linear:
+    """fc_layer (ops.py:82-118): W [in, out] row-major + b, views into the flat buffers."""
+
+    def __init__(self, name, k_in, n_out, k_pad=None):
+        self.name, self.k_in, self.n_out = name, k_in, n_out
+        self.k = k_pad or k_in  # rows of the stored W (zero rows beyond k_in)
+        self.W = self.b = self.dW = self.db = None
+
+    def numel(self):
+        return self.k * self.n_out + self.n_out
+
+
+class ParticleFilteringClipPPONetwork:
+    GLOBAL_STEP0 = 0
+
+    def __init__(self, trainable, state_shape, action_shape, action_lower_bound=None, action_upper_bound=None,
+                 init_sigma=None, fixed_sigma=False, particles=50, resample=3, resample_interval=2000,
+                 resample_threshold=None, normalize_policy_output=False, epsilon=0.2,
+                 common_net_shape=(), critic_net_shape=(1024, 512), actor_net_shape=(1024, 512),
+                 weight_initializer=None, activator="relu6", normalize_state=False, clip_state=False,
+                 normalize_value=False, clip_value=False, normalize_advantage=False, clip_advantage=False,
+                 critic_regularizer=None, actor_regularizer=None, entropy_beta=None, value_loss_coef=0.5,
+                 gamma=0.99, lambd=0.95, log=True, device="cuda", seed=0, **kwargs):
+        if common_net_shape:
+            raise NotImplementedError("common_net_shape is [] in every shipped setting (deepmimic_base.py:4-6)")
+        if fixed_sigma or init_sigma:
+            raise NotImplementedError("fixed_sigma / init_sigma are not used by the shipped PFPN settings")
+        if normalize_value or clip_value or clip_advantage or critic_regularizer or actor_regularizer:
+            raise NotImplementedError("value normaliser / regularisers are off in every shipped setting")
+        if activator not in ("relu6",) and getattr(activator, "__name__", "") != "relu6":
+            raise NotImplementedError("only relu6 (deepmimic_base.py:8)")
+        self.trainable = bool(trainable)
+        self.random_action = self.trainable
+        self.state_shape = list(state_shape) if hasattr(state_shape, "__len__") else [state_shape]
+        self.action_shape = list(action_shape) if hasattr(action_shape, "__len__") else [action_shape]
+        if len(self.action_shape) != 1:
+            raise ValueError("Particle Filtering Policy Network only supports continuous action space.")
+        self.S, self.A, self.P = int(self.state_shape[0]), int(self.action_shape[0]), int(particles)
+        self.dis_action_shape = [self.P] * self.A
+        self.action_lower_bound, self.action_upper_bound = action_lower_bound, action_upper_bound
+        self.resample, self.resample_interval, self.resample_threshold = resample, resample_interval, resample_threshold
+        self.normalize_policy_output = False              # a2c.py:327
+        self.normalize_policy_output_ = bool(normalize_policy_output)  # a2c.py:328
+        self.epsilon = epsilon
+        self.actor_net_shape, self.critic_net_shape = list(actor_net_shape), list(critic_net_shape)
+        self.normalize_state, self.clip_state = bool(normalize_state), float(clip_state or 0.0)
+        self.normalize_advantage = bool(normalize_advantage)
+        self.entropy_beta, self.value_loss_coef = entropy_beta, value_loss_coef
+        self.gamma, self.gae_gamma = gamma, None if lambd is None else gamma * lambd
+        self.device = torch.device(device)
+        self.seed = int(seed)
+        self.init_ops, self.train_ops, self.running_update_ops = [], [], []
+        self.local_update_variables: List[torch.Tensor] = []
+        self.global_step = self.GLOBAL_STEP0
+        self._rng_offset = 0
+        self._act = {}
+
+    # ------------------------------------------------------------------------------ build ----
+    def init(self):
+        S, A, P, dev = self.S, self.A, self.P, self.device
+        self.Sp = _pad4(S)
+        dims_a = [self.Sp] + self.actor_net_shape
+        dims_c = [self.Sp] + self.critic_net_shape
+        self.actor = [_Linear(f"actor/fc{i+1}", (S if i == 0 else dims_a[i]), dims_a[i + 1], dims_a[i])
+                      for i in range(len(self.actor_net_shape))]
+        self.fc_policy = _Linear("actor/fc_policy", dims_a[-1], A * P)
+        self.critic = [_Linear(f"critic/fc{i+1}", (S if i == 0 else dims_c[i]), dims_c[i + 1], dims_c[i])
+                       for i in range(len(self.critic_net_shape))]
+        self.critic.append(_Linear(f"critic/fc{len(self.critic)+1}", dims_c[-1], 1))
+        # flat layout in the reference's variable order ([graph] / SURVEY 2.2 C1)
+        order = [("lin", l) for l in self.actor] + [("samples", None), ("samples_std", None), ("lin", self.fc_policy)] + \
+                [("lin", l) for l in self.critic]
+        self.n_stats = 2 * S + 2 * A * P
+        off = 0
+
+        def take(cnt, shape):
+            nonlocal off
+            assert off % 4 == 0, "every tensor starts 16-byte aligned"
+            p, g = self.params[off:off + cnt].view(*shape), self.grads[off:off + cnt].view(*shape)
+            off += _pad4(cnt)
+            return p, g
+
+        # (padding tensors to multiples of 4 floats keeps every view 16-byte aligned for the kernels)
+        self.n_params = n = _pad4(sum(_pad4(l.k * l.n_out) + _pad4(l.n_out) if k == "lin" else _pad4(A * P)
+                                      for k, l in order))
+        self.params = torch.zeros(n, dtype=torch.float32, device=dev)
+        # gradient bucket = [grads | pushed statistics] : one all-reduce (sync_model.py:92-96)
+        self.bucket = torch.zeros(n + _pad4(self.n_stats), dtype=torch.float32, device=dev)
+        self.grads = self.bucket[:n]
+        for kind, l in order:
+            if kind == "lin":
+                l.W, l.dW = take(l.k * l.n_out, (l.k, l.n_out))
+                l.b, l.db = take(l.n_out, (l.n_out,))
+            elif kind == "samples":
+                self.loc, self.dloc = take(A * P, (A, P))
+            else:
+                self.logstd, self.dlogstd = take(A * P, (A, P))
+        self.policy_weight, self.policy_bias = self.fc_policy.W, self.fc_policy.b  # a2c.py:546-551
+        self._init_values()
+        # non-trainable state (checkpointed / synchronised like the reference's local_update_variables)
+        self.state_mean = torch.zeros(S, dtype=torch.float32, device=dev)
+        self.state_std = torch.ones(S, dtype=torch.float32, device=dev)
+        self.max_active = torch.zeros(A, P, dtype=torch.float32, device=dev)
+        self.sum_active = torch.zeros(A, P, dtype=torch.float32, device=dev)
+        self.train_flag = 0
+        if self.normalize_state:
+            self.local_update_variables += [self.state_mean, self.state_std]   # actor_critic.py:333
+        if self.trainable and self.resample:
+            self.local_update_variables += [self.max_active, self.sum_active]  # a2c.py:362-363
+            self.train_ops.append(self.update)                                 # a2c.py:383
+        self._scratch = torch.empty(max(2 * S, 8), dtype=torch.float32, device=dev)
+        return self
+
+    def _init_values(self):
+        """a2c.py:476-535 particle grid (bounds forced to +-1) + truncated_normal(0, .01) weights."""
+        A, P = self.A, self.P
+        g = torch.Generator().manual_seed(self.seed)
+        if self.normalize_policy_output_:
+            assert P > 3
+            c = -1.0 + (2.0 / P) * (np.arange(P) + 0.5)
+            mu = np.arctanh(c)
+            sd = np.array([max(mu[j] - mu[max(0, j - 1)], mu[min(P - 1, j + 1)] - mu[j]) for j in range(P)])
+        else:
+            mu = -1.0 + 2.0 / (P - 1) * np.arange(P)
+            sd = np.full(P, 2.0 / (P - 1))
+        self.loc.copy_(torch.tensor(mu, dtype=torch.float32).repeat(A, 1))
+        self.logstd.copy_(torch.tensor(np.log(sd), dtype=torch.float32).repeat(A, 1))
+        for l in self.actor + [self.fc_policy] + self.critic:
+            w = torch.empty(l.k_in, l.n_out)
+            torch.nn.init.trunc_normal_(w, mean=0.0, std=0.01, a=-0.02, b=0.02, generator=g)
+            l.W.zero_()
+            l.W[:l.k_in].copy_(w)
+            l.b.zero_()
+
+    # ---------------------------------------------------------------------------- forward ----
+    def _buf(self, name, *shape):
+        t = self._act.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(*shape, dtype=torch.float32, device=self.device)
+            self._act[name] = t
+        return t
+
+    def _linear(self, l: _Linear, X, Y, relu6):
+        _cabi.check(_cabi.pfpn_mlp_linear_fwd(X.data_ptr(), X.stride(0), l.W.data_ptr(), l.b.data_ptr(), Y.data_ptr(),
+                                              Y.stride(0) if Y.dim() > 1 else 1, X.shape[0], l.k, l.n_out,
+                                              1 if relu6 else 0, _stream_ptr()))
+
+    def _forward(self, state: torch.Tensor, want_value=True):
+        B = state.shape[0]
+        x = self._buf("x", B, self.Sp)
+        _cabi.check(_cabi.pfpn_state_normalize(state.data_ptr(), self.state_mean.data_ptr(), self.state_std.data_ptr(),
+                                               x.data_ptr(), B, self.S, self.Sp, self.clip_state,
+                                               1 if self.normalize_state else 0, _stream_ptr()))
+        h = x
+        acts = [x]
+        for i, l in enumerate(self.actor):
+            y = self._buf(f"h{i}", B, l.n_out)
+            self._linear(l, h, y, True)
+            h = y
+            acts.append(y)
+        logits = self._buf("logits", B, self.A * self.P)
+        self._linear(self.fc_policy, h, logits, False)
+        value, cacts = None, [x]
+        if want_value:
+            h = x
+            for i, l in enumerate(self.critic[:-1]):
+                y = self._buf(f"c{i}", B, l.n_out)
+                self._linear(l, h, y, True)
+                h = y
+                cacts.append(y)
+            value = self._buf("value", B)
+            self._linear(self.critic[-1], h, value, False)
+        return logits.view(B, self.A, self.P), acts, value, cacts
+
+    def _dev_state(self, state):
+        t = torch.as_tensor(np.asarray(state, dtype=np.float32) if not torch.is_tensor(state) else state)
+        t = t.to(self.device, dtype=torch.float32, non_blocking=True)
+        return t.reshape(-1, self.S).contiguous()
+
+    # ---------------------------------------------------------------------- rollout side ----
+    def run_batch(self, state, ext_uniform=None, ext_normal=None):
+        """Vectorised ``run``: (action [B,A], log_prob [B], value [B]); updates the activity
+        statistics like the reference's running_update_ops do on every rollout step."""
+        s = self._dev_state(state)
+        logits, _, value, _ = self._forward(s)
+        if self.random_action:
+            if self.normalize_policy_output_:
+                smp, s_pre, _ = _sampling.rsample_fwd(logits, self.loc, self.logstd, seed=self.seed, offset=self._rng_offset,
+                                                      ext_uniform=ext_uniform, ext_normal=ext_normal)
+                action, val = smp, s_pre
+            else:
+                action, _ = _sampling.sample_plain(logits, self.loc, self.logstd, seed=self.seed, offset=self._rng_offset,
+                                                   ext_uniform=ext_uniform, ext_normal=ext_normal)
+                val = action
+            self._rng_offset += 2
+        else:
+            action, _ = _sampling.mean_action(logits, self.loc, tanh=self.normalize_policy_output_)
+            val = torch.atanh(action) if self.normalize_policy_output_ else action
+        out = _head.head_call(_cabi.HEAD_FWD, logits, self.loc, self.logstd, val, tanh=self.normalize_policy_output_)
+        if self.trainable and self.resample:
+            _sampling.stats_update(logits, self.max_active, self.sum_active)
+        return action, out["lp"], value.clone()
+
+    def run(self, sess, state, ops=None):
+        """ppo.py:56-62 + actor_critic.py:368-380: one state in, every output un-batched."""
+        a, lp, v = self.run_batch(np.asarray(state, dtype=np.float32)[None])
+        res = [a[0].cpu().numpy()]
+        if self.trainable:
+            res += [float(lp[0]), float(v[0])]
+        return res
+
+    def evaluate(self, sess, state):
+        """a2c.py:75-78."""
+        _, _, value, _ = self._forward(self._dev_state(np.asarray(state, dtype=np.float32)[None]))
+        return float(value[0])
+
+    # ------------------------------------------------------------------------ train step ----
+    def compute_gradients(self, state, action, value, log_prob, advantage, loss_scale: Optional[float] = None):
+        """Forward + backward of loss = policy_loss + value_loss_coef * value_loss on this rank's
+        minibatch (ppo.py:39-54, actor_critic.py:128-184); gradients land in ``self.grads``.
+        Returns device scalars (loss, entropy | None, policy_loss, value_loss)."""
+        s = self._dev_state(state)
+        B = s.shape[0]
+        dv = lambda t: torch.as_tensor(np.asarray(t, dtype=np.float32) if not torch.is_tensor(t) else t).to(
+            self.device, dtype=torch.float32).contiguous()
+        action, value_old, lp_old, adv = dv(action).reshape(B, self.A), dv(value).reshape(B), dv(log_prob).reshape(B), \
+            dv(advantage).reshape(B)
+        scale = loss_scale if loss_scale else 1.0 / B
+        # statistics pushed with this step (LocalUpdateHookPre, sync_model.py:123-138): computed from
+        # the pre-update values, applied by the optimizer after aggregation
+        if self.normalize_state:
+            self._new_mean, self._new_std = self.state_mean.clone(), self.state_std.clone()
+            _cabi.check(_cabi.pfpn_normalizer_update(s.data_ptr(), self._new_mean.data_ptr(), self._new_std.data_ptr(), B,
+                                                     self.S, float(self.global_step), self._scratch.data_ptr(), _stream_ptr()))
+        logits, acts, v, cacts = self._forward(s)
+        stats = _head.adv_stats(adv) if self.normalize_advantage else None
+        ent_scale = -float(self.entropy_beta) * scale if self.entropy_beta else 0.0
+        out = _head.head_call(_cabi.HEAD_PPO, logits, self.loc, self.logstd, action, tanh=self.normalize_policy_output_,
+                              adv=adv, lp_old=lp_old, adv_stats_t=stats, eps_clip=self.epsilon, loss_scale=scale,
+                              g_ent=ent_scale, dlogits_out=logits,
+                              out=dict(dloc=self.dloc, dlogstd=self.dlogstd, lp=self._buf("lp", B), ent=self._buf("ent", B),
+                                       loss=self._buf("ploss", 1)))
+        dlogits = logits.view(B, self.A * self.P)
+        dval, vloss = self._buf("dval", B), self._buf("vloss", 1)
+        _cabi.check(_cabi.pfpn_value_loss(v.data_ptr(), adv.data_ptr(), value_old.data_ptr(), dval.data_ptr(),
+                                          vloss.data_ptr(), B, float(self.value_loss_coef), scale, _stream_ptr()))
+        self._backward_stack(self.actor + [self.fc_policy], acts, dlogits)
+        self._backward_stack(self.critic, cacts, dval)
+        policy_loss = out["loss"][0]
+        entropy = None
+        if self.entropy_beta:
+            entropy = out["ent"].sum() * scale
+            policy_loss = policy_loss - self.entropy_beta * entropy
+        loss = policy_loss + self.value_loss_coef * vloss[0]
+        return loss, entropy, policy_loss, vloss[0]
+
+    def _backward_stack(self, layers: Sequence[_Linear], acts, dY):
+        """acts[i] is the input of layers[i]; dY is dL/d(output of the last layer)."""
+        st = _stream_ptr()
+        for i in range(len(layers) - 1, -1, -1):
+            l, X = layers[i], acts[i]
+            M = X.shape[0]
+            n = C.c_size_t(0)
+            _cabi.check(_cabi.pfpn_mlp_wgrad_workspace_bytes(M, l.k, l.n_out, C.byref(n)))
+            ws = self._ws(n.value)
+            ldy = dY.stride(0) if dY.dim() > 1 else 1
+            _cabi.check(_cabi.pfpn_mlp_linear_bwd_weight(X.data_ptr(), X.stride(0), dY.data_ptr(), ldy, l.dW.data_ptr(),
+                                                         l.db.data_ptr(), M, l.k, l.n_out, ws.data_ptr(), ws.numel(), st))
+            if i > 0:  # no gradient into the (stop_gradient) normalised state
+                dX = self._buf(f"d_{l.name}", M, l.k)
+                _cabi.check(_cabi.pfpn_mlp_linear_bwd_input(dY.data_ptr(), ldy, l.W.data_ptr(), X.data_ptr(), dX.data_ptr(),
+                                                            dX.stride(0), M, l.k, l.n_out, st))
+                dY = dX
+
+    def _ws(self, nbytes):
+        t = self._act.get("_ws")
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._act["_ws"] = t
+        return t
+
+    def train(self, sess, optimizer, ops, state, action, value, log_prob, advantage):
+        """ppo.py:64-72 -> actor_critic.py:382-404: ((loss, entropy|None, policy_loss, value_loss), extra)."""
+        scale = 1.0 / max(1, np.shape(advantage)[0])
+        losses = self.compute_gradients(state, action, value, log_prob, advantage, loss_scale=scale)
+        if optimizer is not None:
+            optimizer.apply_gradients(self)
+        extra = [] if not ops else [None] * (len(ops) if hasattr(ops, "__len__") else 1)
+        return tuple(None if x is None else float(x) for x in losses), extra
+
+    # ------------------------------------------------------------- resample tick (a2c.py:370-383) ----
+    def update(self):
+        self.train_flag += 1
+        if self.train_flag >= self.resample_interval:
+            _resampling.resample_(self.max_active, self.sum_active, self.loc, self.logstd, self.policy_bias,
+                                  self.policy_weight, resample=self.resample, threshold=self.resample_threshold,
+                                  tanh=self.normalize_policy_output_, seed=self.seed + 1, offset=3 * self.global_step)
+            self.train_flag = 0
+            return True
+        return False
+
+    # -------------------------------------------------------------------- (de)serialisation ----
+    def state_dict(self):
+        return dict(params=self.params.clone(), state_mean=self.state_mean.clone(), state_std=self.state_std.clone(),
+                    max_active=self.max_active.clone(), sum_active=self.sum_active.clone(), train_flag=self.train_flag,
+                    global_step=self.global_step)
+
+    def load_state_dict(self, sd):
+        self.params.copy_(sd["params"])
+        for k in ("state_mean", "state_std", "max_active", "sum_active"):
+            getattr(self, k).copy_(sd[k])
+        self.train_flag, self.global_step = int(sd["train_flag"]), int(sd["global_step"])
+
+    def named_parameters(self):
+        """Reference variable names ([.index] of the shipped checkpoint) -> (param view, grad view)."""
+        out = {}
+        for l in self.actor + [self.fc_policy] + self.critic:
+            out[f"global_net/{l.name}/weight"] = (l.W[:l.k_in], l.dW[:l.k_in])
+            out[f"global_net/{l.name}/bias"] = (l.b, l.db)
+        out["global_net/actor/samples"] = (self.loc, self.dloc)
+        out["global_net/actor/samples_std"] = (self.logstd, self.dlogstd)
+        return out

@@ -1,0 +1,150 @@
+"""K6 / K7 and the DPPO train step through the reference-facing network object, against the fp64
+oracle (oracle/network.py).  Tolerance: 1e-5 norm-wise per tensor."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import network as on
+from pfpn_b200 import _cabi
+from pfpn_b200.head import _stream_ptr
+from pfpn_b200.learner import SyncReplicasAdam
+from pfpn_b200.network import ParticleFilteringClipPPONetwork
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).detach().double().cpu(), torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("M,K,N", [(300, 200, 1024), (1000, 1024, 512), (517, 512, 1260), (129, 512, 1), (4, 8, 4)])
+def test_linear_layers_match_fp64(cuda_dev, M, K, N):
+    g = torch.Generator().manual_seed(M + N)
+    X = torch.randn(M, K, generator=g).clamp(-3, 6.5)
+    W = torch.randn(K, N, generator=g) * 0.05
+    b = torch.randn(N, generator=g) * 0.1
+    dY = torch.randn(M, N, generator=g)
+    cu = lambda t: t.to(cuda_dev).contiguous()
+    Xd, Wd, bd, dYd = cu(X), cu(W), cu(b), cu(dY)
+    st = _stream_ptr()
+    for relu6 in ((0, 1) if N > 1 else (0,)):
+        Y = torch.empty(M, N, device=cuda_dev) if N > 1 else torch.empty(M, device=cuda_dev)
+        _cabi.check(_cabi.pfpn_mlp_linear_fwd(Xd.data_ptr(), K, Wd.data_ptr(), bd.data_ptr(), Y.data_ptr(), N, M, K, N, relu6, st))
+        ref = X.double() @ W.double() + b.double()
+        ref = ref.clamp(0, 6) if relu6 else ref
+        assert rel(Y.reshape(M, N), ref) < TOL
+    dX = torch.empty(M, K, device=cuda_dev)
+    _cabi.check(_cabi.pfpn_mlp_linear_bwd_input(dYd.data_ptr(), N, Wd.data_ptr(), Xd.data_ptr(), dX.data_ptr(), K, M, K, N, st))
+    mask = ((X > 0) & (X < 6)).double()
+    assert rel(dX, (dY.double() @ W.double().T) * mask) < TOL
+    import ctypes as C
+    n = C.c_size_t(0)
+    _cabi.check(_cabi.pfpn_mlp_wgrad_workspace_bytes(M, K, N, C.byref(n)))
+    ws = torch.empty(n.value, dtype=torch.uint8, device=cuda_dev)
+    dW, db = torch.empty(K, N, device=cuda_dev), torch.empty(N, device=cuda_dev)
+    _cabi.check(_cabi.pfpn_mlp_linear_bwd_weight(Xd.data_ptr(), K, dYd.data_ptr(), N, dW.data_ptr(), db.data_ptr(), M, K, N,
+                                                 ws.data_ptr(), ws.numel(), st))
+    assert rel(dW, X.double().T @ dY.double()) < TOL and rel(db, dY.double().sum(0)) < TOL
+
+
+def make_batch(B, S, A, seed):
+    g = torch.Generator().manual_seed(seed)
+    return dict(state=torch.randn(B, S, generator=g) * 1.5 + 0.3, action=torch.rand(B, A, generator=g) * 2 - 1,
+                value=torch.randn(B, generator=g), log_prob=torch.randn(B, generator=g) * 0.3 + 60.0,
+                advantage=torch.randn(B, generator=g))
+
+
+def build(cuda_dev, S=197, A=36, P=35, **kw):
+    net = ParticleFilteringClipPPONetwork(True, [S], [A], action_lower_bound=[-1.0] * A, action_upper_bound=[1.0] * A,
+                                          particles=P, resample=-1, resample_interval=368, normalize_state=True,
+                                          clip_state=5.0, normalize_advantage=True, value_loss_coef=0.5, device=cuda_dev,
+                                          seed=28949, **kw).init()
+    # perturb so every parameter matters (bias 0 / equal particles would hide indexing bugs)
+    g = torch.Generator().manual_seed(1)
+    net.params.add_(0.02 * torch.randn(net.params.shape, generator=g).to(cuda_dev))
+    for l in net.actor + net.critic[:1]:
+        pass
+    net.actor[0].W[net.S:].zero_(); net.critic[0].W[net.S:].zero_()
+    net.state_mean.copy_(torch.randn(S, generator=g) * 0.2)
+    net.state_std.copy_(torch.rand(S, generator=g) + 0.5)
+    return net
+
+
+def oracle_params(net):
+    return {k: p.detach().double().cpu().clone() for k, (p, _) in net.named_parameters().items()}
+
+
+@pytest.mark.parametrize("B", [512, 33])
+def test_train_step_gradients_and_adam_match_oracle(cuda_dev, B):
+    net = build(cuda_dev)
+    batch = make_batch(B, 197, 36, seed=B)
+    p0 = oracle_params(net)
+    mean, std = net.state_mean.double().cpu(), net.state_std.double().cpu()
+    b64 = {k: v.double() for k, v in batch.items()}
+    # make lp_old realistic: behaviour log-prob near the current one
+    logits, _ = on.forward(p0, b64["state"], mean, std)
+    from oracle import head as oh
+    lp = oh.MixtureGaussianOracle(logits.reshape(B, 36, 35), p0["global_net/actor/samples"],
+                                  p0["global_net/actor/samples_std"].exp(), False).log_prob(b64["action"])
+    batch["log_prob"] = (lp + 0.1 * torch.randn(B, dtype=torch.float64)).float()
+    b64["log_prob"] = batch["log_prob"].double()
+    g_ref, l_ref = on.gradients(p0, b64["state"], b64["action"], b64["value"], b64["log_prob"], b64["advantage"],
+                                mean, std, 36, 35)
+    opt = SyncReplicasAdam(lr=1e-4, norm_clip=1.0)
+    losses = net.compute_gradients(batch["state"], batch["action"], batch["value"], batch["log_prob"], batch["advantage"])
+    for k, (_, g) in net.named_parameters().items():
+        assert rel(g, g_ref[k]) < TOL, k
+    assert abs(float(losses[3]) - float(l_ref[3])) < TOL * float(l_ref[3])
+    assert abs(float(losses[0]) - float(l_ref[0])) < 1e-4 * max(1.0, abs(float(l_ref[0])))
+    # clip + Adam + statistics
+    m = {k: torch.zeros_like(v) for k, v in p0.items()}
+    v = {k: torch.zeros_like(t) for k, t in p0.items()}
+    p1 = {k: t.clone() for k, t in p0.items()}
+    _, norm = on.clip_by_global_norm(g_ref, 1.0)
+    # Adam normalises by |g|: near-zero gradients amplify any gradient noise to O(1) in the update, so
+    # the optimizer kernels are checked on the kernel's own (fp32) gradient
+    g_k = {k: g.detach().double().cpu().clone() for k, (_, g) in net.named_parameters().items()}
+    gc, norm_k = on.clip_by_global_norm(g_k, 1.0)
+    assert abs(norm_k - norm) < TOL * norm
+    on.adam_step(p1, gc, m, v, 1)
+    nm, ns = on.normalizer_update(mean, std, b64["state"], 0)
+    opt.apply_gradients(net)
+    assert abs(float(opt.norm_scale[0]) - norm) < TOL * norm
+    for k, (p, _) in net.named_parameters().items():
+        # fp32 parameter storage bounds the agreement: |dp| = 1e-4 on weights up to ~1
+        assert rel(p, p1[k]) < 1e-6, k
+        du, dr = (p.double().cpu() - p0[k]).reshape(-1), (p1[k] - p0[k]).reshape(-1)
+        assert float(torch.dot(du, dr) / (du.norm() * dr.norm())) > 0.999, k
+    assert rel(net.state_mean, nm) < TOL and rel(net.state_std, ns) < TOL
+    assert net.global_step == 1 and net.train_flag == 1
+
+
+def test_reference_facing_train_and_run_signatures(cuda_dev):
+    net = build(cuda_dev)
+    opt = SyncReplicasAdam()
+    batch = make_batch(64, 197, 36, seed=3)
+    np_batch = {k: v.numpy() for k, v in batch.items()}
+    (loss, ent, pl, vl), extra = net.train(None, opt, None, np_batch["state"], np_batch["action"], np_batch["value"],
+                                           np_batch["log_prob"], np_batch["advantage"])
+    assert ent is None and np.isfinite([loss, pl, vl]).all() and extra == []
+    out = net.run(None, np_batch["state"][0])
+    assert out[0].shape == (36,) and isinstance(out[1], float) and isinstance(out[2], float)
+    assert isinstance(net.evaluate(None, np_batch["state"][0]), float)
+    assert float(net.sum_active.sum()) > 0  # running_update_ops executed on run()
+    assert len(net.local_update_variables) == 4 and len(net.train_ops) == 1
+
+
+def test_resample_tick_fires_at_interval_and_is_replica_deterministic(cuda_dev):
+    nets = [build(cuda_dev) for _ in range(2)]
+    for net in nets:
+        net.resample_interval = 3
+        net.max_active.fill_(0.5); net.sum_active.fill_(1.0)
+        net.max_active[:, ::5] = 1e-6
+        fired = []
+        for i in range(3):
+            net.global_step = i
+            fired.append(net.update())
+        assert fired == [False, False, True] and net.train_flag == 0 and not net.max_active.any()
+    assert torch.equal(nets[0].params, nets[1].params)
