@@ -42,6 +42,17 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the head kernel at this
+    exact shape (profiles/head_kernel_ncu.json, written by tools/make_profiles.py); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "head_kernel_ncu.json")) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -139,6 +150,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dppo", action="store_true")
+    ap.add_argument("--dppo-steps", type=int, default=10)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -201,10 +214,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     evs[0].record(stream)
     for i in range(args.steps):
@@ -229,7 +242,6 @@ def main():
     torch.cuda.synchronize()
     kms = sorted(kev[2 * i].elapsed_time(kev[2 * i + 1]) for i in range(args.steps))
     k_avg_ms = sum(kms) / len(kms)
-    clocks = sampler.stop() if sampler else None
 
     # ---- end to end through the host-buffer API -----------------------------------------
     pipe = HostHeadPipeline(B, A, P, dev)
@@ -251,6 +263,42 @@ def main():
     # sanity: the host path and the resident path agree
     assert torch.allclose(out["lp"], lp.cpu(), rtol=0, atol=0), "host pipeline lp mismatch"
 
+    # ---- the DPPO minibatch update around the head (BASELINE c4): B_total = 65536 sharded ------
+    dppo = None
+    if not args.no_dppo:
+        from pfpn_b200.learner import SyncReplicasAdam, shard_bounds
+        from pfpn_b200.network import ParticleFilteringClipPPONetwork
+        lo, hi = shard_bounds(B_PER_GPU, rank, world)
+        Bs = hi - lo
+        net = ParticleFilteringClipPPONetwork(True, [197], [A], action_lower_bound=[-1.0] * A, action_upper_bound=[1.0] * A,
+                                              particles=P, resample=-1, resample_interval=368, normalize_state=True,
+                                              clip_state=5.0, normalize_advantage=True, device=dev, seed=SEED).init()
+        opt = SyncReplicasAdam(lr=1e-4, norm_clip=1.0)
+        st_ = torch.randn(Bs, 197, device=dev, generator=g)
+        ac_, lp_, v_ = net.run_batch(st_)
+        lpo_ = lp_ + 0.05 * torch.randn(Bs, device=dev, generator=g)
+        adv_ = torch.randn(Bs, device=dev, generator=g)
+
+        def upd():
+            net.compute_gradients(st_, ac_, v_, lpo_, adv_)
+            opt.apply_gradients(net)
+        for _ in range(3):
+            upd()
+        barrier()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record(stream)
+        for _ in range(args.dppo_steps):
+            upd()
+        u1.record(stream)
+        barrier()
+        um = torch.tensor([u0.elapsed_time(u1) / args.dppo_steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(um, op=dist.ReduceOp.MAX)
+        dppo = {"workload": f"DPPO minibatch update, B_total={B_PER_GPU} sharded over {world} GPU(s): 197-1024-512 actor+critic trunk (fp32 FFMA), PFPN head, local clip, NCCL all-reduce of the 8.4 MB bucket, Adam",
+                "ms_per_update": float(um.item()), "samples_per_s": B_PER_GPU / (float(um.item()) * 1e-3), "scaling": "strong",
+                "trunk_tflops": 12.6e6 * B_PER_GPU / (float(um.item()) * 1e-3) / 1e12}
+    clocks = sampler.stop() if sampler else None
+
     if rank == 0:
         peak, peak_src = peaks()
         achieved = ALG_BYTES_PER_STATE * B / (k_avg_ms * 1e-3) / 1e9
@@ -267,10 +315,12 @@ def main():
                     "api": "pfpn_b200.host.HostHeadPipeline.run (pinned host buffers, 3-stream chunked)"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "pfpn::head_kernel<4,9,..,BWD> (+head_finalize)",
+                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "pfpn::head_kernel<4,9,..,BWD> (+head_finalize)",
                          "alg_bytes_per_state": ALG_BYTES_PER_STATE, "kernel_ms_avg": k_avg_ms,
                          "kernel_ms_median": kms[len(kms) // 2]},
         }
+        if dppo is not None:
+            line["dppo_update"] = dppo
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             rate, dt = cpu_reference_rate(4096, 3, cores)
