@@ -61,7 +61,7 @@ __device__ __forceinline__ float softplusf_acc(float x) {
 // the DPPO train step) with those branches compiled out.
 // CSM: per-(a,k) constants live in shared memory instead of registers.
 template <int LPR, int EPL, int RPT, int NSTAGE, int KM, int MAXT, int NREG, int PT, int AT, bool CSM>
-__global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const HeadKParams kp) {
+__global__ void __launch_bounds__(MAXT + 32) __maxnreg__(NREG) head_kernel(const HeadKParams kp) {
   constexpr bool BWD = KM != 0;
   constexpr bool LEAN = KM >= 2;
   constexpr int EP2 = (EPL + 1) / 2;  // packed pairs per lane
@@ -91,8 +91,11 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
   float* __restrict__ g_dvalue = LEAN ? nullptr : kp.a.dvalue;
   float* __restrict__ g_ent_ba = LEAN ? nullptr : kp.a.ent_ba;
   const int tid = threadIdx.x;
-  const int nthr = blockDim.x;
+  // the last warp of the CTA is the TMA producer (loads, gradient stores, their waits); the
+  // first nthr threads compute
+  const int nthr = blockDim.x - 32;
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+  const bool is_producer = warp == nwarps;
 
   // ---- shared memory carve-up ------------------------------------------
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
   int my_tiles = 0;
   if (first_tile < kp.num_tiles) my_tiles = (kp.num_tiles - 1 - first_tile) / tile_step + 1;
 
-  auto issue_load = [&](int it) {  // thread 0 only
+  auto issue_load = [&](int it) {  // producer lane 0 only
     const int tile = first_tile + it * tile_step;
     if (it >= my_tiles) return;
     if (tail_exists && tile == tail_tile) return;  // tail is copied cooperatively
@@ -193,9 +196,31 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
     bulk_g2s(smem_u32(stage_base) + st * stage_bytes, g_logits + (size_t)tile * tile_floats,
              (uint32_t)(tile_floats * 4), bar);
   };
-  if (tid == 0) {
+  const uint32_t cta_bar_a = smem_u32(cta_bar);
+  if (is_producer) {
+    // ===================== TMA producer warp ===========================================
+    // Mirrors the compute steps: after step it-1 completed (split barrier phase it-1) every
+    // compute thread has fenced its gradient STS of tile it-2, so that tile can leave; the
+    // stage that load(it+DIST) refills held tile it+DIST-NSTAGE, whose store is older than the
+    // NSTAGE-DIST-2 most recent bulk groups.  Only this warp ever blocks on TMA traffic.
+    if (lane == 0) {
 #pragma unroll
-    for (int d = 0; d <= DIST; ++d) issue_load(d);
+      for (int d = 0; d <= DIST; ++d) issue_load(d);
+    }
+    for (int it = 1; it <= my_tiles; ++it) {
+      mbar_wait(cta_bar_a, (uint32_t)((it - 1) & 1));
+      if (lane == 0) {
+        if (BWD && it >= 2) {
+          const int ptile = first_tile + (it - 2) * tile_step;
+          bulk_s2g(g_dlogits + (size_t)ptile * tile_floats,
+                   smem_u32(stage_base) + ((it - 2) % NSTAGE) * stage_bytes, (uint32_t)(tile_floats * 4));
+          bulk_commit();
+          bulk_wait_read<NSTAGE - DIST - 2>();
+        }
+        issue_load(it + DIST);
+      }
+      __syncwarp();
+    }
   }
 
   // per-thread fixed row offsets inside a tile and the one "writer" thread per state
@@ -203,7 +228,6 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
 #pragma unroll
   for (int j = 0; j < RPT; ++j) row_off[j] = (j * slots + slot) * A + a;
   const bool writer = active && a == 0 && c == 0;
-  const uint32_t cta_bar_a = smem_u32(cta_bar);
 
   // action / per-state scalar prefetch, one tile ahead.  sc = {adv, lp_old} (PPO) or {g_lp, -}
   float v_nxt[RPT], sc0_nxt[RPT], sc1_nxt[RPT];
@@ -264,7 +288,7 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
         const int nvalid = (B - b0) * AP;
         const float* src = g_logits + (size_t)b0 * AP;
         for (int idx = tid; idx < nvalid; idx += nthr) sbuf[idx] = __ldg(&src[idx]);
-        __syncthreads();  // tail tile only (last iteration of exactly one CTA)
+        asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");  // compute threads only; tail tile only
       }
 
       float2* rb = rowbuf + (it % 3) * TS * A;
@@ -346,18 +370,7 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
       const int b0 = tile * TS;
       const float2* rb = rowbuf + (pit % 3) * TS * A;
 
-      mbar_wait(cta_bar_a, (uint32_t)(pit & 1));  // every thread finished iteration it-1
-
-      if (tid == 0) {
-        if (BWD && it >= 2) {  // all threads fenced their STS of tile it-2 before arriving
-          const int ptile = tile - tile_step;
-          bulk_s2g(g_dlogits + (size_t)ptile * tile_floats,
-                   smem_u32(stage_base) + ((it - 2) % NSTAGE) * stage_bytes, (uint32_t)(tile_floats * 4));
-          bulk_commit();
-          bulk_wait_read<1>();
-        }
-        issue_load(it + DIST);
-      }
+      mbar_wait(cta_bar_a, (uint32_t)(pit & 1));  // every compute thread finished iteration it-1
 
 #pragma unroll
       for (int j = 0; j < RPT; ++j) {
@@ -482,9 +495,11 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
     // arrive: this thread's partials of tile it are written, its gradient STS of tile it-1 fenced
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cta_bar_a) : "memory");
   };
-  for (int it = 0; it <= my_tiles; it += 2) {
-    step(it, stA, stB);
-    step(it + 1, stB, stA);
+  if (!is_producer) {
+    for (int it = 0; it <= my_tiles; it += 2) {
+      step(it, stA, stB);
+      step(it + 1, stB, stA);
+    }
   }
 
   // ---------------- drain: the last tile's gradient ------------------------------------
@@ -492,15 +507,14 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
   const int prev_tile = my_tiles >= 1 ? first_tile + (my_tiles - 1) * tile_step : -1;
   const int prev_stage = my_tiles >= 1 ? (my_tiles - 1) % NSTAGE : 0;
   const bool prev_was_tail = tail_exists && prev_tile == tail_tile;
-  // ---------------- epilogue: last store, partial sums --------------------------
   if (BWD && prev_tile >= 0) {
     if (!prev_was_tail) {
-      if (tid == 0) {
+      if (is_producer && lane == 0) {
         bulk_s2g(g_dlogits + (size_t)prev_tile * tile_floats, smem_u32(stage_base) + prev_stage * stage_bytes,
                  (uint32_t)(tile_floats * 4));
         bulk_commit();
       }
-    } else {
+    } else if (!is_producer) {
       const int b0 = prev_tile * TS;
       const int nvalid = (B - b0) * AP;
       const float* sb = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(stage_base) + (size_t)prev_stage * stage_bytes);
@@ -508,14 +522,14 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
       for (int idx = tid; idx < nvalid; idx += nthr) dst[idx] = sb[idx];
     }
   }
-  if (tid == 0) bulk_wait_read<0>();
+  if (is_producer && lane == 0) bulk_wait_read<0>();  // every bulk group was issued by this lane
   if (BWD) {
     // loss terms live in the writer threads; fixed-order two-level sum
-    const float wl = row_sum<32>(loss_acc);
+    const float wl = row_sum<32>(is_producer ? 0.f : loss_acc);
     if (lane == 0) lossbuf[warp] = wl;
-    __syncthreads();  // all bulk reads of smem done (thread 0 waited) before reuse
+    __syncthreads();  // all bulk reads of smem done (the producer waited) before reuse
     float* red = stage_base;  // [slots][2][AP]
-    if (active) {
+    if (active && !is_producer) {
 #pragma unroll
       for (int i2 = 0; i2 < EP2; ++i2) {
 #pragma unroll
@@ -531,7 +545,7 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(NREG) head_kernel(const Head
     }
     __syncthreads();
     float* part = kp.part + (size_t)blockIdx.x * 2 * AP;
-    for (int idx = tid; idx < 2 * AP; idx += nthr) {
+    for (int idx = tid; idx < 2 * AP; idx += nthr + 32) {
       float s = 0.f;
       for (int sl = 0; sl < slots; ++sl) s += red[sl * 2 * AP + idx];
       part[idx] = s;
@@ -659,7 +673,7 @@ static const HeadVariant kHeadVariants[] = {
     PFPN_HEAD_VARIANT_ENTRY(13, 36, 4, 9, 1, 5, 288, 96, 0, 0, false),
     PFPN_HEAD_VARIANT_ENTRY(37, 64, 8, 8, 1, 5, 320, 96, 0, 0, false),
     PFPN_HEAD_VARIANT_ENTRY(65, 104, 8, 13, 1, 5, 288, 96, 0, 0, false),
-    PFPN_HEAD_VARIANT_ENTRY(105, 256, 16, 16, 1, 4, 384, 168, 0, 0, false),
+    PFPN_HEAD_VARIANT_ENTRY(105, 256, 16, 16, 1, 4, 320, 168, 0, 0, false),
 };
 
 static const HeadVariant* pick_variant(int A, int P) {
@@ -700,7 +714,7 @@ static int plan_head(int A, int P, int km, HeadLaunch* L) {
   if (v.at != 0 && slots != v.maxt / per_slot) return PFPN_ERR_UNSUPPORTED;  // kernel derives slots itself
   L->slots = slots;
   L->ts = slots * v.rpt;
-  L->threads = (slots * per_slot + 31) & ~31;
+  L->threads = ((slots * per_slot + 31) & ~31) + 32;  // + the TMA producer warp
   const int stage_bytes = (L->ts * A * P * 4 + 127) & ~127;
   L->smem_bytes = v.nstage * stage_bytes + 8 * (v.nstage + 1) + 3 * L->ts * A * 8 + kHeadMaxWarps * 4 +
                   (v.lpr * v.epl + 1) * 4 + 16 + (v.csm ? ((v.epl + 1) / 2) * 3 * per_slot * 8 : 0);
