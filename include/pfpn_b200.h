@@ -221,6 +221,14 @@ int pfpn_mlp_linear_bwd_weight(const float* X, int32_t ldx, const float* dY, int
                                int32_t M, int32_t K, int32_t N, void* workspace, size_t workspace_bytes,
                                pfpn_stream_t stream);
 
+/* K6, tensor-core path: C[M,N] = epi(A[M,K] * Bt[N,K]^T) with 3xTF32 error compensation on tcgen05
+ * (TMA-fed, TMEM accumulator).  Same epilogues as the FFMA anchor; `Bt` is the weight transposed
+ * for a forward layer and the weight as stored for the input gradient.
+ * epi: 0 none, 1 +bias[n], 2 relu6(+bias), 3 multiply by 1[0 < Hm[m,n] < 6]. */
+int pfpn_tc_gemm_nt(const float* A, int32_t lda, const float* Bt, int32_t ldb, float* C, int32_t ldc,
+                    const float* bias, const float* Hm, int32_t ldh, int32_t M, int32_t N, int32_t K,
+                    int32_t epi, pfpn_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Learner-update element-wise pieces and K7 (clip + Adam).
  * ---------------------------------------------------------------------- */

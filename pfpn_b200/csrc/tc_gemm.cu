@@ -1,0 +1,287 @@
+// K6 (tensor-core path) -- 3xTF32 error-compensated GEMM on tcgen05 with TMA-fed operands and
+// a TMEM accumulator, same epilogues as the FFMA anchor (csrc/sgemm.cu).
+//
+//   C[M,N] = A[M,K] * B[N,K]^T      (both operands K-major fp32, i.e. row-major [rows, K])
+//
+// Plain TF32 (10-bit mantissa) cannot hold 1e-5 through three layers, so every fp32 operand is
+// split on the fly into hi = tf32(x) and lo = x - hi (exact) and three MMAs are accumulated:
+// hi*hi + hi*lo + lo*hi  (relative error ~2^-21 per product, fp32 accumulation in TMEM).
+//
+// CTA = 8 warps, one 128x128 output tile, K in blocks of 32 floats (= one 128-byte swizzle atom):
+//   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B) of A and B into a 3-stage ring
+//   warp 1      single-thread tcgen05.mma issuer (kind::tf32, M=128, N=128, K=8), tcgen05.commit
+//   warp 2      TMEM allocator (2 x 128 fp32 columns: main and correction accumulators)
+//   warps 4-7   splitter: rewrite the landed tile as hi (in place) and lo (second buffer), element
+//               wise in the swizzled layout; afterwards the epilogue: tcgen05.ld -> bias / relu6 /
+//               Relu6Grad mask -> global stores
+// Pipelines: full[s] (TMA -> splitter), conv[s] (splitter -> MMA), empty[s] (MMA -> TMA),
+// tmem_full (MMA -> epilogue).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace pfpn {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                       // 16 KiB per operand tile
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                     // A_hi, A_lo, B_hi, B_lo
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 + 256;  // + alignment slack + barriers
+enum { TC_EPI_NONE = 0, TC_EPI_BIAS = 1, TC_EPI_BIAS_RELU6 = 2, TC_EPI_MASK6 = 3 };
+
+struct TcParams {
+  float* C;
+  const float* bias;
+  const float* Hm;
+  int M, N, K, ldc, ldh, epi;
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address
+  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset
+  d |= (uint64_t)1 << 46;                         // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                         const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  unsigned char* gbase = smem_dyn + (base - raw);
+  const uint32_t bar0 = base + TC_STAGES * TC_STAGE_BYTES;
+  auto full = [&](int s) { return bar0 + 8 * s; };
+  auto conv = [&](int s) { return bar0 + 8 * (TC_STAGES + s); };
+  auto empty = [&](int s) { return bar0 + 8 * (2 * TC_STAGES + s); };
+  const uint32_t tmem_full = bar0 + 8 * 3 * TC_STAGES;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + TC_STAGES * TC_STAGE_BYTES + 8 * (3 * TC_STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+  const int nkb = (p.K + TC_BK - 1) / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(conv(s), 128);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        mbar_wait(empty(s), (uint32_t)(((kb / TC_STAGES) & 1) ^ 1));
+        mbar_expect_tx(full(s), 2 * TC_TILE_BYTES);
+        tma_load_2d(base + s * TC_STAGE_BYTES, &mapA, kb * TC_BK, m0, full(s));
+        tma_load_2d(base + s * TC_STAGE_BYTES + 2 * TC_TILE_BYTES, &mapB, kb * TC_BK, n0, full(s));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B tf32, both K-major, N = 128, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        mbar_wait(conv(s), (uint32_t)((kb / TC_STAGES) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = base + s * TC_STAGE_BYTES, a_lo = a_hi + TC_TILE_BYTES;
+        const uint32_t b_hi = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < TC_BK / 8; ++ks) {
+          const uint32_t off = ks * 32;  // 8 tf32 = 32 bytes along K inside the swizzle atom
+          // The tensor core truncates its fp32 accumulator on every MMA (measured: ~2^-25 relative per
+          // accumulation, systematic).  The dominant hi*hi products therefore get their own accumulator
+          // (K/8 accumulations) and the two small correction products a second one, whose truncation is
+          // relative to its 2^-11 times smaller magnitude; the epilogue adds the two in fp32.
+          umma_tf32(tmem, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, (kb | ks) != 0);
+          umma_tf32(tmem + TC_BN, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, (kb | ks) != 0);
+          umma_tf32(tmem + TC_BN, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1u);
+        }
+        umma_commit(empty(s));  // implicit tcgen05.fence::before_thread_sync
+      }
+      umma_commit(tmem_full);
+    }
+  } else if (warp >= 4) {
+    // -------- splitter: x -> (hi = tf32-truncated x, lo = x - hi), same swizzled position ---------
+    const int t = threadIdx.x - 128;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % TC_STAGES;
+      mbar_wait(full(s), (uint32_t)((kb / TC_STAGES) & 1));
+      float4* st = reinterpret_cast<float4*>(gbase + (size_t)s * TC_STAGE_BYTES);
+#pragma unroll
+      for (int op = 0; op < 2; ++op) {
+        float4* hi = st + op * 2 * (TC_TILE_BYTES / 16);
+        float4* lo = hi + TC_TILE_BYTES / 16;
+#pragma unroll 4
+        for (int i = t; i < TC_TILE_BYTES / 16; i += 128) {
+          const float4 x = hi[i];
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
+          hi[i] = h;
+          lo[i] = l;
+        }
+      }
+      fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(conv(s));
+    }
+    // -------- epilogue: TMEM -> registers -> global --------------------------------------------
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int wq = warp & 3;              // TMEM lane quadrant this warp may read
+    const int m = m0 + wq * 32 + lane;    // accumulator row = TMEM lane
+#pragma unroll 1
+    for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+      uint32_t r[32], q[32];
+      const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+            "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]),
+            "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]),
+            "=r"(q[25]), "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+          : "r"(taddr + (uint32_t)TC_BN));
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (m < p.M) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = n0 + c0 + j;
+          if (n >= p.N) break;  // N % 4 == 0
+          float4 v = make_float4(__uint_as_float(r[j]) + __uint_as_float(q[j]),
+                                 __uint_as_float(r[j + 1]) + __uint_as_float(q[j + 1]),
+                                 __uint_as_float(r[j + 2]) + __uint_as_float(q[j + 2]),
+                                 __uint_as_float(r[j + 3]) + __uint_as_float(q[j + 3]));
+          if (p.epi == TC_EPI_BIAS || p.epi == TC_EPI_BIAS_RELU6) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+          }
+          if (p.epi == TC_EPI_BIAS_RELU6) {
+            v.x = fminf(fmaxf(v.x, 0.f), 6.f); v.y = fminf(fmaxf(v.y, 0.f), 6.f);
+            v.z = fminf(fmaxf(v.z, 0.f), 6.f); v.w = fminf(fmaxf(v.w, 0.f), 6.f);
+          }
+          if (p.epi == TC_EPI_MASK6) {
+            const float4 h = __ldg(reinterpret_cast<const float4*>(p.Hm + (size_t)m * p.ldh + n));
+            v.x = (h.x > 0.f && h.x < 6.f) ? v.x : 0.f; v.y = (h.y > 0.f && h.y < 6.f) ? v.y : 0.f;
+            v.z = (h.z > 0.f && h.z < 6.f) ? v.z : 0.f; v.w = (h.w > 0.f && h.w < 6.f) ? v.w : 0.f;
+          }
+          *reinterpret_cast<float4*>(p.C + (size_t)m * p.ldc + n) = v;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    return q == cudaDriverEntryPointSuccess ? reinterpret_cast<EncodeTiledFn>(f) : nullptr;
+  }();
+  return fn;
+}
+
+// [rows, K] row-major fp32 -> tiles of (box_rows x 32 floats), SWIZZLE_128B, OOB reads return 0
+static int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return PFPN_ERR_UNSUPPORTED;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PFPN_OK : PFPN_ERR_UNSUPPORTED;
+}
+
+}  // namespace pfpn
+
+using namespace pfpn;
+
+// C[M,N] = epi(A[M,K] * Bt[N,K]^T): the tensor-core twin of pfpn_mlp_linear_fwd (Bt = W^T) and
+// pfpn_mlp_linear_bwd_input (Bt = W as stored).  epi: 0 none, 1 +bias, 2 relu6(+bias), 3 Relu6Grad mask by Hm.
+extern "C" int pfpn_tc_gemm_nt(const float* A, int32_t lda, const float* Bt, int32_t ldb, float* Cout, int32_t ldc,
+                               const float* bias, const float* Hm, int32_t ldh, int32_t M, int32_t N, int32_t K,
+                               int32_t epi, pfpn_stream_t stream_) {
+  if (!A || !Bt || !Cout || M < 0 || N <= 0 || K <= 0 || epi < 0 || epi > 3) return PFPN_ERR_ARG;
+  if ((epi == TC_EPI_BIAS || epi == TC_EPI_BIAS_RELU6) && !bias) return PFPN_ERR_ARG;
+  if (epi == TC_EPI_MASK6 && !Hm) return PFPN_ERR_ARG;
+  if (M == 0) return PFPN_OK;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  if ((lda & 3) || (ldb & 3) || (ldc & 3) || (N & 3) || (K & 3) || !al16(A) || !al16(Bt) || !al16(Cout)) return PFPN_ERR_ALIGN;
+  CUtensorMap mapA, mapB;
+  int rc = make_map(&mapA, A, M, K, lda, TC_BM);
+  if (rc != PFPN_OK) return rc;
+  rc = make_map(&mapB, Bt, N, K, ldb, TC_BN);
+  if (rc != PFPN_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PFPN_CUDA_OK(cudaFuncSetAttribute((const void*)tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  TcParams p{Cout, bias, Hm, M, N, K, ldc, ldh, epi};
+  dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
+  tc_gemm_kernel<<<grid, 256, TC_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream_)>>>(mapA, mapB, p);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}

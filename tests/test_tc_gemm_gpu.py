@@ -1,0 +1,39 @@
+"""tcgen05 3xTF32 GEMM (K6 tensor-core path) against fp64: must stay within the same 1e-5 norm-wise
+tolerance as the FFMA anchor, otherwise it may not be used (north_star)."""
+import pytest
+import torch
+
+from pfpn_b200 import _cabi
+from pfpn_b200.head import _stream_ptr
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 128, 64), (300, 1024, 200), (1000, 512, 1024), (517, 1260, 512),
+                                   (4096, 1024, 200), (77, 132, 36)])
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+def test_tc_gemm_nt_matches_fp64(cuda_dev, M, N, K, epi):
+    g = torch.Generator().manual_seed(M * 7 + N + K + epi)
+    A = torch.randn(M, K, generator=g)
+    Bt = torch.randn(N, K, generator=g) * 0.05
+    bias = torch.randn(N, generator=g) * 0.1
+    H = torch.randn(M, N, generator=g) * 4
+    cu = lambda t: t.to(cuda_dev).contiguous()
+    Ad, Bd, bd, Hd = cu(A), cu(Bt), cu(bias), cu(H)
+    C = torch.full((M, N), float("nan"), device=cuda_dev)
+    _cabi.check(_cabi.pfpn_tc_gemm_nt(Ad.data_ptr(), K, Bd.data_ptr(), K, C.data_ptr(), N, bd.data_ptr(), Hd.data_ptr(), N,
+                                      M, N, K, epi, _stream_ptr()))
+    ref = A.double() @ Bt.double().T
+    if epi in (1, 2):
+        ref = ref + bias.double()
+    if epi == 2:
+        ref = ref.clamp(0, 6)
+    if epi == 3:
+        ref = ref * ((H > 0) & (H < 6)).double()
+    assert torch.isfinite(C).all()
+    assert rel(C, ref) < 1e-5
