@@ -228,6 +228,8 @@ int pfpn_mlp_linear_bwd_weight(const float* X, int32_t ldx, const float* dY, int
 int pfpn_tc_gemm_nt(const float* A, int32_t lda, const float* Bt, int32_t ldb, float* C, int32_t ldc,
                     const float* bias, const float* Hm, int32_t ldh, int32_t M, int32_t N, int32_t K,
                     int32_t epi, pfpn_stream_t stream);
+/* out[cols, rows] = in[rows, cols]^T -- keeps the K-major copy W^T of a weight for pfpn_tc_gemm_nt. */
+int pfpn_transpose(const float* in, float* out, int32_t rows, int32_t cols, pfpn_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Learner-update element-wise pieces and K7 (clip + Adam).

@@ -10,7 +10,7 @@
 // CTA = 8 warps, one 128x128 output tile, K in blocks of 32 floats (= one 128-byte swizzle atom):
 //   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B) of A and B into a 3-stage ring
 //   warp 1      single-thread tcgen05.mma issuer (kind::tf32, M=128, N=128, K=8), tcgen05.commit
-//   warp 2      TMEM allocator (2 x 128 fp32 columns: main and correction accumulators)
+//   warp 2      TMEM allocator (all 512 columns: two alternating main accumulators + one correction)
 //   warps 4-7   splitter: rewrite the landed tile as hi (in place) and lo (second buffer), element
 //               wise in the swizzled layout; afterwards the epilogue: tcgen05.ld -> bias / relu6 /
 //               Relu6Grad mask -> global stores
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "n"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -129,9 +129,11 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
           // accumulation, systematic).  The dominant hi*hi products therefore get their own accumulator
           // (K/8 accumulations) and the two small correction products a second one, whose truncation is
           // relative to its 2^-11 times smaller magnitude; the epilogue adds the two in fp32.
-          umma_tf32(tmem, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, (kb | ks) != 0);
-          umma_tf32(tmem + TC_BN, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, (kb | ks) != 0);
-          umma_tf32(tmem + TC_BN, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1u);
+          // Even / odd k-blocks alternate between two main accumulators, halving the chain again.
+          const uint32_t dmain = tmem + (uint32_t)((kb & 1) * TC_BN);
+          umma_tf32(dmain, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, (kb >= 2 || ks != 0) ? 1u : 0u);
+          umma_tf32(tmem + 2 * TC_BN, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, (kb | ks) != 0);
+          umma_tf32(tmem + 2 * TC_BN, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1u);
         }
         umma_commit(empty(s));  // implicit tcgen05.fence::before_thread_sync
       }
@@ -180,7 +182,22 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
             "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]),
             "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]),
             "=r"(q[25]), "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
-          : "r"(taddr + (uint32_t)TC_BN));
+          : "r"(taddr + (uint32_t)(2 * TC_BN)));
+      uint32_t o[32];
+      if (nkb > 1) {  // the odd-k-block accumulator exists only when there are at least two k-blocks
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]), "=r"(o[8]),
+              "=r"(o[9]), "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15]), "=r"(o[16]),
+              "=r"(o[17]), "=r"(o[18]), "=r"(o[19]), "=r"(o[20]), "=r"(o[21]), "=r"(o[22]), "=r"(o[23]), "=r"(o[24]),
+              "=r"(o[25]), "=r"(o[26]), "=r"(o[27]), "=r"(o[28]), "=r"(o[29]), "=r"(o[30]), "=r"(o[31])
+            : "r"(taddr + (uint32_t)TC_BN));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = 0u;
+      }
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
           "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -196,10 +213,10 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
         for (int j = 0; j < 32; j += 4) {
           const int n = n0 + c0 + j;
           if (n >= p.N) break;  // N % 4 == 0
-          float4 v = make_float4(__uint_as_float(r[j]) + __uint_as_float(q[j]),
-                                 __uint_as_float(r[j + 1]) + __uint_as_float(q[j + 1]),
-                                 __uint_as_float(r[j + 2]) + __uint_as_float(q[j + 2]),
-                                 __uint_as_float(r[j + 3]) + __uint_as_float(q[j + 3]));
+          float4 v = make_float4((__uint_as_float(r[j]) + __uint_as_float(o[j])) + __uint_as_float(q[j]),
+                                 (__uint_as_float(r[j + 1]) + __uint_as_float(o[j + 1])) + __uint_as_float(q[j + 1]),
+                                 (__uint_as_float(r[j + 2]) + __uint_as_float(o[j + 2])) + __uint_as_float(q[j + 2]),
+                                 (__uint_as_float(r[j + 3]) + __uint_as_float(o[j + 3])) + __uint_as_float(q[j + 3]));
           if (p.epi == TC_EPI_BIAS || p.epi == TC_EPI_BIAS_RELU6) {
             const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
             v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
@@ -221,7 +238,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
   }
 }
 

@@ -63,6 +63,7 @@ class SyncReplicasAdam:
         if self.m is None:
             self.m = torch.zeros_like(net.params)
             self.v = torch.zeros_like(net.params)
+        if self.norm_scale is None:
             self.norm_scale = torch.zeros(2, dtype=torch.float32, device=net.params.device)
             self._scratch = torch.empty(296 * 8, dtype=torch.uint8, device=net.params.device)
 
@@ -103,6 +104,7 @@ class SyncReplicasAdam:
         _cabi.check(_cabi.pfpn_adam_step(net.params.data_ptr(), net.grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                          net.n_params, self.lr, self.beta1, self.beta2, self.eps, self.step, inv_n, st))
         net.global_step += 1
+        net._wt_dirty = True
         # 6. train_ops chained after the optimizer step (sync_model.py:79-81): resample tick
         for op in net.train_ops:
             op()

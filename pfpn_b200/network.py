@@ -36,7 +36,7 @@ class _Linear:
     def __init__(self, name, k_in, n_out, k_pad=None):
         self.name, self.k_in, self.n_out = name, k_in, n_out
         self.k = k_pad or k_in  # rows of the stored W (zero rows beyond k_in)
-        self.W = self.b = self.dW = self.db = None
+        self.W = self.b = self.dW = self.db = self.WT = None
 
     def numel(self):
         return self.k * self.n_out + self.n_out
@@ -86,6 +86,11 @@ class ParticleFilteringClipPPONetwork:
         self.global_step = self.GLOBAL_STEP0
         self._rng_offset = 0
         self._act = {}
+        # K6 path: tcgen05 3xTF32 GEMMs (within the fp32 tolerance, tests/test_tc_gemm_gpu.py) unless the
+        # fp32 FFMA anchor is requested
+        import os
+        self.use_tensor_cores = os.environ.get("PFPN_TRUNK", "tc") != "ffma"
+        self._wt_dirty = True
 
     # ------------------------------------------------------------------------------ build ----
     def init(self):
@@ -172,7 +177,22 @@ class ParticleFilteringClipPPONetwork:
             self._act[name] = t
         return t
 
+    def _refresh_wt(self):
+        """K-major copies W^T of the weights for the tensor-core forward GEMMs (8 MB per refresh)."""
+        for l in self.actor + [self.fc_policy] + self.critic[:-1]:
+            if l.WT is None:
+                l.WT = torch.empty(l.n_out, l.k, dtype=torch.float32, device=self.device)
+            _cabi.check(_cabi.pfpn_transpose(l.W.data_ptr(), l.WT.data_ptr(), l.k, l.n_out, _stream_ptr()))
+        self._wt_dirty = False
+
     def _linear(self, l: _Linear, X, Y, relu6):
+        if self.use_tensor_cores and l.n_out > 1:
+            if self._wt_dirty:
+                self._refresh_wt()
+            _cabi.check(_cabi.pfpn_tc_gemm_nt(X.data_ptr(), X.stride(0), l.WT.data_ptr(), l.k, Y.data_ptr(), Y.stride(0),
+                                              l.b.data_ptr(), None, 0, X.shape[0], l.n_out, l.k, 2 if relu6 else 1,
+                                              _stream_ptr()))
+            return
         _cabi.check(_cabi.pfpn_mlp_linear_fwd(X.data_ptr(), X.stride(0), l.W.data_ptr(), l.b.data_ptr(), Y.data_ptr(),
                                               Y.stride(0) if Y.dim() > 1 else 1, X.shape[0], l.k, l.n_out,
                                               1 if relu6 else 0, _stream_ptr()))
@@ -300,6 +320,12 @@ class ParticleFilteringClipPPONetwork:
                                                          l.db.data_ptr(), M, l.k, l.n_out, ws.data_ptr(), ws.numel(), st))
             if i > 0:  # no gradient into the (stop_gradient) normalised state
                 dX = self._buf(f"d_{l.name}", M, l.k)
+                if self.use_tensor_cores and l.n_out > 1:
+                    # dX[M, k] = (dY[M, n] W[k, n]^T) .* relu6'(X): W as stored is already the K-major operand
+                    _cabi.check(_cabi.pfpn_tc_gemm_nt(dY.data_ptr(), ldy, l.W.data_ptr(), l.n_out, dX.data_ptr(), dX.stride(0),
+                                                      None, X.data_ptr(), X.stride(0), M, l.k, l.n_out, 3, st))
+                    dY = dX
+                    continue
                 _cabi.check(_cabi.pfpn_mlp_linear_bwd_input(dY.data_ptr(), ldy, l.W.data_ptr(), X.data_ptr(), dX.data_ptr(),
                                                             dX.stride(0), M, l.k, l.n_out, st))
                 dY = dX
@@ -328,6 +354,7 @@ class ParticleFilteringClipPPONetwork:
                                   self.policy_weight, resample=self.resample, threshold=self.resample_threshold,
                                   tanh=self.normalize_policy_output_, seed=self.seed + 1, offset=3 * self.global_step)
             self.train_flag = 0
+            self._wt_dirty = True
             return True
         return False
 
@@ -342,6 +369,7 @@ class ParticleFilteringClipPPONetwork:
         for k in ("state_mean", "state_std", "max_active", "sum_active"):
             getattr(self, k).copy_(sd[k])
         self.train_flag, self.global_step = int(sd["train_flag"]), int(sd["global_step"])
+        self._wt_dirty = True
 
     def named_parameters(self):
         """Reference variable names ([.index] of the shipped checkpoint) -> (param view, grad view)."""
