@@ -228,8 +228,17 @@ int pfpn_mlp_linear_bwd_weight(const float* X, int32_t ldx, const float* dY, int
 int pfpn_tc_gemm_nt(const float* A, int32_t lda, const float* Bt, int32_t ldb, float* C, int32_t ldc,
                     const float* bias, const float* Hm, int32_t ldh, int32_t M, int32_t N, int32_t K,
                     int32_t epi, pfpn_stream_t stream);
-/* out[cols, rows] = in[rows, cols]^T -- keeps the K-major copy W^T of a weight for pfpn_tc_gemm_nt. */
-int pfpn_transpose(const float* in, float* out, int32_t rows, int32_t cols, pfpn_stream_t stream);
+/* out[cols, ldo] = in[rows, ldi]^T -- K-major copies (W^T, batch-contiguous activations) for the tensor-core GEMMs. */
+int pfpn_transpose(const float* in, int32_t ldi, float* out, int32_t ldo, int32_t rows, int32_t cols,
+                   pfpn_stream_t stream);
+/* Weight gradient on tcgen05: dW[K,N] = X^T dY from batch-contiguous operands XT[K, M], dYT[N, M]
+ * (split-K over the batch in chunks of 2048 rows, deterministic fp32 second stage). */
+int pfpn_tc_wgrad_workspace_bytes(int32_t M, int32_t K, int32_t N, size_t* bytes);
+int pfpn_tc_linear_bwd_weight(const float* XT, int32_t ldxt, const float* dYT, int32_t ldyt, float* dW, int32_t M,
+                              int32_t K, int32_t N, void* workspace, size_t workspace_bytes, pfpn_stream_t stream);
+/* db[N] = column sums of dY[M,N]; workspace >= 1024*N floats. */
+int pfpn_bias_grad(const float* dY, int32_t ldy, float* db, int32_t M, int32_t N, void* workspace,
+                   size_t workspace_bytes, pfpn_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Learner-update element-wise pieces and K7 (clip + Adam).

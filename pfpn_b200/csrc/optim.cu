@@ -133,17 +133,17 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 
 // out[c, r] = in[r, c]  (weights -> K-major operand of the tensor-core forward GEMM)
-__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc) {
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc, int ldi, int ldo) {
   __shared__ float t[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int r = r0 + i, c = c0 + threadIdx.x;
-    t[i][threadIdx.x] = (r < R && c < Cc) ? in[(size_t)r * Cc + c] : 0.f;
+    t[i][threadIdx.x] = (r < R && c < Cc) ? in[(size_t)r * ldi + c] : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int c = c0 + i, r = r0 + threadIdx.x;
-    if (r < R && c < Cc) out[(size_t)c * R + r] = t[threadIdx.x][i];
+    if (r < R && c < Cc) out[(size_t)c * ldo + r] = t[threadIdx.x][i];
   }
 }
 
@@ -151,9 +151,10 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 
 using namespace pfpn;
 
-extern "C" int pfpn_transpose(const float* in, float* out, int32_t rows, int32_t cols, pfpn_stream_t stream_) {
-  if (!in || !out || rows <= 0 || cols <= 0) return PFPN_ERR_ARG;
-  transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream_)>>>(in, out, rows, cols);
+extern "C" int pfpn_transpose(const float* in, int32_t ldi, float* out, int32_t ldo, int32_t rows, int32_t cols,
+                              pfpn_stream_t stream_) {
+  if (!in || !out || rows <= 0 || cols <= 0 || ldi < cols || ldo < rows) return PFPN_ERR_ARG;
+  transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream_)>>>(in, out, rows, cols, ldi, ldo);
   PFPN_CUDA_OK(cudaGetLastError());
   return PFPN_OK;
 }

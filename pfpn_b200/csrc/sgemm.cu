@@ -335,3 +335,21 @@ extern "C" int pfpn_mlp_linear_bwd_weight(const float* X, int32_t ldx, const flo
   }
   return PFPN_OK;
 }
+
+// db[N] = column sums of dY[M,N] (bias gradient alone; the tensor-core weight-gradient path uses it)
+extern "C" int pfpn_bias_grad(const float* dY, int32_t ldy, float* db, int32_t M, int32_t N, void* workspace,
+                              size_t workspace_bytes, pfpn_stream_t stream_) {
+  if (!dY || !db || M <= 0 || N <= 0) return PFPN_ERR_ARG;
+  if (!workspace || workspace_bytes < (size_t)1024 * N * sizeof(float)) return PFPN_ERR_WORKSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  int chunks = (M + 255) / 256;
+  if (chunks > 1024) chunks = 1024;
+  const int rows_per = (M + chunks - 1) / chunks;
+  chunks = (M + rows_per - 1) / rows_per;
+  float* cpart = reinterpret_cast<float*>(workspace);
+  colsum_kernel<<<dim3((N + 63) / 64, chunks), 256, 0, st>>>(dY, M, N, ldy, rows_per, cpart, nullptr);
+  PFPN_CUDA_OK(cudaGetLastError());
+  colsum_reduce_kernel<<<(N + 255) / 256, 256, 0, st>>>(cpart, db, N, chunks);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}

@@ -33,6 +33,7 @@ struct TcParams {
   const float* bias;
   const float* Hm;
   int M, N, K, ldc, ldh, epi;
+  int k_chunk;  // split-K: K range per blockIdx.z (multiple of TC_BK); C then is [splits][M][ldc]
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
@@ -80,7 +81,9 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
-  const int nkb = (p.K + TC_BK - 1) / TC_BK;
+  const int k_begin = blockIdx.z * p.k_chunk;
+  const int k_end = min(p.K, k_begin + p.k_chunk);
+  const int nkb = (k_end - k_begin + TC_BK - 1) / TC_BK;  // (TMA zero-fills beyond K; chunks are TC_BK multiples)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -108,8 +111,8 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
         const int s = kb % TC_STAGES;
         mbar_wait(empty(s), (uint32_t)(((kb / TC_STAGES) & 1) ^ 1));
         mbar_expect_tx(full(s), 2 * TC_TILE_BYTES);
-        tma_load_2d(base + s * TC_STAGE_BYTES, &mapA, kb * TC_BK, m0, full(s));
-        tma_load_2d(base + s * TC_STAGE_BYTES + 2 * TC_TILE_BYTES, &mapB, kb * TC_BK, n0, full(s));
+        tma_load_2d(base + s * TC_STAGE_BYTES, &mapA, k_begin + kb * TC_BK, m0, full(s));
+        tma_load_2d(base + s * TC_STAGE_BYTES + 2 * TC_TILE_BYTES, &mapB, k_begin + kb * TC_BK, n0, full(s));
       }
     }
   } else if (warp == 1) {
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
             v.x = (h.x > 0.f && h.x < 6.f) ? v.x : 0.f; v.y = (h.y > 0.f && h.y < 6.f) ? v.y : 0.f;
             v.z = (h.z > 0.f && h.z < 6.f) ? v.z : 0.f; v.w = (h.w > 0.f && h.w < 6.f) ? v.w : 0.f;
           }
-          *reinterpret_cast<float4*>(p.C + (size_t)m * p.ldc + n) = v;
+          *reinterpret_cast<float4*>(p.C + ((size_t)blockIdx.z * p.M + m) * p.ldc + n) = v;
         }
       }
     }
@@ -296,9 +299,66 @@ extern "C" int pfpn_tc_gemm_nt(const float* A, int32_t lda, const float* Bt, int
     PFPN_CUDA_OK(cudaFuncSetAttribute((const void*)tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set = true;
   }
-  TcParams p{Cout, bias, Hm, M, N, K, ldc, ldh, epi};
+  TcParams p{Cout, bias, Hm, M, N, K, ldc, ldh, epi, (K + TC_BK - 1) / TC_BK * TC_BK};
   dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
   tc_gemm_kernel<<<grid, 256, TC_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream_)>>>(mapA, mapB, p);
   PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient on the tensor cores: dW[K,N] = X[M,K]^T dY[M,N] with both operands supplied
+// batch-contiguous (XT [K, M], dYT [N, M]).  The reduction axis is the batch, so the launch is
+// split-K in chunks of 2048 rows (<= 128 accumulations per TMEM accumulator, see above) and the
+// partial tiles are summed in fp32 in a fixed order.
+// ------------------------------------------------------------------------------------------------
+namespace pfpn {
+constexpr int TC_WGRAD_CHUNK = 2048;
+__global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, size_t n4, int splits,
+                                        size_t stride) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 s = make_float4(0, 0, 0, 0);
+  for (int z = 0; z < splits; ++z) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(part + (size_t)z * stride) + i);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  reinterpret_cast<float4*>(out)[i] = s;
+}
+}  // namespace pfpn
+
+extern "C" int pfpn_tc_wgrad_workspace_bytes(int32_t M, int32_t K, int32_t N, size_t* bytes) {
+  if (!bytes || M <= 0 || K <= 0 || N <= 0) return PFPN_ERR_ARG;
+  const size_t splits = ((size_t)M + TC_WGRAD_CHUNK - 1) / TC_WGRAD_CHUNK;
+  *bytes = splits * (size_t)K * N * sizeof(float) + 256;
+  return PFPN_OK;
+}
+
+extern "C" int pfpn_tc_linear_bwd_weight(const float* XT, int32_t ldxt, const float* dYT, int32_t ldyt, float* dW, int32_t M,
+                                         int32_t K, int32_t N, void* workspace, size_t workspace_bytes, pfpn_stream_t stream_) {
+  if (!XT || !dYT || !dW || M <= 0 || K <= 0 || N <= 0) return PFPN_ERR_ARG;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  if ((ldxt & 3) || (ldyt & 3) || (N & 3) || !al16(XT) || !al16(dYT) || !al16(dW) || !al16(workspace)) return PFPN_ERR_ALIGN;
+  const int splits = (M + TC_WGRAD_CHUNK - 1) / TC_WGRAD_CHUNK;
+  size_t need;
+  pfpn_tc_wgrad_workspace_bytes(M, K, N, &need);
+  if (splits > 1 && (!workspace || workspace_bytes < need)) return PFPN_ERR_WORKSPACE;
+  CUtensorMap mapA, mapB;
+  int rc = make_map(&mapA, XT, K, M, ldxt, TC_BM);   // rows = K_in, "K" axis = batch
+  if (rc != PFPN_OK) return rc;
+  rc = make_map(&mapB, dYT, N, M, ldyt, TC_BN);
+  if (rc != PFPN_OK) return rc;
+  PFPN_CUDA_OK(cudaFuncSetAttribute((const void*)tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  float* out = splits > 1 ? reinterpret_cast<float*>(workspace) : dW;
+  TcParams p{out, nullptr, nullptr, K, N, M, N, 0, TC_EPI_NONE, TC_WGRAD_CHUNK};
+  dim3 grid((N + TC_BN - 1) / TC_BN, (K + TC_BM - 1) / TC_BM, splits);
+  tc_gemm_kernel<<<grid, 256, TC_SMEM_BYTES, st>>>(mapA, mapB, p);
+  PFPN_CUDA_OK(cudaGetLastError());
+  if (splits > 1) {
+    const size_t n4 = (size_t)K * N / 4;
+    tc_splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(out, dW, n4, splits, (size_t)K * N);
+    PFPN_CUDA_OK(cudaGetLastError());
+  }
   return PFPN_OK;
 }

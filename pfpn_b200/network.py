@@ -182,7 +182,7 @@ class ParticleFilteringClipPPONetwork:
         for l in self.actor + [self.fc_policy] + self.critic[:-1]:
             if l.WT is None:
                 l.WT = torch.empty(l.n_out, l.k, dtype=torch.float32, device=self.device)
-            _cabi.check(_cabi.pfpn_transpose(l.W.data_ptr(), l.WT.data_ptr(), l.k, l.n_out, _stream_ptr()))
+            _cabi.check(_cabi.pfpn_transpose(l.W.data_ptr(), l.n_out, l.WT.data_ptr(), l.k, l.k, l.n_out, _stream_ptr()))
         self._wt_dirty = False
 
     def _linear(self, l: _Linear, X, Y, relu6):
@@ -312,6 +312,14 @@ class ParticleFilteringClipPPONetwork:
         for i in range(len(layers) - 1, -1, -1):
             l, X = layers[i], acts[i]
             M = X.shape[0]
+            if self.use_tensor_cores and l.n_out > 1 and M >= 512:
+                self._tc_wgrad(l, X, dY, M)
+                if i > 0:
+                    dX = self._buf(f"d_{l.name}", M, l.k)
+                    _cabi.check(_cabi.pfpn_tc_gemm_nt(dY.data_ptr(), dY.stride(0), l.W.data_ptr(), l.n_out, dX.data_ptr(),
+                                                      dX.stride(0), None, X.data_ptr(), X.stride(0), M, l.k, l.n_out, 3, st))
+                    dY = dX
+                continue
             n = C.c_size_t(0)
             _cabi.check(_cabi.pfpn_mlp_wgrad_workspace_bytes(M, l.k, l.n_out, C.byref(n)))
             ws = self._ws(n.value)
@@ -329,6 +337,21 @@ class ParticleFilteringClipPPONetwork:
                 _cabi.check(_cabi.pfpn_mlp_linear_bwd_input(dY.data_ptr(), ldy, l.W.data_ptr(), X.data_ptr(), dX.data_ptr(),
                                                             dX.stride(0), M, l.k, l.n_out, st))
                 dY = dX
+
+    def _tc_wgrad(self, l, X, dY, M):
+        """dW on the tensor cores: batch-contiguous copies of X and dY, split-K GEMM, bias column sums."""
+        st = _stream_ptr()
+        ldb = _pad4(M)
+        XT = self._buf(f"T_{l.name}_x", l.k, ldb)
+        YT = self._buf(f"T_{l.name}_dy", l.n_out, ldb)
+        _cabi.check(_cabi.pfpn_transpose(X.data_ptr(), X.stride(0), XT.data_ptr(), ldb, M, l.k, st))
+        _cabi.check(_cabi.pfpn_transpose(dY.data_ptr(), dY.stride(0), YT.data_ptr(), ldb, M, l.n_out, st))
+        n = C.c_size_t(0)
+        _cabi.check(_cabi.pfpn_tc_wgrad_workspace_bytes(M, l.k, l.n_out, C.byref(n)))
+        ws = self._ws(max(n.value, 1024 * l.n_out * 4))
+        _cabi.check(_cabi.pfpn_tc_linear_bwd_weight(XT.data_ptr(), ldb, YT.data_ptr(), ldb, l.dW.data_ptr(), M, l.k, l.n_out,
+                                                    ws.data_ptr(), ws.numel(), st))
+        _cabi.check(_cabi.pfpn_bias_grad(dY.data_ptr(), dY.stride(0), l.db.data_ptr(), M, l.n_out, ws.data_ptr(), ws.numel(), st))
 
     def _ws(self, nbytes):
         t = self._act.get("_ws")
