@@ -61,7 +61,7 @@ __device__ __forceinline__ float softplusf_acc(float x) {
 // the DPPO train step) with those branches compiled out.
 // CSM: per-(a,k) constants live in shared memory instead of registers.
 template <int LPR, int EPL, int RPT, int NSTAGE, int KM, int MAXT, int NREG, int PT, int AT, bool CSM>
-__global__ void __launch_bounds__(MAXT + 32) __maxnreg__(NREG) head_kernel(const HeadKParams kp) {
+__global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG) head_kernel(const HeadKParams kp) {
   constexpr bool BWD = KM != 0;
   constexpr bool LEAN = KM >= 2;
   constexpr int EP2 = (EPL + 1) / 2;  // packed pairs per lane
@@ -80,8 +80,9 @@ __global__ void __launch_bounds__(MAXT + 32) __maxnreg__(NREG) head_kernel(const
   const int slots = AT > 0 ? MAXT / (AT * LPR) : kp.slots;
   // SEG: a state's rows end on a 16-lane boundary, so the sum over a can be done with
   // half-warp partials (4 rows each) + one 16-lane butterfly instead of A/LPR strided reads.
-  constexpr bool SEG = AT > 0 && ((AT * LPR) % 16 == 0) && (AT * LPR / 16 <= 16);
-  constexpr int HPS = SEG ? AT * LPR / 16 : 1;  // half-warps per state
+  constexpr int GL = 4 * LPR;  // lanes of a 4-row group (a state ends on a group boundary when A % 4 == 0)
+  constexpr bool SEG = AT > 0 && (AT % 4 == 0) && GL <= 32;
+  constexpr int HPS = SEG ? AT / 4 : 1;  // 4-row groups per state
   const int TS = slots * RPT;
   const int tile_floats = TS * AP;
   const uint32_t mode = KM == 2 ? (uint32_t)PFPN_HEAD_PPO : (KM == 3 ? (uint32_t)PFPN_HEAD_GRAD : kp.a.mode);
@@ -349,11 +350,11 @@ __global__ void __launch_bounds__(MAXT + 32) __maxnreg__(NREG) head_kernel(const
         if (SEG) {
           // 4 rows of this half-warp -> one partial (lanes differing in bits 2,3 hold different rows)
           float pl = row_ok ? lnp : 0.f, ph = row_ok ? Hval : 0.f;
-          pl += __shfl_xor_sync(0xffffffffu, pl, 4);
-          ph += __shfl_xor_sync(0xffffffffu, ph, 4);
-          pl += __shfl_xor_sync(0xffffffffu, pl, 8);
-          ph += __shfl_xor_sync(0xffffffffu, ph, 8);
-          if ((tid & 15) == 0) rb[j * (MAXT / 16) + (tid >> 4)] = make_float2(pl, ph);
+          pl += __shfl_xor_sync(0xffffffffu, pl, LPR);
+          ph += __shfl_xor_sync(0xffffffffu, ph, LPR);
+          pl += __shfl_xor_sync(0xffffffffu, pl, 2 * LPR);
+          ph += __shfl_xor_sync(0xffffffffu, ph, 2 * LPR);
+          if ((tid % GL) == 0) rb[j * (MAXT / GL + 1) + (tid / GL)] = make_float2(pl, ph);
         } else if (row_ok && c == 0) {
           rb[row_off[j]] = make_float2(lnp, Hval);
         }
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(MAXT + 32) __maxnreg__(NREG) head_kernel(const
         // ---- log_prob of the state: sum over a of the per-row log p
         float lp = 0.f, en = 0.f;
         if (SEG) {
-          const float2* hb = rb + j * (MAXT / 16) + slot * HPS;
+          const float2* hb = rb + j * (MAXT / GL + 1) + slot * HPS;
 #pragma unroll
           for (int h = 0; h < HPS; ++h) {
             const float2 r = hb[h];
@@ -662,9 +663,9 @@ struct HeadVariant {
 // dims, P in {10, 35, 100}); PT == AT == 0 entries take both at run time.
 static const HeadVariant kHeadVariants[] = {
     PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, true),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, false),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 72, 35, 36, true),
     PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 6, 288, 96, 35, 36, true),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, false),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 5, 144, 128, 35, 36, true),
     PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 2, 5, 288, 96, 35, 36, true),
     PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 5, 288, 96, 100, 36, true),
     PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 4, 288, 72, 100, 36, true),
