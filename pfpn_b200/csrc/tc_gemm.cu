@@ -22,6 +22,9 @@
 
 namespace pfpn {
 
+#ifndef PFPN_TC_REWRITE_HI
+#define PFPN_TC_REWRITE_HI 0  // 0: rely on the tensor core ignoring the low 13 mantissa bits of a tf32 operand
+#endif
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                       // 16 KiB per operand tile
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                     // A_hi, A_lo, B_hi, B_lo
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
           h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
           h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
           h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
-          hi[i] = h;
+          if (PFPN_TC_REWRITE_HI) hi[i] = h;
           lo[i] = l;
         }
       }
