@@ -294,7 +294,7 @@ def main():
         um = torch.tensor([u0.elapsed_time(u1) / args.dppo_steps], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(um, op=dist.ReduceOp.MAX)
-        dppo = {"workload": f"DPPO minibatch update, B_total={B_PER_GPU} sharded over {world} GPU(s): 197-1024-512 actor+critic trunk (fp32 FFMA), PFPN head, local clip, NCCL all-reduce of the 8.4 MB bucket, Adam",
+        dppo = {"workload": f"DPPO minibatch update, B_total={B_PER_GPU} sharded over {world} GPU(s): 197-1024-512 actor+critic trunk (tcgen05 3xTF32 GEMMs), PFPN head, local clip, NCCL all-reduce of the 8.4 MB bucket, Adam",
                 "ms_per_update": float(um.item()), "samples_per_s": B_PER_GPU / (float(um.item()) * 1e-3), "scaling": "strong",
                 "trunk_tflops": 12.6e6 * B_PER_GPU / (float(um.item()) * 1e-3) / 1e12}
     clocks = sampler.stop() if sampler else None
