@@ -266,6 +266,29 @@ int pfpn_clip_by_global_norm(float* grads, size_t n, float clip, float* norm_sca
 int pfpn_adam_step(float* params, const float* grads, float* m, float* v, size_t n, float lr, float beta1,
                    float beta2, float eps, int64_t step, float grad_scale, pfpn_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * K7 fused with the data-parallel exchange: sum of the N ranks' clipped [gradient | statistics]
+ * buckets read straight from peer memory (NVLink P2P) + mean + Adam in ONE kernel.
+ * Replaces (semantics): SyncReplicasOptimizer accumulator mean + ApplyAdam
+ *                       models/sync_model.py:92-96, models/workers/base_worker.py:64-70.
+ * `buckets` / `flags` are HOST arrays of nranks DEVICE pointers (this rank's own buffer at index
+ * `rank`, the others mapped through CUDA IPC); flags[r] is an int32[nranks] array owned by rank r.
+ * Per step: write the bucket, pfpn_peer_signal(value = step), pfpn_peer_allreduce_adam(value = step).
+ * ---------------------------------------------------------------------- */
+int pfpn_enable_peer_access(int32_t peer_device);
+/* Peer-visible buffers: cudaMalloc'ed + zeroed, exported as a 64-byte CUDA IPC handle; `pfpn_peer_open`
+ * maps a peer's buffer into the caller's CURRENT device context with lazy peer access. */
+int pfpn_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int pfpn_peer_open(const unsigned char* handle64, void** ptr);
+int pfpn_peer_close(void* ptr);
+int pfpn_peer_free(void* ptr);
+int pfpn_peer_signal(const float* const* buckets, int32_t* const* flags, int32_t rank, int32_t nranks,
+                     int32_t value, pfpn_stream_t stream);
+int pfpn_peer_allreduce_adam(const float* const* buckets, int32_t* const* flags, int32_t rank, int32_t nranks,
+                             int32_t value, size_t n_params, size_t n_total, float* params, float* m, float* v,
+                             float* avg_out, float lr, float beta1, float beta2, float eps, int64_t step,
+                             pfpn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -149,3 +149,12 @@ pfpn_transpose = _sig("pfpn_transpose", C.c_int, [_vp, _i32, _vp, _i32, _i32, _i
 pfpn_tc_wgrad_workspace_bytes = _sig("pfpn_tc_wgrad_workspace_bytes", C.c_int, [_i32, _i32, _i32, C.POINTER(C.c_size_t)])
 pfpn_tc_linear_bwd_weight = _sig("pfpn_tc_linear_bwd_weight", C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _vp, C.c_size_t, _vp])
 pfpn_bias_grad = _sig("pfpn_bias_grad", C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp, C.c_size_t, _vp])
+pfpn_enable_peer_access = _sig("pfpn_enable_peer_access", C.c_int, [_i32])
+pfpn_peer_signal = _sig("pfpn_peer_signal", C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp])
+pfpn_peer_allreduce_adam = _sig("pfpn_peer_allreduce_adam", C.c_int,
+                                [_vp, _vp, _i32, _i32, _i32, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _vp, _f, _f, _f, _f,
+                                 C.c_int64, _vp])
+pfpn_peer_alloc = _sig("pfpn_peer_alloc", C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p])
+pfpn_peer_open = _sig("pfpn_peer_open", C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)])
+pfpn_peer_close = _sig("pfpn_peer_close", C.c_int, [_vp])
+pfpn_peer_free = _sig("pfpn_peer_free", C.c_int, [_vp])

@@ -1,0 +1,158 @@
+// K7 fused with the data-parallel exchange C1: one kernel that sums the clipped gradient buckets of
+// all ranks straight out of peer memory (NVLink 5 / NVSwitch P2P loads) and applies the averaged
+// gradient with Adam, instead of NCCL all-reduce + a separate Adam launch.
+//
+// Replaces (semantics): SyncReplicasOptimizer's accumulator mean + ApplyAdam
+//   /root/reference/models/sync_model.py:92-96, models/workers/base_worker.py:64-70.
+//
+// Protocol (one process per GPU, buffers shared through CUDA IPC by the host side):
+//   1. every rank writes its clipped [gradients | statistics] bucket into its own staging buffer
+//      (double-buffered by step parity) and then runs `peer_signal_kernel`, which publishes the step
+//      number into the flag array of every peer (system-scope fence + remote store);
+//   2. `peer_allreduce_adam_kernel` spins until all flags carry the step number, then every rank
+//      sums the N buckets in rank order 0..N-1 -- the same order on every rank, so the replicas stay
+//      bit-identical without a broadcast -- scales by 1/N, updates params / m / v for the gradient
+//      part and writes the averaged statistics back for the caller.
+// A staging buffer of parity p is rewritten two steps later; by then every peer has signalled the
+// step in between, which it does only after its own reduce kernel of the earlier step finished.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace pfpn {
+
+constexpr int kMaxPeers = 8;
+struct PeerPtrs {
+  const float* bucket[kMaxPeers];
+  int* flags[kMaxPeers];
+};
+
+__global__ void peer_signal_kernel(PeerPtrs pp, int rank, int nranks, int value) {
+  const int p = threadIdx.x;
+  if (p < nranks) {
+    __threadfence_system();  // this rank's bucket (written by earlier kernels on the stream) -> visible
+    *reinterpret_cast<volatile int*>(pp.flags[p] + rank) = value;
+  }
+}
+
+__global__ void __launch_bounds__(256) peer_allreduce_adam_kernel(PeerPtrs pp, int rank, int nranks, int value,
+                                                                  size_t n_params, size_t n_total, float* __restrict__ params,
+                                                                  float* __restrict__ m, float* __restrict__ v,
+                                                                  float* __restrict__ avg_out, float lr_t, float b1, float b2,
+                                                                  float eps) {
+  if (threadIdx.x < nranks) {
+    const volatile int* f = reinterpret_cast<const volatile int*>(pp.flags[rank]) + threadIdx.x;
+    while (*f < value) {
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const float inv_n = 1.f / (float)nranks;
+  const size_t n4 = n_total / 4;  // buckets are padded to a multiple of 4 floats
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < nranks; ++p) {  // fixed order: identical result on every rank
+      const float4 g = __ldcg(reinterpret_cast<const float4*>(pp.bucket[p]) + i);
+      s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+    }
+    s.x *= inv_n; s.y *= inv_n; s.z *= inv_n; s.w *= inv_n;
+    reinterpret_cast<float4*>(avg_out)[i] = s;
+    if (i * 4 < n_params) {  // n_params % 4 == 0
+      float4 mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i], pi = reinterpret_cast<float4*>(params)[i];
+#define PFPN_ADAM1(c)                                   \
+  mi.c = b1 * mi.c + (1.f - b1) * s.c;                  \
+  vi.c = b2 * vi.c + (1.f - b2) * s.c * s.c;            \
+  pi.c -= lr_t * mi.c / (sqrtf(vi.c) + eps);
+      PFPN_ADAM1(x) PFPN_ADAM1(y) PFPN_ADAM1(z) PFPN_ADAM1(w)
+#undef PFPN_ADAM1
+      reinterpret_cast<float4*>(m)[i] = mi;
+      reinterpret_cast<float4*>(v)[i] = vi;
+      reinterpret_cast<float4*>(params)[i] = pi;
+    }
+  }
+}
+
+}  // namespace pfpn
+
+using namespace pfpn;
+
+extern "C" int pfpn_enable_peer_access(int32_t peer_device) {
+  int dev = 0;
+  PFPN_CUDA_OK(cudaGetDevice(&dev));
+  if (dev == peer_device) return PFPN_OK;
+  int can = 0;
+  PFPN_CUDA_OK(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+  if (!can) return PFPN_ERR_UNSUPPORTED;
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return PFPN_OK;
+  }
+  return (int)e;
+}
+
+static int fill_peers(PeerPtrs* pp, const float* const* buckets, int32_t* const* flags, int nranks) {
+  if (!buckets || !flags || nranks < 1 || nranks > kMaxPeers) return PFPN_ERR_ARG;
+  for (int p = 0; p < kMaxPeers; ++p) {
+    pp->bucket[p] = p < nranks ? buckets[p] : nullptr;
+    pp->flags[p] = p < nranks ? flags[p] : nullptr;
+    if (p < nranks && (!buckets[p] || !flags[p])) return PFPN_ERR_ARG;
+  }
+  return PFPN_OK;
+}
+
+// `buckets` / `flags`: HOST arrays of nranks device pointers (peer-mapped), indexed by rank.
+extern "C" int pfpn_peer_signal(const float* const* buckets, int32_t* const* flags, int32_t rank, int32_t nranks,
+                                int32_t value, pfpn_stream_t stream_) {
+  PeerPtrs pp;
+  int rc = fill_peers(&pp, buckets, flags, nranks);
+  if (rc != PFPN_OK) return rc;
+  peer_signal_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(pp, rank, nranks, value);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}
+
+extern "C" int pfpn_peer_allreduce_adam(const float* const* buckets, int32_t* const* flags, int32_t rank, int32_t nranks,
+                                        int32_t value, size_t n_params, size_t n_total, float* params, float* m, float* v,
+                                        float* avg_out, float lr, float beta1, float beta2, float eps, int64_t step,
+                                        pfpn_stream_t stream_) {
+  PeerPtrs pp;
+  int rc = fill_peers(&pp, buckets, flags, nranks);
+  if (rc != PFPN_OK) return rc;
+  if (!params || !m || !v || !avg_out || (n_params & 3) || (n_total & 3) || n_params > n_total || step < 1) return PFPN_ERR_ARG;
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
+  peer_allreduce_adam_kernel<<<296, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      pp, rank, nranks, value, n_params, n_total, params, m, v, avg_out, (float)lr_t, beta1, beta2, eps);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}
+
+// ---- peer-visible allocations (cudaMalloc + CUDA IPC), opened on the CALLER's current device ----------
+extern "C" int pfpn_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
+  if (!ptr || !handle64 || bytes == 0) return PFPN_ERR_ARG;
+  PFPN_CUDA_OK(cudaMalloc(ptr, bytes));
+  PFPN_CUDA_OK(cudaMemset(*ptr, 0, bytes));
+  PFPN_CUDA_OK(cudaDeviceSynchronize());
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  PFPN_CUDA_OK(cudaIpcGetMemHandle(&h, *ptr));
+  memcpy(handle64, &h, 64);
+  return PFPN_OK;
+}
+extern "C" int pfpn_peer_open(const unsigned char* handle64, void** ptr) {
+  if (!ptr || !handle64) return PFPN_ERR_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  PFPN_CUDA_OK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return PFPN_OK;
+}
+extern "C" int pfpn_peer_close(void* ptr) {
+  if (!ptr) return PFPN_ERR_ARG;
+  PFPN_CUDA_OK(cudaIpcCloseMemHandle(ptr));
+  return PFPN_OK;
+}
+extern "C" int pfpn_peer_free(void* ptr) {
+  if (!ptr) return PFPN_ERR_ARG;
+  PFPN_CUDA_OK(cudaFree(ptr));
+  return PFPN_OK;
+}

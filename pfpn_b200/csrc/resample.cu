@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(1024) resample_plan_kernel(const pfpn_resample
         if (cdf[mid] > to_find) hi = mid;
         else lo = mid + 1;
       }
-      ws.cand[i] = lo;
+      ws.cand[i] = min(lo, P - 1);  // (all-zero statistics: TF would emit the out-of-range class P)
     }
   } else {
     for (int i = tid; i < AP; i += nthr) {  // descending rank, ties -> lower index

@@ -50,10 +50,15 @@ class SyncReplicasAdam:
     network whose parameters / gradients are flat buffers (pfpn_b200.network)."""
 
     def __init__(self, lr: float = 1e-4, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
-                 norm_clip: Optional[float] = 1.0, group=None):
+                 norm_clip: Optional[float] = 1.0, group=None, fused_peer: Optional[bool] = None):
         self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
         self.norm_clip = float(norm_clip) if norm_clip else 0.0
         self.group = group
+        # N > 1: sum the buckets straight out of NVLink peer memory inside the Adam kernel (csrc/comm.cu)
+        # instead of NCCL all-reduce + Adam; PFPN_FUSED_ALLREDUCE=0 selects the NCCL path.
+        import os
+        self.fused_peer = (os.environ.get("PFPN_FUSED_ALLREDUCE", "1") != "0") if fused_peer is None else fused_peer
+        self._peers = None
         self.step = 0
         self.m = self.v = None
         self.norm_scale = None
@@ -95,8 +100,10 @@ class SyncReplicasAdam:
         _cabi.check(_cabi.pfpn_clip_by_global_norm(net.grads.data_ptr(), net.n_params, self.norm_clip,
                                                    self.norm_scale.data_ptr(), self._scratch.data_ptr(),
                                                    self._scratch.numel(), st))
-        # 2-4. one all-reduce of [clipped gradients | statistics], mean, assign statistics
         self.pack_stats(net)
+        if self.fused_peer and world()[1] > 1 and net.params.is_cuda:
+            return self._apply_fused_peer(net, st)
+        # 2-4. one all-reduce of [clipped gradients | statistics], mean, assign statistics
         inv_n = allreduce_mean_(net.bucket, self.group)
         self.unpack_stats(net, inv_n)
         # 5. Adam (identical on every rank -> replicas stay bit-identical)
@@ -106,6 +113,27 @@ class SyncReplicasAdam:
         net.global_step += 1
         net._wt_dirty = True
         # 6. train_ops chained after the optimizer step (sync_model.py:79-81): resample tick
+        for op in net.train_ops:
+            op()
+
+    def _apply_fused_peer(self, net, st):
+        """Steps 2-5 in one kernel over peer memory: sum in rank order, mean, Adam, averaged statistics."""
+        from .peer import PeerBuckets
+        if self._peers is None:
+            self._peers = PeerBuckets(net.bucket.numel(), net.params.device, self.group)
+        pb = self._peers
+        self.step += 1
+        parity = self.step & 1
+        pb.stage[parity].copy_(net.bucket)  # publish this rank's clipped bucket (device-to-device, 8.4 MB)
+        buckets, flags = pb.ptrs(parity)
+        _cabi.check(_cabi.pfpn_peer_signal(buckets, flags, pb.rank, pb.world, self.step, st))
+        _cabi.check(_cabi.pfpn_peer_allreduce_adam(buckets, flags, pb.rank, pb.world, self.step, net.n_params,
+                                                   net.bucket.numel(), net.params.data_ptr(), self.m.data_ptr(),
+                                                   self.v.data_ptr(), net.bucket.data_ptr(), self.lr, self.beta1, self.beta2,
+                                                   self.eps, self.step, st))
+        self.unpack_stats(net, 1.0)  # the kernel wrote the averaged bucket back
+        net.global_step += 1
+        net._wt_dirty = True
         for op in net.train_ops:
             op()
 

@@ -1,0 +1,58 @@
+"""Peer-memory plumbing for the fused all-reduce + Adam kernel (csrc/comm.cu).
+
+Every rank owns a double-buffered staging area for its [gradient | statistics] bucket and an int32
+flag array, allocated by the library (cudaMalloc) and exported through CUDA IPC; the 64-byte handles
+travel over torch.distributed and every rank maps its peers' buffers into its own device context
+(cudaIpcOpenMemHandle with lazy peer access).  torch only wraps the local buffer as a tensor.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+
+
+class _CudaArray:
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _alloc(nbytes: int):
+    ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+    _cabi.check(_cabi.pfpn_peer_alloc(nbytes, C.byref(ptr), handle))
+    return ptr.value, handle.raw
+
+
+class PeerBuckets:
+    def __init__(self, n_total: int, device: torch.device, group=None):
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise ValueError("peer all-reduce covers one NVSwitch node (<= 8 ranks)")
+        self.n_total, self.dev, self.group = n_total, device, group
+        with torch.cuda.device(device):
+            self._stage_ptr, h_stage = _alloc(2 * n_total * 4)
+            self._flag_ptr, h_flag = _alloc(16 * 4)
+            self.stage = torch.as_tensor(_CudaArray(self._stage_ptr, 2 * n_total, "<f4"), device=device).view(2, n_total)
+            gathered: List = [None] * self.world
+            dist.all_gather_object(gathered, (h_stage, h_flag), group=group)
+            stage_ptrs, flag_ptrs = [], []
+            for r, (hs, hf) in enumerate(gathered):
+                if r == self.rank:
+                    stage_ptrs.append(self._stage_ptr)
+                    flag_ptrs.append(self._flag_ptr)
+                    continue
+                ps, pf = C.c_void_p(), C.c_void_p()
+                _cabi.check(_cabi.pfpn_peer_open(hs, C.byref(ps)))
+                _cabi.check(_cabi.pfpn_peer_open(hf, C.byref(pf)))
+                stage_ptrs.append(ps.value)
+                flag_ptrs.append(pf.value)
+        dist.barrier(group=group)
+        self._flag_ptrs = (C.c_void_p * self.world)(*flag_ptrs)
+        self._bucket_ptrs = [(C.c_void_p * self.world)(*[p + par * n_total * 4 for p in stage_ptrs]) for par in (0, 1)]
+
+    def ptrs(self, parity: int):
+        return self._bucket_ptrs[parity], self._flag_ptrs

@@ -1,0 +1,25 @@
+"""Fused peer-memory all-reduce + Adam (csrc/comm.cu) on >= 2 GPUs: replicas stay bit-identical and
+agree with the NCCL path.  Skipped on single-GPU boxes (the round-end GPU tier has one GPU)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_fused_peer_allreduce_adam_matches_nccl():
+    port = 29600 + os.getpid() % 300
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "test_peer_2gpu.py")],
+                       capture_output=True, text=True, timeout=600)
+    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 2, r.stdout[-2000:] + r.stderr[-2000:]
+    for d in lines:
+        assert d["replica_equal"] == [True, True] and d["stats_equal"]
+        assert d["max_abs_param_diff_fused_vs_nccl"] < 1e-7

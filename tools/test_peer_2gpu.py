@@ -1,0 +1,48 @@
+"""torchrun --nproc-per-node N: fused peer-memory all-reduce + Adam (csrc/comm.cu) vs the NCCL path."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+from pfpn_b200.learner import SyncReplicasAdam
+from pfpn_b200.network import ParticleFilteringClipPPONetwork
+
+rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local); dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+S, A, P, B = 197, 36, 35, 2048
+
+def make():
+    net = ParticleFilteringClipPPONetwork(True, [S], [A], action_lower_bound=[-1.] * A, action_upper_bound=[1.] * A, particles=P,
+                                          resample=-1, resample_interval=3, normalize_state=True, clip_state=5.0,
+                                          normalize_advantage=True, device=dev, seed=28949).init()
+    return net
+
+g = torch.Generator(device="cuda"); g.manual_seed(100 + rank)
+state = torch.randn(B, S, device=dev, generator=g); action = torch.rand(B, A, device=dev, generator=g) * 2 - 1
+value = torch.randn(B, device=dev, generator=g); adv = torch.randn(B, device=dev, generator=g)
+res = {}
+for name, fused in (("nccl", False), ("fused", True)):
+    net, opt = make(), SyncReplicasAdam(lr=1e-4, norm_clip=1.0, fused_peer=fused)
+    _, lp, _ = net.run_batch(state); lp_old = lp.clone()
+    for it in range(4):  # crosses a resample tick (interval 3): replicas must stay identical
+        net.compute_gradients(state, action, value, lp_old, adv)
+        opt.apply_gradients(net)
+    torch.cuda.synchronize()
+    snap = dict(params=net.params.clone(), mean=net.state_mean.clone(), maxa=net.max_active.clone())
+    # timing of the exchange + Adam alone (repeated applies on a stale bucket: timing only)
+    net.compute_gradients(state, action, value, lp_old, adv)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20): opt.apply_gradients(net)
+    e1.record(); torch.cuda.synchronize()
+    res[name] = dict(ms=e0.elapsed_time(e1) / 20, **snap)
+# replicas identical across ranks?
+for name in res:
+    ref = res[name]["params"].clone(); dist.broadcast(ref, 0)
+    res[name]["replica_equal"] = bool(torch.equal(ref, res[name]["params"]))
+d = (res["fused"]["params"] - res["nccl"]["params"]).abs().max().item()
+out = dict(rank=rank, world=world, max_abs_param_diff_fused_vs_nccl=d, replica_equal=(res["nccl"]["replica_equal"], res["fused"]["replica_equal"]),
+           stats_equal=bool(torch.allclose(res["fused"]["mean"], res["nccl"]["mean"], rtol=1e-6, atol=1e-7)),
+           ms_apply_nccl=round(res["nccl"]["ms"], 4), ms_apply_fused=round(res["fused"]["ms"], 4))
+print(json.dumps(out), flush=True)
+dist.barrier(); dist.destroy_process_group()
