@@ -123,8 +123,8 @@ struct Philox {
     uint32_t k0 = key[0], k1 = key[1];
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-      uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-      uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;  // one IMAD.WIDE each
+      const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
       c0 = hi1 ^ c1 ^ k0;
       c1 = lo1;
       c2 = hi0 ^ c3 ^ k1;

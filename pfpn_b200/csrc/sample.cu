@@ -107,128 +107,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32) sample_kernel(const pfpn_sa
     __syncwarp();
   }
 }
-
-// ------------------------------------------------------------------------------------------------
-// K3: reparameterised sample.  FWD writes sample / s_ / idx; BWD adds the straight-through
-// gradients into dlogits (overwritten) and dloc / dlogstd (atomically accumulated, pre-zeroed).
-// ------------------------------------------------------------------------------------------------
-template <bool BWD>
-__global__ void __launch_bounds__(kSampleWarps * 32) rsample_kernel(const pfpn_rsample_args ar) {
-  extern __shared__ float acc_s[];  // BWD: [2][A*P] per-CTA dloc / dlogstd partials
-  const int A = ar.A, P = ar.P, AP = A * P;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (BWD) {
-    for (int i = threadIdx.x; i < 2 * AP; i += blockDim.x) acc_s[i] = 0.f;
-    __syncthreads();
-  }
-  const long long rows = (long long)ar.B * A;
-  const Philox rng(ar.seed);
-  constexpr int MAXE = 8;  // particles per lane held in registers (P <= 256)
-  for (long long r = (long long)blockIdx.x * kSampleWarps + warp; r < rows; r += (long long)gridDim.x * kSampleWarps) {
-    const int a = (int)(r % A);
-    const float* x = ar.logits + r * P;
-    float y[MAXE], pk[MAXE], ek[MAXE];
-    float m = -3.402823466e38f;
-    int arg = 0x7fffffff;
-#pragma unroll
-    for (int e = 0; e < MAXE; ++e) {
-      const int k = lane + 32 * e;
-      y[e] = -3.402823466e38f;
-      pk[e] = 0.f;
-      ek[e] = 0.f;
-      if (k < P) {
-        float u, eps;
-        if (ar.ext_uniform != nullptr) {
-          u = ar.ext_uniform[r * P + k];
-          eps = ar.ext_normal[r * P + k];
-        } else {
-          const uint4 q = rng(ar.offset, (uint64_t)(r * P + k));
-          u = fmaxf(u32_to_unit_open(q.x), kF32Tiny);
-          const float u1 = u32_to_unit_open(q.y), u2 = u32_to_unit_open(q.z);
-          eps = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
-        }
-        const float g = -logf(-logf(u));  // Gumbel
-        y[e] = x[k] + g;                  // (G + logits) / T, T = 1
-        ek[e] = eps;
-        pk[e] = __fadd_rn(__fmul_rn(eps, expf(ar.logstd[a * P + k])), ar.loc[a * P + k]);
-      }
-      m = fmaxf(m, y[e]);
-    }
-    m = warp_max(m);
-    // argmax of w = argmax of the noisy logits; ties -> smallest index (tf.argmax)
-#pragma unroll
-    for (int e = 0; e < MAXE; ++e) {
-      const int k = lane + 32 * e;
-      if (k < P && y[e] == m) arg = min(arg, k);
-    }
-    arg = warp_min_i(arg);
-    float psel = 0.f, esel = 0.f;
-#pragma unroll
-    for (int e = 0; e < MAXE; ++e) {  // static register indexing: pick slot arg>>5 on lane arg&31
-      const float cand_p = __shfl_sync(0xffffffffu, pk[e], arg & 31);
-      const float cand_e = __shfl_sync(0xffffffffu, ek[e], arg & 31);
-      if (e == (arg >> 5)) {
-        psel = cand_p;
-        esel = cand_e;
-      }
-    }
-    const float t = tanhf(psel);
-    if (!BWD) {
-      if (lane == 0) {
-        ar.sample[r] = t;
-        ar.s_pre[r] = psel;
-        ar.idx[r] = arg;
-      }
-    } else {
-      // w = exp(log_softmax(y)); D_k = (tanh p_k - t) (g_a + g_u / max(1e-6, 1 - t^2))
-      float s = 0.f;
-#pragma unroll
-      for (int e = 0; e < MAXE; ++e) {
-        const int k = lane + 32 * e;
-        if (k < P) s += expf(y[e] - m);
-      }
-      s = warp_sum(s);
-      const float g_a = ar.g_sample[r];
-      const float g_u = ar.g_s_pre != nullptr ? ar.g_s_pre[r] : 0.f;
-      // 1 - tanh(u)^2 without the fp32 cancellation of the literal form (the fp64 oracle is the
-      // arbiter): sech^2(u) = 4 e^{-2|u|} / (1 + e^{-2|u|})^2
-      const float e2m = expf(-2.f * fabsf(psel));
-      const float omt2 = 4.f * e2m / ((1.f + e2m) * (1.f + e2m));
-      const float coef = g_a + g_u / fmaxf(1e-6f, omt2);
-      float wd = 0.f;
-      float w[MAXE], D[MAXE];
-#pragma unroll
-      for (int e = 0; e < MAXE; ++e) {
-        const int k = lane + 32 * e;
-        w[e] = 0.f;
-        D[e] = 0.f;
-        if (k < P) {
-          w[e] = expf(y[e] - m) / s;
-          D[e] = (tanhf(pk[e]) - t) * coef;
-          wd += w[e] * D[e];
-        }
-      }
-      wd = warp_sum(wd);
-#pragma unroll
-      for (int e = 0; e < MAXE; ++e) {
-        const int k = lane + 32 * e;
-        if (k < P) ar.dlogits[r * P + k] = w[e] * (D[e] - wd);
-      }
-      if (lane == 0) {
-        const float gp = omt2 * g_a + g_u;  // dL/dp_{k*}
-        atomicAdd(&acc_s[a * P + arg], gp);
-        atomicAdd(&acc_s[AP + a * P + arg], gp * expf(ar.logstd[a * P + arg]) * esel);
-      }
-    }
-  }
-  if (BWD) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < AP; i += blockDim.x) {
-      if (acc_s[i] != 0.f) atomicAdd(&ar.dloc[i], acc_s[i]);
-      if (acc_s[AP + i] != 0.f) atomicAdd(&ar.dlogstd[i], acc_s[AP + i]);
-    }
-  }
-}
+// K3 (reparameterised sample, forward + straight-through backward) lives in rsample.cu.
 
 // deterministic action: plain -> loc[argmax logits]; tanh -> tanh(loc[argmax softmax(logits)])
 __global__ void __launch_bounds__(kSampleWarps * 32) mean_kernel(const float* __restrict__ logits,
@@ -284,40 +163,6 @@ extern "C" int pfpn_head_sample(const pfpn_sample_args* args, pfpn_stream_t stre
   return PFPN_OK;
 }
 
-static int rsample_common(const pfpn_rsample_args& a) {
-  if (a.B < 0 || a.A <= 0 || a.P <= 0) return PFPN_ERR_ARG;
-  if (a.P > 256) return PFPN_ERR_UNSUPPORTED;
-  if (!a.logits || !a.loc || !a.logstd) return PFPN_ERR_ARG;
-  if ((a.ext_uniform == nullptr) != (a.ext_normal == nullptr)) return PFPN_ERR_ARG;
-  return PFPN_OK;
-}
-
-extern "C" int pfpn_head_rsample_fwd(const pfpn_rsample_args* args, pfpn_stream_t stream_) {
-  if (!args) return PFPN_ERR_ARG;
-  const pfpn_rsample_args& a = *args;
-  int rc = rsample_common(a);
-  if (rc != PFPN_OK) return rc;
-  if (a.B == 0) return PFPN_OK;
-  if (!a.sample || !a.s_pre || !a.idx) return PFPN_ERR_ARG;
-  rsample_kernel<false><<<rows_grid((long long)a.B * a.A), kSampleWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(a);
-  PFPN_CUDA_OK(cudaGetLastError());
-  return PFPN_OK;
-}
-
-extern "C" int pfpn_head_rsample_bwd(const pfpn_rsample_args* args, pfpn_stream_t stream_) {
-  if (!args) return PFPN_ERR_ARG;
-  const pfpn_rsample_args& a = *args;
-  int rc = rsample_common(a);
-  if (rc != PFPN_OK) return rc;
-  if (a.B == 0) return PFPN_OK;
-  if (!a.g_sample || !a.dlogits || !a.dloc || !a.dlogstd) return PFPN_ERR_ARG;
-  const size_t smem = 2 * (size_t)a.A * a.P * sizeof(float);
-  if (smem > 200 * 1024) return PFPN_ERR_UNSUPPORTED;
-  PFPN_CUDA_OK(cudaFuncSetAttribute((const void*)rsample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rsample_kernel<true><<<rows_grid((long long)a.B * a.A), kSampleWarps * 32, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(a);
-  PFPN_CUDA_OK(cudaGetLastError());
-  return PFPN_OK;
-}
 
 extern "C" int pfpn_head_mean(const float* logits, const float* loc, float* action, int32_t* idx, int32_t B, int32_t A,
                               int32_t P, uint32_t flags, pfpn_stream_t stream_) {

@@ -83,6 +83,51 @@ def test_rsample_forward_backward(cuda_dev, B, A, P):
     assert rel(dl, lg.grad) < TOL and rel(dc, lc.grad) < TOL and rel(ds, ls.grad) < TOL
 
 
+@pytest.mark.parametrize("P", [35, 100, 200])
+def test_rsample_philox_mode_distribution_and_fwd_bwd_consistency(cuda_dev, P):
+    """Production mode (Philox draws, MUFU arithmetic): the selected particle follows softmax(logits), the
+    location draw is N(0,1), and the backward regenerates exactly the draws the forward used."""
+    B, A = 20000, 6
+    g = torch.Generator().manual_seed(77 + P)
+    row = torch.randn(A, P, generator=g) * 1.5
+    logits = row.expand(B, A, P).contiguous()
+    loc_np, logstd_np = oh.init_particles(A, P, tanh=True)
+    loc = torch.tensor(loc_np, dtype=torch.float32)
+    logstd = torch.tensor(logstd_np, dtype=torch.float32) + 0.3 * torch.randn(A, P, generator=g)
+    cu = lambda t: t.to(cuda_dev)
+    kw = dict(seed=991, offset=5)
+    smp, spre, idx = sampling.rsample_fwd(cu(logits), cu(loc), cu(logstd), **kw)
+    smp2, spre2, idx2 = sampling.rsample_fwd(cu(logits), cu(loc), cu(logstd), **kw)
+    assert torch.equal(idx, idx2) and torch.equal(spre, spre2) and torch.equal(smp, smp2)
+    _, _, idx3 = sampling.rsample_fwd(cu(logits), cu(loc), cu(logstd), seed=991, offset=6)
+    assert not torch.equal(idx, idx3)
+    idx_l = idx.cpu().long()
+    assert int(idx_l.min()) >= 0 and int(idx_l.max()) < P
+    pi = torch.softmax(row.double(), -1)
+    for a in range(A):
+        freq = torch.bincount(idx_l[:, a], minlength=P).double() / B
+        sd = (pi[a] * (1 - pi[a]) / B).sqrt()
+        assert float(((freq - pi[a]).abs() / (sd + 1e-4)).max()) < 5.0
+    a_ix = torch.arange(A).expand(B, A)
+    z = (spre.cpu().double() - loc.double()[a_ix, idx_l]) / logstd.double().exp()[a_ix, idx_l]
+    assert abs(float(z.mean())) < 0.02 and abs(float(z.std()) - 1) < 0.02
+    assert abs(float((z ** 4).mean()) - 3.0) < 0.15 and float(z.abs().max()) < 6.5
+    assert rel(smp, torch.tanh(spre.cpu().double())) < TOL
+    # backward on the same (seed, offset): d loc[a,k] = sum over rows that selected k of sech^2(s_) g_a + g_u
+    g_a = torch.randn(B, A, generator=g)
+    g_u = torch.randn(B, A, generator=g) * 0.3
+    dl, dc, ds = sampling.rsample_bwd(cu(logits), cu(loc), cu(logstd), cu(g_a), cu(g_u), **kw)
+    s64 = spre.cpu().double()
+    gp = (1 - torch.tanh(s64) ** 2) * g_a.double() + g_u.double()
+    dc_ref = torch.zeros(A, P, dtype=torch.float64).index_put_((a_ix.reshape(-1), idx_l.reshape(-1)), gp.reshape(-1),
+                                                              accumulate=True)
+    ds_ref = torch.zeros(A, P, dtype=torch.float64).index_put_(
+        (a_ix.reshape(-1), idx_l.reshape(-1)), (gp * (s64 - loc.double()[a_ix, idx_l])).reshape(-1), accumulate=True)
+    assert rel(dc, dc_ref) < 1e-4 and rel(ds, ds_ref) < 1e-4
+    assert float(dl.sum(-1).abs().max()) < 1e-4  # softmax Jacobian rows sum to zero
+    assert torch.isfinite(dl).all()
+
+
 def test_sac_policy_gradient_through_the_distribution_object(cuda_dev):
     """sample -> log_prob((sample, s_)) -> alpha*logp - q(sample): the composition of sac.py:128-130,166-173."""
     B, A, P = 256, 36, 35
