@@ -643,17 +643,18 @@ __global__ void __launch_bounds__(1024) adv_stats_kernel(const float* __restrict
 // ---------------------------------------------------------------------------
 typedef void (*head_kernel_t)(const HeadKParams);
 
-// Compiled instantiations.  `pmax` = largest P the (LPR, EPL) pair covers; the
-// first entry whose pmax >= P is the default, PFPN_HEAD_VARIANT=<n> picks the
-// n-th matching entry instead (tuning aid, read once per process).
+// Compiled instantiations.  [pmin, pmax] = particle counts the (LPR, EPL) pair serves; the
+// first matching entry whose `kmmask` has the kernel mode's bit is the default for that
+// mode, PFPN_HEAD_VARIANT=<n> picks the n-th matching entry instead (tuning aid, read once).
 struct HeadVariant {
   int pmin, pmax, lpr, epl, rpt, nstage, maxt, nreg, pt, at, csm;
+  int kmmask;           // bit KM set: this entry may be the default for kernel mode KM (0 = tuning alternate only)
   head_kernel_t fn[4];  // indexed by KM
 };
 #define PFPN_HK(LPR, EPL, RPT, NST, KM, MAXT, NREG, PT, AT, CSM) head_kernel<LPR, EPL, RPT, NST, KM, MAXT, NREG, PT, AT, CSM>
-#define PFPN_HEAD_VARIANT_ENTRY(PMIN, PMAX, LPR, EPL, RPT, NST, MAXT, NREG, PT, AT, CSM)                       \
+#define PFPN_HEAD_VARIANT_ENTRY(PMIN, PMAX, LPR, EPL, RPT, NST, MAXT, NREG, PT, AT, CSM, KMM)                  \
   {                                                                                                            \
-    PMIN, PMAX, LPR, EPL, RPT, NST, MAXT, NREG, PT, AT, CSM, {                                                 \
+    PMIN, PMAX, LPR, EPL, RPT, NST, MAXT, NREG, PT, AT, CSM, KMM, {                                                 \
       PFPN_HK(LPR, EPL, RPT, NST, 0, MAXT, NREG, PT, AT, CSM), PFPN_HK(LPR, EPL, RPT, NST, 1, MAXT, NREG, PT, AT, CSM), \
           PFPN_HK(LPR, EPL, RPT, NST, 2, MAXT, NREG, PT, AT, CSM), PFPN_HK(LPR, EPL, RPT, NST, 3, MAXT, NREG, PT, AT, CSM) \
     }                                                                                                          \
@@ -662,27 +663,35 @@ struct HeadVariant {
 // exactly (P, A) == (PT, AT) -- the shapes BASELINE.json names (A = 36 DeepMimic action
 // dims, P in {10, 35, 100}); PT == AT == 0 entries take both at run time.
 static const HeadVariant kHeadVariants[] = {
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, true),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 6, 288, 96, 35, 36, true),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, false),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 5, 144, 128, 35, 36, true),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 2, 5, 288, 96, 35, 36, true),
-    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 5, 288, 96, 100, 36, true),
-    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 4, 288, 72, 100, 36, true),
-    PFPN_HEAD_VARIANT_ENTRY(10, 10, 4, 3, 2, 5, 288, 72, 10, 36, false),
-    PFPN_HEAD_VARIANT_ENTRY(1, 12, 4, 3, 2, 5, 320, 96, 0, 0, false),
-    PFPN_HEAD_VARIANT_ENTRY(13, 36, 4, 9, 1, 5, 288, 96, 0, 0, false),
-    PFPN_HEAD_VARIANT_ENTRY(37, 64, 8, 8, 1, 5, 320, 96, 0, 0, false),
-    PFPN_HEAD_VARIANT_ENTRY(65, 104, 8, 13, 1, 5, 288, 96, 0, 0, false),
-    PFPN_HEAD_VARIANT_ENTRY(105, 256, 16, 16, 1, 4, 320, 168, 0, 0, false),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, true, 15),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 6, 288, 96, 35, 36, true, 0),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, false, 0),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 5, 144, 128, 35, 36, true, 0),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 2, 5, 288, 96, 35, 36, true, 0),
+    // P = 100 (SAC sweep): 13 particles per lane spill in the backward modes at 96 registers, so those run
+    // 16 lanes per row (7 per lane, one 19-warp CTA per SM); the forward keeps 8 lanes and two CTAs per SM.
+    // Measured at B = 65536 (ms): FWD .252 (8 lanes) vs .51; PPO .64 vs .70; GRAD .59 vs .63; full .88 vs .91.
+    PFPN_HEAD_VARIANT_ENTRY(100, 100, 16, 7, 1, 6, 576, 96, 100, 36, true, 2 | 4),
+    PFPN_HEAD_VARIANT_ENTRY(100, 100, 16, 7, 1, 5, 576, 96, 100, 36, false, 8),
+    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 5, 288, 96, 100, 36, false, 1),
+    PFPN_HEAD_VARIANT_ENTRY(100, 100, 16, 7, 1, 5, 576, 96, 100, 36, true, 0),
+    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 4, 288, 96, 100, 36, true, 0),
+    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 4, 288, 72, 100, 36, true, 0),
+    PFPN_HEAD_VARIANT_ENTRY(10, 10, 4, 3, 2, 5, 288, 72, 10, 36, false, 15),
+    PFPN_HEAD_VARIANT_ENTRY(1, 12, 4, 3, 2, 5, 320, 96, 0, 0, false, 15),
+    PFPN_HEAD_VARIANT_ENTRY(13, 36, 4, 9, 1, 5, 288, 96, 0, 0, false, 15),
+    PFPN_HEAD_VARIANT_ENTRY(37, 64, 8, 8, 1, 5, 320, 96, 0, 0, false, 15),
+    PFPN_HEAD_VARIANT_ENTRY(65, 104, 8, 13, 1, 5, 288, 96, 0, 0, false, 15),
+    PFPN_HEAD_VARIANT_ENTRY(105, 256, 16, 16, 1, 4, 320, 168, 0, 0, false, 15),
 };
 
-static const HeadVariant* pick_variant(int A, int P) {
+static const HeadVariant* pick_variant(int A, int P, int km) {
   static const int want = []() {
     const char* e = getenv("PFPN_HEAD_VARIANT");
-    return e ? atoi(e) : 0;
+    return e ? atoi(e) : -1;
   }();
-  const HeadVariant* first = nullptr;
+  const HeadVariant* first = nullptr;   // first entry serving (A, P): defines the specialisation group
+  const HeadVariant* deflt = nullptr;   // first entry of that group allowed as default for this mode
   int seen = 0;
   for (const HeadVariant& v : kHeadVariants) {
     if (P < v.pmin || P > v.pmax) continue;
@@ -690,9 +699,10 @@ static const HeadVariant* pick_variant(int A, int P) {
     if (first == nullptr) first = &v;
     if (v.pt != first->pt || v.at != first->at) break;
     if (seen == want) return &v;
+    if (deflt == nullptr && (v.kmmask >> km & 1)) deflt = &v;
     ++seen;
   }
-  return first;
+  return deflt != nullptr ? deflt : first;
 }
 
 struct HeadLaunch {
@@ -703,7 +713,7 @@ struct HeadLaunch {
 
 static int plan_head(int A, int P, int km, HeadLaunch* L) {
   if (A <= 0 || P <= 0) return PFPN_ERR_ARG;
-  L->cfg = pick_variant(A, P);
+  L->cfg = pick_variant(A, P, km);
   if (L->cfg == nullptr) return PFPN_ERR_UNSUPPORTED;
   const HeadVariant& v = *L->cfg;
   const int per_slot = A * v.lpr;

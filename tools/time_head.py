@@ -16,8 +16,13 @@ out = head.head_call(_cabi.HEAD_FWD, logits, loc, logstd, value)
 lp_old = out["lp"] + 0.05 * torch.randn(B, device=dev, generator=g)
 stats = head.adv_stats(adv)
 res = {"variant": os.environ.get("PFPN_HEAD_VARIANT", "0"), "B": B, "A": A, "P": P}
-for name, mode in (("ppo", _cabi.HEAD_PPO), ("fwd", _cabi.HEAD_FWD)):
+g_lp = torch.randn(B, device=dev, generator=g)
+for name, mode in (("ppo", _cabi.HEAD_PPO), ("fwd", _cabi.HEAD_FWD), ("grad", _cabi.HEAD_GRAD), ("sac", _cabi.HEAD_GRAD)):
     kw = dict(adv=adv, lp_old=lp_old, adv_stats_t=stats) if mode == _cabi.HEAD_PPO else {}
+    if name == "grad":
+        kw = dict(g_lp=g_lp)
+    if name == "sac":  # tanh-squashed value (the pre-tanh sample), gradient w.r.t. the value as well
+        kw = dict(g_lp=g_lp, tanh=True, want_dvalue=True)
     o = {}
     for _ in range(5):
         head.head_call(mode, logits, loc, logstd, value, out=o, **kw)
