@@ -221,20 +221,26 @@ int pfpn_mlp_linear_bwd_weight(const float* X, int32_t ldx, const float* dY, int
                                int32_t M, int32_t K, int32_t N, void* workspace, size_t workspace_bytes,
                                pfpn_stream_t stream);
 
-/* K6, tensor-core path: C[M,N] = epi(A[M,K] * Bt[N,K]^T) with 3xTF32 error compensation on tcgen05
- * (TMA-fed, TMEM accumulator).  Same epilogues as the FFMA anchor; `Bt` is the weight transposed
- * for a forward layer and the weight as stored for the input gradient.
- * epi: 0 none, 1 +bias[n], 2 relu6(+bias), 3 multiply by 1[0 < Hm[m,n] < 6]. */
+/* K6, tensor-core path: 3xTF32 error-compensated GEMMs on tcgen05 (TMA-fed, TMEM accumulators), same
+ * epilogues as the FFMA anchor.  Operands are read as stored -- K-major or MN-major UMMA descriptors --
+ * so neither the weights nor the batch-major activations are ever transposed in HBM.
+ * epi: 0 none, 1 +bias[n], 2 relu6(+bias), 3 multiply by 1[0 < Hm[m,n] < 6].
+ *   pfpn_tc_gemm_nt: C[M,N] = epi(A[M,K] * Bt[N,K]^T)   input gradient dX = dY * W^T with Bt = W[in,out] as stored
+ *                    (replaces the MatMul(transpose_b) of the fc_layer gradient, networks/ops.py:82-118)
+ *   pfpn_tc_gemm_nn: C[M,N] = epi(A[M,K] * B[K,N])      forward act(X * W + b) with B = W as stored (ops.py:108-116) */
 int pfpn_tc_gemm_nt(const float* A, int32_t lda, const float* Bt, int32_t ldb, float* C, int32_t ldc,
                     const float* bias, const float* Hm, int32_t ldh, int32_t M, int32_t N, int32_t K,
                     int32_t epi, pfpn_stream_t stream);
-/* out[cols, ldo] = in[rows, ldi]^T -- K-major copies (W^T, batch-contiguous activations) for the tensor-core GEMMs. */
+int pfpn_tc_gemm_nn(const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
+                    const float* bias, const float* Hm, int32_t ldh, int32_t M, int32_t N, int32_t K,
+                    int32_t epi, pfpn_stream_t stream);
+/* out[cols, ldo] = in[rows, ldi]^T (utility; the GEMMs above no longer need transposed copies). */
 int pfpn_transpose(const float* in, int32_t ldi, float* out, int32_t ldo, int32_t rows, int32_t cols,
                    pfpn_stream_t stream);
-/* Weight gradient on tcgen05: dW[K,N] = X^T dY from batch-contiguous operands XT[K, M], dYT[N, M]
- * (split-K over the batch in chunks of 2048 rows, deterministic fp32 second stage). */
+/* Weight gradient on tcgen05: dW[K,N] = X[M,K]^T dY[M,N], X and dY row-major as stored (both MN-major
+ * operands; split-K over the batch in chunks of 2048 rows, deterministic fp32 second stage). */
 int pfpn_tc_wgrad_workspace_bytes(int32_t M, int32_t K, int32_t N, size_t* bytes);
-int pfpn_tc_linear_bwd_weight(const float* XT, int32_t ldxt, const float* dYT, int32_t ldyt, float* dW, int32_t M,
+int pfpn_tc_linear_bwd_weight(const float* X, int32_t ldx, const float* dY, int32_t ldy, float* dW, int32_t M,
                               int32_t K, int32_t N, void* workspace, size_t workspace_bytes, pfpn_stream_t stream);
 /* db[N] = column sums of dY[M,N]; workspace >= 1024*N floats. */
 int pfpn_bias_grad(const float* dY, int32_t ldy, float* db, int32_t M, int32_t N, void* workspace,

@@ -145,6 +145,7 @@ pfpn_value_loss = _sig("pfpn_value_loss", C.c_int, [_vp, _vp, _vp, _vp, _vp, _i3
 pfpn_clip_by_global_norm = _sig("pfpn_clip_by_global_norm", C.c_int, [_vp, C.c_size_t, _f, _vp, _vp, C.c_size_t, _vp])
 pfpn_adam_step = _sig("pfpn_adam_step", C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _f, _f, _f, _f, C.c_int64, _f, _vp])
 pfpn_tc_gemm_nt = _sig("pfpn_tc_gemm_nt", C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp])
+pfpn_tc_gemm_nn = _sig("pfpn_tc_gemm_nn", C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp])
 pfpn_transpose = _sig("pfpn_transpose", C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _vp])
 pfpn_tc_wgrad_workspace_bytes = _sig("pfpn_tc_wgrad_workspace_bytes", C.c_int, [_i32, _i32, _i32, C.POINTER(C.c_size_t)])
 pfpn_tc_linear_bwd_weight = _sig("pfpn_tc_linear_bwd_weight", C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _vp, C.c_size_t, _vp])

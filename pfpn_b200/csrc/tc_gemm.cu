@@ -1,7 +1,10 @@
 // K6 (tensor-core path) -- 3xTF32 error-compensated GEMM on tcgen05 with TMA-fed operands and
 // a TMEM accumulator, same epilogues as the FFMA anchor (csrc/sgemm.cu).
 //
-//   C[M,N] = A[M,K] * B[N,K]^T      (both operands K-major fp32, i.e. row-major [rows, K])
+//   C[M,N] = A[M,K] * B[N,K]^T      fp32 operands, each either K-major (row-major [rows, K]) or
+//                                   MN-major (row-major [K, rows]) -- template flags A_MN / B_MN.
+// With both majors available no operand is ever transposed in HBM: forward X*W (A K-major, W as
+// stored = MN-major B), input gradient dY*W^T (K-major, K-major), weight gradient X^T*dY (MN, MN).
 //
 // Plain TF32 (10-bit mantissa) cannot hold 1e-5 through three layers, so every fp32 operand is
 // split on the fly into hi = tf32(x) and lo = x - hi (exact) and three MMAs are accumulated:
@@ -58,6 +61,21 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
   return d;
 }
+// MN-major operand tile: four panels of [32 k-rows][32 floats along M/N] (what one TMA box of a row-major
+// [K, rows] matrix lands as).  For 32-bit MN-major operands the only swizzled layout the tensor core takes
+// is SWIZZLE_128B with 32-byte atomicity (layout type 1; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): the
+// 32-byte chunk index is XORed with the row index mod 4, so a swizzle atom is 4 k-rows of 128 B.
+// Canonical form ((4,8,m),(4,k)):((1,4,LBO),(32,SBO)) in floats: SBO = next 4 k-rows (512 B),
+// LBO = next 32-float panel (4096 B).
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(4096 >> 4) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -69,6 +87,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
                                                          const __grid_constant__ CUtensorMap mapB, const TcParams p) {
   extern __shared__ unsigned char smem_dyn[];
@@ -114,14 +133,27 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
         const int s = kb % TC_STAGES;
         mbar_wait(empty(s), (uint32_t)(((kb / TC_STAGES) & 1) ^ 1));
         mbar_expect_tx(full(s), 2 * TC_TILE_BYTES);
-        tma_load_2d(base + s * TC_STAGE_BYTES, &mapA, k_begin + kb * TC_BK, m0, full(s));
-        tma_load_2d(base + s * TC_STAGE_BYTES + 2 * TC_TILE_BYTES, &mapB, k_begin + kb * TC_BK, n0, full(s));
+        const uint32_t a_dst = base + s * TC_STAGE_BYTES, b_dst = a_dst + 2 * TC_TILE_BYTES;
+        const int k0 = k_begin + kb * TC_BK;
+        if (A_MN) {
+#pragma unroll
+          for (int q = 0; q < TC_BM / 32; ++q) tma_load_2d(a_dst + q * 4096, &mapA, m0 + 32 * q, k0, full(s));
+        } else {
+          tma_load_2d(a_dst, &mapA, k0, m0, full(s));
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int q = 0; q < TC_BN / 32; ++q) tma_load_2d(b_dst + q * 4096, &mapB, n0 + 32 * q, k0, full(s));
+        } else {
+          tma_load_2d(b_dst, &mapB, k0, n0, full(s));
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // instruction descriptor: D fp32, A/B tf32, both K-major, N = 128, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      // instruction descriptor: D fp32, A/B tf32, major bits 15 / 16 (0 = K-major, 1 = MN-major), N = 128, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % TC_STAGES;
         mbar_wait(conv(s), (uint32_t)((kb / TC_STAGES) & 1));
@@ -130,16 +162,20 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
         const uint32_t b_hi = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
 #pragma unroll
         for (int ks = 0; ks < TC_BK / 8; ++ks) {
-          const uint32_t off = ks * 32;  // 8 tf32 = 32 bytes along K inside the swizzle atom
+          // one MMA eats 8 tf32 along K: 32 bytes inside the swizzle atom (K-major) / one 8-row atom (MN-major)
+          const uint64_t da_hi = A_MN ? umma_desc_mn(a_hi + ks * 1024) : umma_desc(a_hi + ks * 32);
+          const uint64_t da_lo = A_MN ? umma_desc_mn(a_lo + ks * 1024) : umma_desc(a_lo + ks * 32);
+          const uint64_t db_hi = B_MN ? umma_desc_mn(b_hi + ks * 1024) : umma_desc(b_hi + ks * 32);
+          const uint64_t db_lo = B_MN ? umma_desc_mn(b_lo + ks * 1024) : umma_desc(b_lo + ks * 32);
           // The tensor core truncates its fp32 accumulator on every MMA (measured: ~2^-25 relative per
           // accumulation, systematic).  The dominant hi*hi products therefore get their own accumulator
           // (K/8 accumulations) and the two small correction products a second one, whose truncation is
           // relative to its 2^-11 times smaller magnitude; the epilogue adds the two in fp32.
           // Even / odd k-blocks alternate between two main accumulators, halving the chain again.
           const uint32_t dmain = tmem + (uint32_t)((kb & 1) * TC_BN);
-          umma_tf32(dmain, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, (kb >= 2 || ks != 0) ? 1u : 0u);
-          umma_tf32(tmem + 2 * TC_BN, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, (kb | ks) != 0);
-          umma_tf32(tmem + 2 * TC_BN, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1u);
+          umma_tf32(dmain, da_hi, db_hi, idesc, (kb >= 2 || ks != 0) ? 1u : 0u);
+          umma_tf32(tmem + 2 * TC_BN, da_lo, db_hi, idesc, (kb | ks) != 0);
+          umma_tf32(tmem + 2 * TC_BN, da_hi, db_lo, idesc, 1u);
         }
         umma_commit(empty(s));  // implicit tcgen05.fence::before_thread_sync
       }
@@ -263,57 +299,79 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// [rows, K] row-major fp32 -> tiles of (box_rows x 32 floats), SWIZZLE_128B, OOB reads return 0
-static int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld, int box_rows) {
+// K-major: [rows, K] row-major fp32 -> boxes of (box_rows x 32 floats along K);
+// MN-major: [K, rows] row-major fp32 -> boxes of (32 k-rows x 32 floats along M/N).  128-byte swizzle (16-byte
+// chunks for K-major, 32-byte chunks for MN-major), OOB reads return 0.
+static int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld, int box_rows, bool mn_major = false) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return PFPN_ERR_UNSUPPORTED;
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t dims[2] = {(cuuint64_t)(mn_major ? rows : K), (cuuint64_t)(mn_major ? K : rows)};
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {32u, (cuuint32_t)(mn_major ? TC_BK : box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? PFPN_OK : PFPN_ERR_UNSUPPORTED;
+}
+
+template <bool A_MN, bool B_MN>
+static int tc_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcParams& p, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    PFPN_CUDA_OK(cudaFuncSetAttribute((const void*)tc_gemm_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  tc_gemm_kernel<A_MN, B_MN><<<grid, 256, TC_SMEM_BYTES, st>>>(mapA, mapB, p);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}
+
+static int tc_gemm_common(const float* A, int lda, const float* Bm, int ldb, bool b_mn, float* Cout, int ldc, const float* bias,
+                          const float* Hm, int ldh, int M, int N, int K, int epi, cudaStream_t st) {
+  if (!A || !Bm || !Cout || M < 0 || N <= 0 || K <= 0 || epi < 0 || epi > 3) return PFPN_ERR_ARG;
+  if ((epi == TC_EPI_BIAS || epi == TC_EPI_BIAS_RELU6) && !bias) return PFPN_ERR_ARG;
+  if (epi == TC_EPI_MASK6 && !Hm) return PFPN_ERR_ARG;
+  if (M == 0) return PFPN_OK;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  if ((lda & 3) || (ldb & 3) || (ldc & 3) || (N & 3) || (K & 3) || !al16(A) || !al16(Bm) || !al16(Cout)) return PFPN_ERR_ALIGN;
+  CUtensorMap mapA, mapB;
+  int rc = make_map(&mapA, A, M, K, lda, TC_BM);
+  if (rc != PFPN_OK) return rc;
+  rc = make_map(&mapB, Bm, N, K, ldb, TC_BN, b_mn);
+  if (rc != PFPN_OK) return rc;
+  TcParams p{Cout, bias, Hm, M, N, K, ldc, ldh, epi, (K + TC_BK - 1) / TC_BK * TC_BK};
+  dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
+  return b_mn ? tc_launch<false, true>(mapA, mapB, p, grid, st) : tc_launch<false, false>(mapA, mapB, p, grid, st);
 }
 
 }  // namespace pfpn
 
 using namespace pfpn;
 
-// C[M,N] = epi(A[M,K] * Bt[N,K]^T): the tensor-core twin of pfpn_mlp_linear_fwd (Bt = W^T) and
-// pfpn_mlp_linear_bwd_input (Bt = W as stored).  epi: 0 none, 1 +bias, 2 relu6(+bias), 3 Relu6Grad mask by Hm.
+// C[M,N] = epi(A[M,K] * Bt[N,K]^T): the tensor-core twin of pfpn_mlp_linear_bwd_input (Bt = W as stored, [in, out]
+// seen as [N = in, K = out]).  epi: 0 none, 1 +bias, 2 relu6(+bias), 3 Relu6Grad mask by Hm.
 extern "C" int pfpn_tc_gemm_nt(const float* A, int32_t lda, const float* Bt, int32_t ldb, float* Cout, int32_t ldc,
                                const float* bias, const float* Hm, int32_t ldh, int32_t M, int32_t N, int32_t K,
                                int32_t epi, pfpn_stream_t stream_) {
-  if (!A || !Bt || !Cout || M < 0 || N <= 0 || K <= 0 || epi < 0 || epi > 3) return PFPN_ERR_ARG;
-  if ((epi == TC_EPI_BIAS || epi == TC_EPI_BIAS_RELU6) && !bias) return PFPN_ERR_ARG;
-  if (epi == TC_EPI_MASK6 && !Hm) return PFPN_ERR_ARG;
-  if (M == 0) return PFPN_OK;
-  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-  if ((lda & 3) || (ldb & 3) || (ldc & 3) || (N & 3) || (K & 3) || !al16(A) || !al16(Bt) || !al16(Cout)) return PFPN_ERR_ALIGN;
-  CUtensorMap mapA, mapB;
-  int rc = make_map(&mapA, A, M, K, lda, TC_BM);
-  if (rc != PFPN_OK) return rc;
-  rc = make_map(&mapB, Bt, N, K, ldb, TC_BN);
-  if (rc != PFPN_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PFPN_CUDA_OK(cudaFuncSetAttribute((const void*)tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    attr_set = true;
-  }
-  TcParams p{Cout, bias, Hm, M, N, K, ldc, ldh, epi, (K + TC_BK - 1) / TC_BK * TC_BK};
-  dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
-  tc_gemm_kernel<<<grid, 256, TC_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream_)>>>(mapA, mapB, p);
-  PFPN_CUDA_OK(cudaGetLastError());
-  return PFPN_OK;
+  return tc_gemm_common(A, lda, Bt, ldb, false, Cout, ldc, bias, Hm, ldh, M, N, K, epi, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+// C[M,N] = epi(A[M,K] * B[K,N]): the tensor-core twin of pfpn_mlp_linear_fwd with W as stored ([in, out] row-major,
+// read as an MN-major operand -- no transposed copy of the weights).
+extern "C" int pfpn_tc_gemm_nn(const float* A, int32_t lda, const float* B, int32_t ldb, float* Cout, int32_t ldc,
+                               const float* bias, const float* Hm, int32_t ldh, int32_t M, int32_t N, int32_t K,
+                               int32_t epi, pfpn_stream_t stream_) {
+  return tc_gemm_common(A, lda, B, ldb, true, Cout, ldc, bias, Hm, ldh, M, N, K, epi, reinterpret_cast<cudaStream_t>(stream_));
 }
 
 // ------------------------------------------------------------------------------------------------
-// Weight gradient on the tensor cores: dW[K,N] = X[M,K]^T dY[M,N] with both operands supplied
-// batch-contiguous (XT [K, M], dYT [N, M]).  The reduction axis is the batch, so the launch is
-// split-K in chunks of 2048 rows (<= 128 accumulations per TMEM accumulator, see above) and the
-// partial tiles are summed in fp32 in a fixed order.
+// Weight gradient on the tensor cores: dW[K,N] = X[M,K]^T dY[M,N], X and dY as stored (row-major,
+// batch-major): both are MN-major operands of the GEMM whose reduction axis is the batch.  The
+// launch is split-K in chunks of 2048 rows (<= 128 accumulations per TMEM accumulator, see above)
+// and the partial tiles are summed in fp32 in a fixed order.
 // ------------------------------------------------------------------------------------------------
 namespace pfpn {
 constexpr int TC_WGRAD_CHUNK = 2048;
@@ -337,27 +395,26 @@ extern "C" int pfpn_tc_wgrad_workspace_bytes(int32_t M, int32_t K, int32_t N, si
   return PFPN_OK;
 }
 
-extern "C" int pfpn_tc_linear_bwd_weight(const float* XT, int32_t ldxt, const float* dYT, int32_t ldyt, float* dW, int32_t M,
+extern "C" int pfpn_tc_linear_bwd_weight(const float* X, int32_t ldx, const float* dY, int32_t ldy, float* dW, int32_t M,
                                          int32_t K, int32_t N, void* workspace, size_t workspace_bytes, pfpn_stream_t stream_) {
-  if (!XT || !dYT || !dW || M <= 0 || K <= 0 || N <= 0) return PFPN_ERR_ARG;
+  if (!X || !dY || !dW || M <= 0 || K <= 0 || N <= 0) return PFPN_ERR_ARG;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-  if ((ldxt & 3) || (ldyt & 3) || (N & 3) || !al16(XT) || !al16(dYT) || !al16(dW) || !al16(workspace)) return PFPN_ERR_ALIGN;
+  if ((ldx & 3) || (ldy & 3) || (N & 3) || !al16(X) || !al16(dY) || !al16(dW) || !al16(workspace)) return PFPN_ERR_ALIGN;
   const int splits = (M + TC_WGRAD_CHUNK - 1) / TC_WGRAD_CHUNK;
   size_t need;
   pfpn_tc_wgrad_workspace_bytes(M, K, N, &need);
   if (splits > 1 && (!workspace || workspace_bytes < need)) return PFPN_ERR_WORKSPACE;
   CUtensorMap mapA, mapB;
-  int rc = make_map(&mapA, XT, K, M, ldxt, TC_BM);   // rows = K_in, "K" axis = batch
+  int rc = make_map(&mapA, X, K, M, ldx, TC_BM, true);  // GEMM rows = K_in, reduction axis = batch
   if (rc != PFPN_OK) return rc;
-  rc = make_map(&mapB, dYT, N, M, ldyt, TC_BN);
+  rc = make_map(&mapB, dY, N, M, ldy, TC_BN, true);
   if (rc != PFPN_OK) return rc;
-  PFPN_CUDA_OK(cudaFuncSetAttribute((const void*)tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   float* out = splits > 1 ? reinterpret_cast<float*>(workspace) : dW;
   TcParams p{out, nullptr, nullptr, K, N, M, N, 0, TC_EPI_NONE, TC_WGRAD_CHUNK};
   dim3 grid((N + TC_BN - 1) / TC_BN, (K + TC_BM - 1) / TC_BM, splits);
-  tc_gemm_kernel<<<grid, 256, TC_SMEM_BYTES, st>>>(mapA, mapB, p);
-  PFPN_CUDA_OK(cudaGetLastError());
+  rc = tc_launch<true, true>(mapA, mapB, p, grid, st);
+  if (rc != PFPN_OK) return rc;
   if (splits > 1) {
     const size_t n4 = (size_t)K * N / 4;
     tc_splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(out, dW, n4, splits, (size_t)K * N);

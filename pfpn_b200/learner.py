@@ -111,7 +111,6 @@ class SyncReplicasAdam:
         _cabi.check(_cabi.pfpn_adam_step(net.params.data_ptr(), net.grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                          net.n_params, self.lr, self.beta1, self.beta2, self.eps, self.step, inv_n, st))
         net.global_step += 1
-        net._wt_dirty = True
         # 6. train_ops chained after the optimizer step (sync_model.py:79-81): resample tick
         for op in net.train_ops:
             op()
@@ -133,7 +132,6 @@ class SyncReplicasAdam:
                                                    self.eps, self.step, st))
         self.unpack_stats(net, 1.0)  # the kernel wrote the averaged bucket back
         net.global_step += 1
-        net._wt_dirty = True
         for op in net.train_ops:
             op()
 

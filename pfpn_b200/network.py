@@ -36,7 +36,7 @@ class _Linear:
     def __init__(self, name, k_in, n_out, k_pad=None):
         self.name, self.k_in, self.n_out = name, k_in, n_out
         self.k = k_pad or k_in  # rows of the stored W (zero rows beyond k_in)
-        self.W = self.b = self.dW = self.db = self.WT = None
+        self.W = self.b = self.dW = self.db = None
 
     def numel(self):
         return self.k * self.n_out + self.n_out
@@ -90,7 +90,6 @@ class ParticleFilteringClipPPONetwork:
         # fp32 FFMA anchor is requested
         import os
         self.use_tensor_cores = os.environ.get("PFPN_TRUNK", "tc") != "ffma"
-        self._wt_dirty = True
 
     # ------------------------------------------------------------------------------ build ----
     def init(self):
@@ -177,19 +176,10 @@ class ParticleFilteringClipPPONetwork:
             self._act[name] = t
         return t
 
-    def _refresh_wt(self):
-        """K-major copies W^T of the weights for the tensor-core forward GEMMs (8 MB per refresh)."""
-        for l in self.actor + [self.fc_policy] + self.critic[:-1]:
-            if l.WT is None:
-                l.WT = torch.empty(l.n_out, l.k, dtype=torch.float32, device=self.device)
-            _cabi.check(_cabi.pfpn_transpose(l.W.data_ptr(), l.n_out, l.WT.data_ptr(), l.k, l.k, l.n_out, _stream_ptr()))
-        self._wt_dirty = False
-
     def _linear(self, l: _Linear, X, Y, relu6):
         if self.use_tensor_cores and l.n_out > 1:
-            if self._wt_dirty:
-                self._refresh_wt()
-            _cabi.check(_cabi.pfpn_tc_gemm_nt(X.data_ptr(), X.stride(0), l.WT.data_ptr(), l.k, Y.data_ptr(), Y.stride(0),
+            # W [in, out] as stored is the MN-major B operand: no transposed copy of the weights
+            _cabi.check(_cabi.pfpn_tc_gemm_nn(X.data_ptr(), X.stride(0), l.W.data_ptr(), l.n_out, Y.data_ptr(), Y.stride(0),
                                               l.b.data_ptr(), None, 0, X.shape[0], l.n_out, l.k, 2 if relu6 else 1,
                                               _stream_ptr()))
             return
@@ -339,18 +329,13 @@ class ParticleFilteringClipPPONetwork:
                 dY = dX
 
     def _tc_wgrad(self, l, X, dY, M):
-        """dW on the tensor cores: batch-contiguous copies of X and dY, split-K GEMM, bias column sums."""
+        """dW on the tensor cores: X and dY as stored (MN-major operands), split-K GEMM, bias column sums."""
         st = _stream_ptr()
-        ldb = _pad4(M)
-        XT = self._buf(f"T_{l.name}_x", l.k, ldb)
-        YT = self._buf(f"T_{l.name}_dy", l.n_out, ldb)
-        _cabi.check(_cabi.pfpn_transpose(X.data_ptr(), X.stride(0), XT.data_ptr(), ldb, M, l.k, st))
-        _cabi.check(_cabi.pfpn_transpose(dY.data_ptr(), dY.stride(0), YT.data_ptr(), ldb, M, l.n_out, st))
         n = C.c_size_t(0)
         _cabi.check(_cabi.pfpn_tc_wgrad_workspace_bytes(M, l.k, l.n_out, C.byref(n)))
         ws = self._ws(max(n.value, 1024 * l.n_out * 4))
-        _cabi.check(_cabi.pfpn_tc_linear_bwd_weight(XT.data_ptr(), ldb, YT.data_ptr(), ldb, l.dW.data_ptr(), M, l.k, l.n_out,
-                                                    ws.data_ptr(), ws.numel(), st))
+        _cabi.check(_cabi.pfpn_tc_linear_bwd_weight(X.data_ptr(), X.stride(0), dY.data_ptr(), dY.stride(0), l.dW.data_ptr(),
+                                                    M, l.k, l.n_out, ws.data_ptr(), ws.numel(), st))
         _cabi.check(_cabi.pfpn_bias_grad(dY.data_ptr(), dY.stride(0), l.db.data_ptr(), M, l.n_out, ws.data_ptr(), ws.numel(), st))
 
     def _ws(self, nbytes):
@@ -377,7 +362,6 @@ class ParticleFilteringClipPPONetwork:
                                   self.policy_weight, resample=self.resample, threshold=self.resample_threshold,
                                   tanh=self.normalize_policy_output_, seed=self.seed + 1, offset=3 * self.global_step)
             self.train_flag = 0
-            self._wt_dirty = True
             return True
         return False
 
@@ -392,7 +376,6 @@ class ParticleFilteringClipPPONetwork:
         for k in ("state_mean", "state_std", "max_active", "sum_active"):
             getattr(self, k).copy_(sd[k])
         self.train_flag, self.global_step = int(sd["train_flag"]), int(sd["global_step"])
-        self._wt_dirty = True
 
     def named_parameters(self):
         """Reference variable names ([.index] of the shipped checkpoint) -> (param view, grad view)."""

@@ -37,3 +37,43 @@ def test_tc_gemm_nt_matches_fp64(cuda_dev, M, N, K, epi):
         ref = ref * ((H > 0) & (H < 6)).double()
     assert torch.isfinite(C).all()
     assert rel(C, ref) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (300, 1024, 200), (1000, 512, 1024), (517, 1260, 512), (77, 132, 36)])
+@pytest.mark.parametrize("epi", [1, 2])
+def test_tc_gemm_nn_weights_as_stored(cuda_dev, M, N, K, epi):
+    """Forward layer act(X W + b) with W [in, out] read as an MN-major operand (no transposed copy)."""
+    g = torch.Generator().manual_seed(M * 5 + N + K + epi)
+    X = torch.randn(M, K, generator=g)
+    W = torch.randn(K, N, generator=g) * 0.05
+    bias = torch.randn(N, generator=g) * 0.1
+    cu = lambda t: t.to(cuda_dev).contiguous()
+    Xd, Wd, bd = cu(X), cu(W), cu(bias)
+    C = torch.full((M, N), float("nan"), device=cuda_dev)
+    _cabi.check(_cabi.pfpn_tc_gemm_nn(Xd.data_ptr(), K, Wd.data_ptr(), N, C.data_ptr(), N, bd.data_ptr(), None, 0,
+                                      M, N, K, epi, _stream_ptr()))
+    ref = X.double() @ W.double() + bias.double()
+    if epi == 2:
+        ref = ref.clamp(0, 6)
+    assert torch.isfinite(C).all()
+    assert rel(C, ref) < 1e-5
+
+
+@pytest.mark.parametrize("M,K,N", [(2048, 200, 1024), (5000, 1024, 512), (4099, 512, 1260), (513, 36, 132), (65536, 200, 128)])
+def test_tc_wgrad_operands_as_stored(cuda_dev, M, K, N):
+    """dW = X^T dY from row-major X [M, K] and dY [M, N] (both MN-major operands), split-K over the batch."""
+    g = torch.Generator().manual_seed(M + K + N)
+    X = torch.randn(M, K, generator=g)
+    dY = torch.randn(M, N, generator=g) * 0.01
+    cu = lambda t: t.to(cuda_dev).contiguous()
+    Xd, Yd = cu(X), cu(dY)
+    import ctypes as C
+    n = C.c_size_t(0)
+    _cabi.check(_cabi.pfpn_tc_wgrad_workspace_bytes(M, K, N, C.byref(n)))
+    ws = torch.empty(max(n.value, 16), dtype=torch.uint8, device=cuda_dev)
+    dW = torch.full((K, N), float("nan"), device=cuda_dev)
+    _cabi.check(_cabi.pfpn_tc_linear_bwd_weight(Xd.data_ptr(), K, Yd.data_ptr(), N, dW.data_ptr(), M, K, N, ws.data_ptr(),
+                                                ws.numel(), _stream_ptr()))
+    ref = X.double().T @ dY.double()
+    assert torch.isfinite(dW).all()
+    assert rel(dW, ref) < 1e-5
