@@ -14,9 +14,11 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B) of A and B into a 3-stage ring
 //   warp 1      single-thread tcgen05.mma issuer (kind::tf32, M=128, N=128, K=8), tcgen05.commit
 //   warp 2      TMEM allocator (all 512 columns: two alternating main accumulators + one correction)
-//   warps 4-7   splitter: rewrite the landed tile as hi (in place) and lo (second buffer), element
-//               wise in the swizzled layout; afterwards the epilogue: tcgen05.ld -> bias / relu6 /
-//               Relu6Grad mask -> global stores
+//   warps 4-7   splitter: thread m moves row m of the landed A tile into TENSOR MEMORY as (hi, lo) with
+//               tcgen05.st -- the MMAs then take A from TMEM and only B from shared memory, which is
+//               the scarce resource of this kernel -- and writes the B_lo tile elementwise in the
+//               swizzled layout; afterwards the epilogue: tcgen05.ld -> bias / relu6 / Relu6Grad
+//               mask -> global stores
 // Pipelines: full[s] (TMA -> splitter), conv[s] (splitter -> MMA), empty[s] (MMA -> TMA),
 // tmem_full (MMA -> epilogue).
 #include <cuda.h>
@@ -25,13 +27,13 @@
 
 namespace pfpn {
 
-#ifndef PFPN_TC_REWRITE_HI
-#define PFPN_TC_REWRITE_HI 0  // 0: rely on the tensor core ignoring the low 13 mantissa bits of a tf32 operand
-#endif
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 4;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                       // 16 KiB per operand tile
-constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                     // A_hi, A_lo, B_hi, B_lo
+constexpr int TC_STAGE_BYTES = 3 * TC_TILE_BYTES;                     // A (raw), B (raw = hi), B_lo
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 + 256;  // + alignment slack + barriers
+// TMEM columns: [0,128) [128,256) main accumulators (even / odd k-blocks), [256,384) correction
+// accumulator, [384,512) the A operand: two slots of (hi: 32 columns, lo: 32 columns)
+constexpr uint32_t TC_TMEM_A = 3 * TC_BN;
 enum { TC_EPI_NONE = 0, TC_EPI_BIAS = 1, TC_EPI_BIAS_RELU6 = 2, TC_EPI_MASK6 = 3 };
 
 struct TcParams {
@@ -81,6 +83,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// A operand from tensor memory (lane = row m, 32-bit column = k), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -133,7 +154,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
         const int s = kb % TC_STAGES;
         mbar_wait(empty(s), (uint32_t)(((kb / TC_STAGES) & 1) ^ 1));
         mbar_expect_tx(full(s), 2 * TC_TILE_BYTES);
-        const uint32_t a_dst = base + s * TC_STAGE_BYTES, b_dst = a_dst + 2 * TC_TILE_BYTES;
+        const uint32_t a_dst = base + s * TC_STAGE_BYTES, b_dst = a_dst + TC_TILE_BYTES;
         const int k0 = k_begin + kb * TC_BK;
         if (A_MN) {
 #pragma unroll
@@ -151,20 +172,19 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // instruction descriptor: D fp32, A/B tf32, major bits 15 / 16 (0 = K-major, 1 = MN-major), N = 128, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+      // instruction descriptor: D fp32, A/B tf32, A from TMEM (always K-major), B major bit 16 (1 = MN-major), N = 128, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % TC_STAGES;
         mbar_wait(conv(s), (uint32_t)((kb / TC_STAGES) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = base + s * TC_STAGE_BYTES, a_lo = a_hi + TC_TILE_BYTES;
-        const uint32_t b_hi = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
+        const uint32_t b_hi = base + s * TC_STAGE_BYTES + TC_TILE_BYTES, b_lo = b_hi + TC_TILE_BYTES;
+        const uint32_t a_hi = tmem + TC_TMEM_A + (uint32_t)((kb & 1) * 64), a_lo = a_hi + 32;
 #pragma unroll
         for (int ks = 0; ks < TC_BK / 8; ++ks) {
-          // one MMA eats 8 tf32 along K: 32 bytes inside the swizzle atom (K-major) / one 8-row atom (MN-major)
-          const uint64_t da_hi = A_MN ? umma_desc_mn(a_hi + ks * 1024) : umma_desc(a_hi + ks * 32);
-          const uint64_t da_lo = A_MN ? umma_desc_mn(a_lo + ks * 1024) : umma_desc(a_lo + ks * 32);
+          // one MMA eats 8 tf32 along K: 8 TMEM columns of A; for B 32 bytes inside the swizzle atom (K-major)
+          // or two 4-row atoms (MN-major)
           const uint64_t db_hi = B_MN ? umma_desc_mn(b_hi + ks * 1024) : umma_desc(b_hi + ks * 32);
           const uint64_t db_lo = B_MN ? umma_desc_mn(b_lo + ks * 1024) : umma_desc(b_lo + ks * 32);
           // The tensor core truncates its fp32 accumulator on every MMA (measured: ~2^-25 relative per
@@ -173,38 +193,66 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
           // relative to its 2^-11 times smaller magnitude; the epilogue adds the two in fp32.
           // Even / odd k-blocks alternate between two main accumulators, halving the chain again.
           const uint32_t dmain = tmem + (uint32_t)((kb & 1) * TC_BN);
-          umma_tf32(dmain, da_hi, db_hi, idesc, (kb >= 2 || ks != 0) ? 1u : 0u);
-          umma_tf32(tmem + 2 * TC_BN, da_lo, db_hi, idesc, (kb | ks) != 0);
-          umma_tf32(tmem + 2 * TC_BN, da_hi, db_lo, idesc, 1u);
+          umma_tf32_ts(dmain, a_hi + ks * 8, db_hi, idesc, (kb >= 2 || ks != 0) ? 1u : 0u);
+          umma_tf32_ts(tmem + 2 * TC_BN, a_lo + ks * 8, db_hi, idesc, (kb | ks) != 0);
+          umma_tf32_ts(tmem + 2 * TC_BN, a_hi + ks * 8, db_lo, idesc, 1u);
         }
         umma_commit(empty(s));  // implicit tcgen05.fence::before_thread_sync
       }
       umma_commit(tmem_full);
     }
   } else if (warp >= 4) {
-    // -------- splitter: x -> (hi = tf32-truncated x, lo = x - hi), same swizzled position ---------
+    // -------- splitter ------------------------------------------------------------------------------
+    // A: thread t owns row t of the tile (= TMEM lane t): x -> TMEM (hi = x as is: the tensor core ignores
+    // the low 13 mantissa bits; lo = x - tf32(x), exact).  B: lo tile written elementwise in place-layout.
     const int t = threadIdx.x - 128;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % TC_STAGES;
       mbar_wait(full(s), (uint32_t)((kb / TC_STAGES) & 1));
-      float4* st = reinterpret_cast<float4*>(gbase + (size_t)s * TC_STAGE_BYTES);
+      const unsigned char* sa = gbase + (size_t)s * TC_STAGE_BYTES;
+      uint32_t xh[32], xl[32];
+      if (A_MN) {
+        // [4 panels][32 k-rows][32 floats along m], 32-byte chunks XORed with (k-row & 3)
+        const unsigned char* pa = sa + (t >> 5) * 4096 + (t & 7) * 4;
+        const int c = (t & 31) >> 3;
 #pragma unroll
-      for (int op = 0; op < 2; ++op) {
-        float4* hi = st + op * 2 * (TC_TILE_BYTES / 16);
-        float4* lo = hi + TC_TILE_BYTES / 16;
+        for (int r = 0; r < 32; ++r) xh[r] = *reinterpret_cast<const uint32_t*>(pa + r * 128 + ((c ^ (r & 3)) << 5));
+      } else {
+        // [128 rows][32 floats along k], 16-byte chunks XORed with (row & 7)
+        const unsigned char* pa = sa + t * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 v = *reinterpret_cast<const uint4*>(pa + ((c ^ (t & 7)) << 4));
+          xh[4 * c] = v.x; xh[4 * c + 1] = v.y; xh[4 * c + 2] = v.z; xh[4 * c + 3] = v.w;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        xl[r] = __float_as_uint(__uint_as_float(xh[r]) - __uint_as_float(xh[r] & 0xffffe000u));
+      // the TMEM slot (kb & 1) was last read by the MMAs of k-block kb - 2: wait for their commit
+      if (kb >= 2) mbar_wait(empty((kb - 2) % TC_STAGES), (uint32_t)((((kb - 2) / TC_STAGES)) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t ta = tmem + lane_base + TC_TMEM_A + (uint32_t)((kb & 1) * 64);
+      tmem_st32(ta, xh);
+      tmem_st32(ta + 32, xl);
+      {
+        const float4* hi = reinterpret_cast<const float4*>(sa + TC_TILE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(const_cast<unsigned char*>(sa) + 2 * TC_TILE_BYTES);
 #pragma unroll 4
         for (int i = t; i < TC_TILE_BYTES / 16; i += 128) {
           const float4 x = hi[i];
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
-          h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
-          h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
-          h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
-          if (PFPN_TC_REWRITE_HI) hi[i] = h;
+          float4 l;
+          l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+          l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+          l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+          l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
           lo[i] = l;
         }
       }
-      fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      fence_async_smem();  // generic-proxy writes of B_lo -> visible to the tensor core (async proxy)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(conv(s));
     }
     // -------- epilogue: TMEM -> registers -> global --------------------------------------------
