@@ -230,12 +230,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
 #pragma unroll
       for (int r = 0; r < 32; ++r)
         xl[r] = __float_as_uint(__uint_as_float(xh[r]) - __uint_as_float(xh[r] & 0xffffe000u));
-      // the TMEM slot (kb & 1) was last read by the MMAs of k-block kb - 2: wait for their commit
-      if (kb >= 2) mbar_wait(empty((kb - 2) % TC_STAGES), (uint32_t)((((kb - 2) / TC_STAGES)) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t ta = tmem + lane_base + TC_TMEM_A + (uint32_t)((kb & 1) * 64);
-      tmem_st32(ta, xh);
-      tmem_st32(ta + 32, xl);
+      // B_lo first: it only touches shared memory, so it overlaps the MMAs that still read the TMEM slot
       {
         const float4* hi = reinterpret_cast<const float4*>(sa + TC_TILE_BYTES);
         float4* lo = reinterpret_cast<float4*>(const_cast<unsigned char*>(sa) + 2 * TC_TILE_BYTES);
@@ -250,6 +245,12 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
           lo[i] = l;
         }
       }
+      // the TMEM slot (kb & 1) was last read by the MMAs of k-block kb - 2: wait for their commit
+      if (kb >= 2) mbar_wait(empty((kb - 2) % TC_STAGES), (uint32_t)((((kb - 2) / TC_STAGES)) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t ta = tmem + lane_base + TC_TMEM_A + (uint32_t)((kb & 1) * 64);
+      tmem_st32(ta, xh);
+      tmem_st32(ta + 32, xl);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       fence_async_smem();  // generic-proxy writes of B_lo -> visible to the tensor core (async proxy)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -259,7 +260,6 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
     mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int wq = warp & 3;              // TMEM lane quadrant this warp may read
-    const int m = m0 + wq * 32 + lane;    // accumulator row = TMEM lane
 #pragma unroll 1
     for (int c0 = 0; c0 < TC_BN; c0 += 32) {
       uint32_t r[32], q[32];
@@ -298,29 +298,59 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
             "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (m < p.M) {
+      // stage the summed row chunk in shared memory (the operand ring is idle by now): 128-byte rows,
+      // 16-byte chunks XORed with (row & 7) -> conflict-free for this row-per-thread write and for the
+      // row-per-warp read below
+      unsigned char* srow = gbase + (size_t)(c0 >> 5) * TC_TILE_BYTES + (size_t)(wq * 32 + lane) * 128;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + c0 + j;
-          if (n >= p.N) break;  // N % 4 == 0
-          float4 v = make_float4((__uint_as_float(r[j]) + __uint_as_float(o[j])) + __uint_as_float(q[j]),
-                                 (__uint_as_float(r[j + 1]) + __uint_as_float(o[j + 1])) + __uint_as_float(q[j + 1]),
-                                 (__uint_as_float(r[j + 2]) + __uint_as_float(o[j + 2])) + __uint_as_float(q[j + 2]),
-                                 (__uint_as_float(r[j + 3]) + __uint_as_float(o[j + 3])) + __uint_as_float(q[j + 3]));
-          if (p.epi == TC_EPI_BIAS || p.epi == TC_EPI_BIAS_RELU6) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+      for (int j = 0; j < 32; j += 4) {
+        const float4 v = make_float4((__uint_as_float(r[j]) + __uint_as_float(o[j])) + __uint_as_float(q[j]),
+                                     (__uint_as_float(r[j + 1]) + __uint_as_float(o[j + 1])) + __uint_as_float(q[j + 1]),
+                                     (__uint_as_float(r[j + 2]) + __uint_as_float(o[j + 2])) + __uint_as_float(q[j + 2]),
+                                     (__uint_as_float(r[j + 3]) + __uint_as_float(o[j + 3])) + __uint_as_float(q[j + 3]));
+        *reinterpret_cast<float4*>(srow + ((((j >> 2) ^ (lane & 7))) << 4)) = v;
+      }
+    }
+  }
+  // ---- coalesced second phase, all 8 warps (producer / MMA / allocator warps are idle by now): one warp
+  // writes one full 512-byte output row per instruction; 8 rows per warp in flight hide the Hm load latency
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  {
+    const int n = n0 + lane * 4;
+    const bool n_ok = n < p.N;  // N % 4 == 0
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n_ok && (p.epi == TC_EPI_BIAS || p.epi == TC_EPI_BIAS_RELU6)) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    const unsigned char* sbuf = gbase + (size_t)(lane >> 3) * TC_TILE_BYTES;
+    const int rows_here = min(TC_BM, p.M - m0);
+    float* crow = p.C + ((size_t)blockIdx.z * p.M + m0) * p.ldc + n;
+    if (n_ok) {
+#pragma unroll 1
+      for (int r0 = warp; r0 < rows_here; r0 += 64) {
+        float4 h[8];
+        if (p.epi == TC_EPI_MASK6) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int row = r0 + 8 * u;
+            h[u] = row < rows_here ? __ldg(reinterpret_cast<const float4*>(p.Hm + (size_t)(m0 + row) * p.ldh + n))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int row = r0 + 8 * u;
+          if (row >= rows_here) break;
+          float4 v = *reinterpret_cast<const float4*>(sbuf + (size_t)row * 128 + ((((lane & 7) ^ (row & 7))) << 4));
+          v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
           if (p.epi == TC_EPI_BIAS_RELU6) {
             v.x = fminf(fmaxf(v.x, 0.f), 6.f); v.y = fminf(fmaxf(v.y, 0.f), 6.f);
             v.z = fminf(fmaxf(v.z, 0.f), 6.f); v.w = fminf(fmaxf(v.w, 0.f), 6.f);
           }
           if (p.epi == TC_EPI_MASK6) {
-            const float4 h = __ldg(reinterpret_cast<const float4*>(p.Hm + (size_t)m * p.ldh + n));
-            v.x = (h.x > 0.f && h.x < 6.f) ? v.x : 0.f; v.y = (h.y > 0.f && h.y < 6.f) ? v.y : 0.f;
-            v.z = (h.z > 0.f && h.z < 6.f) ? v.z : 0.f; v.w = (h.w > 0.f && h.w < 6.f) ? v.w : 0.f;
+            v.x = (h[u].x > 0.f && h[u].x < 6.f) ? v.x : 0.f; v.y = (h[u].y > 0.f && h[u].y < 6.f) ? v.y : 0.f;
+            v.z = (h[u].z > 0.f && h[u].z < 6.f) ? v.z : 0.f; v.w = (h[u].w > 0.f && h[u].w < 6.f) ? v.w : 0.f;
           }
-          *reinterpret_cast<float4*>(p.C + ((size_t)blockIdx.z * p.M + m) * p.ldc + n) = v;
+          *reinterpret_cast<float4*>(crow + (size_t)row * p.ldc) = v;
         }
       }
     }

@@ -25,3 +25,18 @@ for (N, K) in [(1024, 200), (512, 1024), (1260, 512), (1024, 512), (512, 1260)]:
     fl = 2.0 * M * N * K
     print(json.dumps({"M": M, "N": N, "K": K, "tc_ms": round(ms_tc, 3), "tc_TFLOPs": round(fl / ms_tc / 1e9, 1), "ffma_ms": round(ms_ff, 3),
                       "ffma_TFLOPs": round(fl / ms_ff / 1e9, 1), "err_tc": e_tc, "err_ffma": e_ff}))
+# input-gradient (Relu6Grad mask epilogue) and weight-gradient shapes of the DPPO trunk
+import ctypes as CT
+for (N, K) in [(1024, 512), (512, 1260)]:
+    dY = torch.randn(M, K, device=dev) * 0.01; W = torch.randn(N, K, device=dev) * 0.05; H = torch.rand(M, N, device=dev) * 8 - 1
+    dX = torch.empty(M, N, device=dev); st = _stream_ptr()
+    f = lambda: _cabi.check(_cabi.pfpn_tc_gemm_nt(dY.data_ptr(), K, W.data_ptr(), K, dX.data_ptr(), N, None, H.data_ptr(), N, M, N, K, 3, st))
+    ms = t(f)
+    print(json.dumps({"kind": "dX(mask)", "M": M, "N": N, "K": K, "tc_ms": round(ms, 3), "tc_TFLOPs": round(2.0 * M * N * K / ms / 1e9, 1)}))
+for (Kin, N) in [(200, 1024), (1024, 512), (512, 1260)]:
+    X = torch.randn(M, Kin, device=dev); dY = torch.randn(M, N, device=dev) * 0.01; dW = torch.empty(Kin, N, device=dev)
+    n = CT.c_size_t(0); _cabi.check(_cabi.pfpn_tc_wgrad_workspace_bytes(M, Kin, N, CT.byref(n)))
+    ws = torch.empty(n.value, dtype=torch.uint8, device=dev); st = _stream_ptr()
+    f = lambda: _cabi.check(_cabi.pfpn_tc_linear_bwd_weight(X.data_ptr(), Kin, dY.data_ptr(), N, dW.data_ptr(), M, Kin, N, ws.data_ptr(), ws.numel(), st))
+    ms = t(f)
+    print(json.dumps({"kind": "wgrad", "M": M, "Kin": Kin, "N": N, "tc_ms": round(ms, 3), "tc_TFLOPs": round(2.0 * M * N * Kin / ms / 1e9, 1)}))
