@@ -238,10 +238,13 @@ int pfpn_tc_gemm_nn(const float* A, int32_t lda, const float* B, int32_t ldb, fl
 int pfpn_transpose(const float* in, int32_t ldi, float* out, int32_t ldo, int32_t rows, int32_t cols,
                    pfpn_stream_t stream);
 /* Weight gradient on tcgen05: dW[K,N] = X[M,K]^T dY[M,N], X and dY row-major as stored (both MN-major
- * operands; split-K over the batch in chunks of 2048 rows, deterministic fp32 second stage). */
+ * operands; split-K over the batch in chunks of 2048 rows, deterministic fp32 second stage).  `db`
+ * (nullable) receives the bias gradient db[N] = column sums of dY, accumulated from the dY tiles the
+ * GEMM stages anyway (no extra pass over dY).  Replaces tf.gradients through fc_layer, networks/ops.py:108-116. */
 int pfpn_tc_wgrad_workspace_bytes(int32_t M, int32_t K, int32_t N, size_t* bytes);
-int pfpn_tc_linear_bwd_weight(const float* X, int32_t ldx, const float* dY, int32_t ldy, float* dW, int32_t M,
-                              int32_t K, int32_t N, void* workspace, size_t workspace_bytes, pfpn_stream_t stream);
+int pfpn_tc_linear_bwd_weight(const float* X, int32_t ldx, const float* dY, int32_t ldy, float* dW, float* db,
+                              int32_t M, int32_t K, int32_t N, void* workspace, size_t workspace_bytes,
+                              pfpn_stream_t stream);
 /* db[N] = column sums of dY[M,N]; workspace >= 1024*N floats. */
 int pfpn_bias_grad(const float* dY, int32_t ldy, float* db, int32_t M, int32_t N, void* workspace,
                    size_t workspace_bytes, pfpn_stream_t stream);

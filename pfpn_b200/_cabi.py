@@ -148,7 +148,7 @@ pfpn_tc_gemm_nt = _sig("pfpn_tc_gemm_nt", C.c_int, [_vp, _i32, _vp, _i32, _vp, _
 pfpn_tc_gemm_nn = _sig("pfpn_tc_gemm_nn", C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp])
 pfpn_transpose = _sig("pfpn_transpose", C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _vp])
 pfpn_tc_wgrad_workspace_bytes = _sig("pfpn_tc_wgrad_workspace_bytes", C.c_int, [_i32, _i32, _i32, C.POINTER(C.c_size_t)])
-pfpn_tc_linear_bwd_weight = _sig("pfpn_tc_linear_bwd_weight", C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _vp, C.c_size_t, _vp])
+pfpn_tc_linear_bwd_weight = _sig("pfpn_tc_linear_bwd_weight", C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, C.c_size_t, _vp])
 pfpn_bias_grad = _sig("pfpn_bias_grad", C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp, C.c_size_t, _vp])
 pfpn_enable_peer_access = _sig("pfpn_enable_peer_access", C.c_int, [_i32])
 pfpn_peer_signal = _sig("pfpn_peer_signal", C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp])

@@ -42,6 +42,7 @@ struct TcParams {
   const float* Hm;
   int M, N, K, ldc, ldh, epi;
   int k_chunk;  // split-K: K range per blockIdx.z (multiple of TC_BK); C then is [splits][M][ldc]
+  float* colsum;  // weight gradient only (B MN-major): [splits][N] column sums of the B operand (= bias gradient)
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
@@ -207,6 +208,15 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
     // the low 13 mantissa bits; lo = x - tf32(x), exact).  B: lo tile written elementwise in place-layout.
     const int t = threadIdx.x - 128;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    // bias gradient riding on the weight-gradient GEMM: the B operand (dY) passes through this thread's
+    // registers anyway.  float4 number t + 128 j of an MN-major tile sits in panel j / 2 at a column
+    // offset that depends only on t (the 32-byte-chunk swizzle uses (row & 3) = (t / 8) & 3), so four
+    // float4 accumulators per thread cover its share; 16 threads share a column and are combined in a
+    // fixed order after the main loop.
+    const bool do_cs = B_MN && p.colsum != nullptr && blockIdx.y == 0;
+    float4 cs[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cs[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % TC_STAGES;
       mbar_wait(full(s), (uint32_t)((kb / TC_STAGES) & 1));
@@ -234,8 +244,9 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
       {
         const float4* hi = reinterpret_cast<const float4*>(sa + TC_TILE_BYTES);
         float4* lo = reinterpret_cast<float4*>(const_cast<unsigned char*>(sa) + 2 * TC_TILE_BYTES);
-#pragma unroll 4
-        for (int i = t; i < TC_TILE_BYTES / 16; i += 128) {
+#pragma unroll
+        for (int j = 0; j < TC_TILE_BYTES / 16 / 128; ++j) {
+          const int i = t + 128 * j;
           const float4 x = hi[i];
           float4 l;
           l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
@@ -243,6 +254,9 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
           l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
           l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
           lo[i] = l;
+          if (B_MN && do_cs) {
+            cs[j >> 1].x += x.x; cs[j >> 1].y += x.y; cs[j >> 1].z += x.z; cs[j >> 1].w += x.w;
+          }
         }
       }
       // the TMEM slot (kb & 1) was last read by the MMAs of k-block kb - 2: wait for their commit
@@ -259,6 +273,12 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
     // -------- epilogue: TMEM -> registers -> global --------------------------------------------
     mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (B_MN && do_cs) {  // scratch behind the 64 KiB output staging area: [16 row groups][128 columns]
+      float* scr = reinterpret_cast<float*>(gbase + 4 * TC_TILE_BYTES);
+      const int noff = ((((t & 7) >> 1) ^ ((t >> 3) & 3)) << 3) + ((t & 1) << 2);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(scr + (t >> 3) * 128 + q * 32 + noff) = cs[q];
+    }
     const int wq = warp & 3;              // TMEM lane quadrant this warp may read
 #pragma unroll 1
     for (int c0 = 0; c0 < TC_BN; c0 += 32) {
@@ -316,6 +336,13 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
   // writes one full 512-byte output row per instruction; 8 rows per warp in flight hide the Hm load latency
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (B_MN && p.colsum != nullptr && blockIdx.y == 0 && threadIdx.x < TC_BN) {
+    const float* scr = reinterpret_cast<const float*>(gbase + 4 * TC_TILE_BYTES);
+    float sum = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) sum += scr[g * 128 + threadIdx.x];
+    if (n0 + (int)threadIdx.x < p.N) p.colsum[(size_t)blockIdx.z * p.N + n0 + threadIdx.x] = sum;
+  }
   {
     const int n = n0 + lane * 4;
     const bool n_ok = n < p.N;  // N % 4 == 0
@@ -420,7 +447,7 @@ static int tc_gemm_common(const float* A, int lda, const float* Bm, int ldb, boo
   if (rc != PFPN_OK) return rc;
   rc = make_map(&mapB, Bm, N, K, ldb, TC_BN, b_mn);
   if (rc != PFPN_OK) return rc;
-  TcParams p{Cout, bias, Hm, M, N, K, ldc, ldh, epi, (K + TC_BK - 1) / TC_BK * TC_BK};
+  TcParams p{Cout, bias, Hm, M, N, K, ldc, ldh, epi, (K + TC_BK - 1) / TC_BK * TC_BK, nullptr};
   dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
   return b_mn ? tc_launch<false, true>(mapA, mapB, p, grid, st) : tc_launch<false, false>(mapA, mapB, p, grid, st);
 }
@@ -469,19 +496,20 @@ __global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, float* _
 extern "C" int pfpn_tc_wgrad_workspace_bytes(int32_t M, int32_t K, int32_t N, size_t* bytes) {
   if (!bytes || M <= 0 || K <= 0 || N <= 0) return PFPN_ERR_ARG;
   const size_t splits = ((size_t)M + TC_WGRAD_CHUNK - 1) / TC_WGRAD_CHUNK;
-  *bytes = splits * (size_t)K * N * sizeof(float) + 256;
+  *bytes = splits * ((size_t)K * N + N) * sizeof(float) + 256;
   return PFPN_OK;
 }
 
-extern "C" int pfpn_tc_linear_bwd_weight(const float* X, int32_t ldx, const float* dY, int32_t ldy, float* dW, int32_t M,
-                                         int32_t K, int32_t N, void* workspace, size_t workspace_bytes, pfpn_stream_t stream_) {
+extern "C" int pfpn_tc_linear_bwd_weight(const float* X, int32_t ldx, const float* dY, int32_t ldy, float* dW, float* db,
+                                         int32_t M, int32_t K, int32_t N, void* workspace, size_t workspace_bytes,
+                                         pfpn_stream_t stream_) {
   if (!X || !dY || !dW || M <= 0 || K <= 0 || N <= 0) return PFPN_ERR_ARG;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-  if ((ldx & 3) || (ldy & 3) || (N & 3) || !al16(X) || !al16(dY) || !al16(dW) || !al16(workspace)) return PFPN_ERR_ALIGN;
+  if ((ldx & 3) || (ldy & 3) || (N & 3) || !al16(X) || !al16(dY) || !al16(dW) || !al16(db) || !al16(workspace)) return PFPN_ERR_ALIGN;
   const int splits = (M + TC_WGRAD_CHUNK - 1) / TC_WGRAD_CHUNK;
   size_t need;
   pfpn_tc_wgrad_workspace_bytes(M, K, N, &need);
-  if (splits > 1 && (!workspace || workspace_bytes < need)) return PFPN_ERR_WORKSPACE;
+  if ((splits > 1 || db) && (!workspace || workspace_bytes < need)) return PFPN_ERR_WORKSPACE;
   CUtensorMap mapA, mapB;
   int rc = make_map(&mapA, X, K, M, ldx, TC_BM, true);  // GEMM rows = K_in, reduction axis = batch
   if (rc != PFPN_OK) return rc;
@@ -489,13 +517,18 @@ extern "C" int pfpn_tc_linear_bwd_weight(const float* X, int32_t ldx, const floa
   if (rc != PFPN_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   float* out = splits > 1 ? reinterpret_cast<float*>(workspace) : dW;
-  TcParams p{out, nullptr, nullptr, K, N, M, N, 0, TC_EPI_NONE, TC_WGRAD_CHUNK};
+  float* cs_part = db ? reinterpret_cast<float*>(workspace) + (size_t)splits * K * N : nullptr;
+  TcParams p{out, nullptr, nullptr, K, N, M, N, 0, TC_EPI_NONE, TC_WGRAD_CHUNK, cs_part};
   dim3 grid((N + TC_BN - 1) / TC_BN, (K + TC_BM - 1) / TC_BM, splits);
   rc = tc_launch<true, true>(mapA, mapB, p, grid, st);
   if (rc != PFPN_OK) return rc;
   if (splits > 1) {
     const size_t n4 = (size_t)K * N / 4;
     tc_splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(out, dW, n4, splits, (size_t)K * N);
+    PFPN_CUDA_OK(cudaGetLastError());
+  }
+  if (db) {  // bias gradient: the per-split column sums of dY, combined in split order
+    tc_splitk_reduce_kernel<<<(unsigned)((N / 4 + 255) / 256), 256, 0, st>>>(cs_part, db, (size_t)N / 4, splits, (size_t)N);
     PFPN_CUDA_OK(cudaGetLastError());
   }
   return PFPN_OK;

@@ -329,14 +329,14 @@ class ParticleFilteringClipPPONetwork:
                 dY = dX
 
     def _tc_wgrad(self, l, X, dY, M):
-        """dW on the tensor cores: X and dY as stored (MN-major operands), split-K GEMM, bias column sums."""
+        """dW and db on the tensor cores: X and dY as stored (MN-major operands), split-K GEMM; the bias
+        gradient is accumulated from the dY tiles the GEMM stages anyway."""
         st = _stream_ptr()
         n = C.c_size_t(0)
         _cabi.check(_cabi.pfpn_tc_wgrad_workspace_bytes(M, l.k, l.n_out, C.byref(n)))
-        ws = self._ws(max(n.value, 1024 * l.n_out * 4))
+        ws = self._ws(n.value)
         _cabi.check(_cabi.pfpn_tc_linear_bwd_weight(X.data_ptr(), X.stride(0), dY.data_ptr(), dY.stride(0), l.dW.data_ptr(),
-                                                    M, l.k, l.n_out, ws.data_ptr(), ws.numel(), st))
-        _cabi.check(_cabi.pfpn_bias_grad(dY.data_ptr(), dY.stride(0), l.db.data_ptr(), M, l.n_out, ws.data_ptr(), ws.numel(), st))
+                                                    l.db.data_ptr(), M, l.k, l.n_out, ws.data_ptr(), ws.numel(), st))
 
     def _ws(self, nbytes):
         t = self._act.get("_ws")

@@ -72,8 +72,16 @@ def test_tc_wgrad_operands_as_stored(cuda_dev, M, K, N):
     _cabi.check(_cabi.pfpn_tc_wgrad_workspace_bytes(M, K, N, C.byref(n)))
     ws = torch.empty(max(n.value, 16), dtype=torch.uint8, device=cuda_dev)
     dW = torch.full((K, N), float("nan"), device=cuda_dev)
-    _cabi.check(_cabi.pfpn_tc_linear_bwd_weight(Xd.data_ptr(), K, Yd.data_ptr(), N, dW.data_ptr(), M, K, N, ws.data_ptr(),
-                                                ws.numel(), _stream_ptr()))
+    db = torch.full((N,), float("nan"), device=cuda_dev)
+    _cabi.check(_cabi.pfpn_tc_linear_bwd_weight(Xd.data_ptr(), K, Yd.data_ptr(), N, dW.data_ptr(), db.data_ptr(), M, K, N,
+                                                ws.data_ptr(), ws.numel(), _stream_ptr()))
     ref = X.double().T @ dY.double()
     assert torch.isfinite(dW).all()
     assert rel(dW, ref) < 1e-5
+    # bias gradient accumulated from the staged dY tiles (fc_layer's `b`, networks/ops.py:108-116)
+    assert rel(db, dY.double().sum(0)) < 1e-5
+    # deterministic: a second launch reproduces both bit for bit
+    dW2, db2 = torch.empty_like(dW), torch.empty_like(db)
+    _cabi.check(_cabi.pfpn_tc_linear_bwd_weight(Xd.data_ptr(), K, Yd.data_ptr(), N, dW2.data_ptr(), db2.data_ptr(), M, K, N,
+                                                ws.data_ptr(), ws.numel(), _stream_ptr()))
+    assert torch.equal(dW, dW2) and torch.equal(db, db2)

@@ -22,7 +22,7 @@ for m1 in (0, 1, 9, 33):
     dY = torch.zeros(Mb, Nw, device=dev); dY[m1, :] = (torch.arange(Nw, device=dev).float() + 1) * 0.001
     dW = torch.full((Kw, Nw), float("nan"), device=dev)
     ws = torch.empty(1 << 20, dtype=torch.uint8, device=dev)
-    _cabi.check(_cabi.pfpn_tc_linear_bwd_weight(X.data_ptr(), Kw, dY.data_ptr(), Nw, dW.data_ptr(), Mb, Kw, Nw, ws.data_ptr(), ws.numel(), _stream_ptr()))
+    _cabi.check(_cabi.pfpn_tc_linear_bwd_weight(X.data_ptr(), Kw, dY.data_ptr(), Nw, dW.data_ptr(), None, Mb, Kw, Nw, ws.data_ptr(), ws.numel(), _stream_ptr()))
     torch.cuda.synchronize()
     ref = X.T @ dY
     print("m1", m1, "err", float((dW - ref).abs().max()), "dW[0,:4]", dW[0, :4].tolist(), "dW[3,:4]", dW[3, :4].tolist(), "ref[3,:4]", ref[3, :4].tolist())

@@ -34,9 +34,9 @@ for (N, K) in [(1024, 512), (512, 1260)]:
     ms = t(f)
     print(json.dumps({"kind": "dX(mask)", "M": M, "N": N, "K": K, "tc_ms": round(ms, 3), "tc_TFLOPs": round(2.0 * M * N * K / ms / 1e9, 1)}))
 for (Kin, N) in [(200, 1024), (1024, 512), (512, 1260)]:
-    X = torch.randn(M, Kin, device=dev); dY = torch.randn(M, N, device=dev) * 0.01; dW = torch.empty(Kin, N, device=dev)
+    X = torch.randn(M, Kin, device=dev); dY = torch.randn(M, N, device=dev) * 0.01; dW = torch.empty(Kin, N, device=dev); db = torch.empty(N, device=dev)
     n = CT.c_size_t(0); _cabi.check(_cabi.pfpn_tc_wgrad_workspace_bytes(M, Kin, N, CT.byref(n)))
     ws = torch.empty(n.value, dtype=torch.uint8, device=dev); st = _stream_ptr()
-    f = lambda: _cabi.check(_cabi.pfpn_tc_linear_bwd_weight(X.data_ptr(), Kin, dY.data_ptr(), N, dW.data_ptr(), M, Kin, N, ws.data_ptr(), ws.numel(), st))
+    f = lambda: _cabi.check(_cabi.pfpn_tc_linear_bwd_weight(X.data_ptr(), Kin, dY.data_ptr(), N, dW.data_ptr(), db.data_ptr(), M, Kin, N, ws.data_ptr(), ws.numel(), st))
     ms = t(f)
     print(json.dumps({"kind": "wgrad", "M": M, "Kin": Kin, "N": N, "tc_ms": round(ms, 3), "tc_TFLOPs": round(2.0 * M * N * Kin / ms / 1e9, 1)}))
