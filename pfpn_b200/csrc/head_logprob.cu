@@ -100,7 +100,10 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
 
   // ---- shared memory carve-up ------------------------------------------
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int stage_bytes = (tile_floats * 4 + 127) & ~127;
+  // a stage = the logits tile followed by the tile's action values [TS][A] (fetched by the same producer
+  // with a second bulk copy when A % 4 == 0, i.e. 16-byte granular; otherwise read with LDG one tile ahead)
+  constexpr bool VAL_TMA = AT > 0 && (AT % 4 == 0);
+  const int stage_bytes = (tile_floats * 4 + TS * A * 4 + 127) & ~127;
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   unsigned char* tail = smem_raw + (size_t)NSTAGE * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
@@ -193,9 +196,12 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
     if (tail_exists && tile == tail_tile) return;  // tail is copied cooperatively
     const int st = it % NSTAGE;
     const uint32_t bar = smem_u32(&full_bar[st]);
-    mbar_expect_tx(bar, (uint32_t)(tile_floats * 4));
+    mbar_expect_tx(bar, (uint32_t)(tile_floats * 4 + (VAL_TMA ? TS * A * 4 : 0)));
     bulk_g2s(smem_u32(stage_base) + st * stage_bytes, g_logits + (size_t)tile * tile_floats,
              (uint32_t)(tile_floats * 4), bar);
+    if (VAL_TMA)
+      bulk_g2s(smem_u32(stage_base) + st * stage_bytes + tile_floats * 4, g_value + (size_t)tile * TS * A,
+               (uint32_t)(TS * A * 4), bar);
   };
   const uint32_t cta_bar_a = smem_u32(cta_bar);
   if (is_producer) {
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
     for (int j = 0; j < RPT; ++j) {
       const int b = tile * TS + j * slots + slot;
       const bool ok = it < my_tiles && active && b < B;
-      v_nxt[j] = ok ? __ldg(&g_value[(size_t)b * A + a]) : 0.f;
+      v_nxt[j] = (!VAL_TMA && ok) ? __ldg(&g_value[(size_t)b * A + a]) : 0.f;
       if (BWD) {
         if (mode == PFPN_HEAD_PPO) {
           sc0_nxt[j] = ok ? __ldg(&kp.a.adv[b]) : 0.f;
@@ -289,7 +295,16 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
         const int nvalid = (B - b0) * AP;
         const float* src = g_logits + (size_t)b0 * AP;
         for (int idx = tid; idx < nvalid; idx += nthr) sbuf[idx] = __ldg(&src[idx]);
+        if (VAL_TMA)
+          for (int idx = tid; idx < (B - b0) * A; idx += nthr) sbuf[tile_floats + idx] = __ldg(&g_value[(size_t)b0 * A + idx]);
         asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");  // compute threads only; tail tile only
+      }
+      if (VAL_TMA) {
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+          const bool row_ok = active && (b0 + j * slots + slot < B);
+          nw.v_c[j] = sbuf[tile_floats + (row_ok ? row_off[j] : a)];
+        }
       }
 
       float2* rb = rowbuf + (it % 3) * TS * A;
@@ -726,7 +741,7 @@ static int plan_head(int A, int P, int km, HeadLaunch* L) {
   L->slots = slots;
   L->ts = slots * v.rpt;
   L->threads = ((slots * per_slot + 31) & ~31) + 32;  // + the TMA producer warp
-  const int stage_bytes = (L->ts * A * P * 4 + 127) & ~127;
+  const int stage_bytes = (L->ts * A * P * 4 + L->ts * A * 4 + 127) & ~127;  // logits tile + its action values
   L->smem_bytes = v.nstage * stage_bytes + 8 * (v.nstage + 1) + 3 * L->ts * A * 8 + kHeadMaxWarps * 4 +
                   (v.lpr * v.epl + 1) * 4 + 16 + (v.csm ? ((v.epl + 1) / 2) * 3 * per_slot * 8 : 0);
   L->fn = v.fn[km];
@@ -782,7 +797,7 @@ extern "C" int pfpn_head_logprob(const pfpn_head_args* args, void* workspace, si
   if (bwd && (!a.dlogits || !a.dloc || !a.dlogstd)) return PFPN_ERR_ARG;
   if (a.mode == PFPN_HEAD_GRAD && !a.g_lp) return PFPN_ERR_ARG;
   if (a.mode == PFPN_HEAD_PPO && (!a.adv || !a.lp_old || !a.loss)) return PFPN_ERR_ARG;
-  if (!aligned16(a.logits) || (bwd && !aligned16(a.dlogits))) return PFPN_ERR_ALIGN;
+  if (!aligned16(a.logits) || !aligned16(a.value) || (bwd && !aligned16(a.dlogits))) return PFPN_ERR_ALIGN;
 
   HeadLaunch L;
   const bool has_ent_grad = (a.g_ent != 0.f || a.g_ent_ba != nullptr);
