@@ -199,15 +199,26 @@ def main():
     a.eps_clip, a.loss_scale = 0.2, 1.0 / (B * world)
     a.dlogits, a.dloc, a.dlogstd, a.loss = dlogits.data_ptr(), dloc.data_ptr(), dlogstd.data_ptr(), loss.data_ptr()
     flat_small = torch.empty(2, A, P, device=dev)
+    use_peer = world > 1 and os.environ.get("PFPN_FUSED_ALLREDUCE", "1") != "0"
+    if use_peer:
+        from pfpn_b200.peer import PeerSum
+        psum = PeerSum(2 * A * P, dev)
 
     def step():
         _cabi.check(_cabi.pfpn_adv_stats(adv.data_ptr(), B, stats.data_ptr(), stream.cuda_stream))
+        if use_peer:
+            # the path's only exchange: [2, A, P] particle gradients.  K1's finalize kernel writes
+            # them straight into this rank's peer-visible staging slot; one kernel signals, waits and sums.
+            slot = psum.slot()
+            a.dloc, a.dlogstd = slot.data_ptr(), slot.data_ptr() + 4 * A * P
         _cabi.check(_cabi.pfpn_head_logprob(a, ws.data_ptr(), ws.numel(), stream.cuda_stream))
-        if world > 1:  # the path's only exchange: [2, A, P] particle gradients
+        if use_peer:
+            psum.reduce(flat_small.view(-1), 1.0, stream.cuda_stream)
+        elif world > 1:
             flat_small[0].copy_(dloc)
             flat_small[1].copy_(dlogstd)
             dist.all_reduce(flat_small)
-    launches_per_step = 3
+    launches_per_step = 3 + (1 if use_peer else 0)
 
     def barrier():
         if world > 1:
@@ -294,7 +305,7 @@ def main():
         um = torch.tensor([u0.elapsed_time(u1) / args.dppo_steps], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(um, op=dist.ReduceOp.MAX)
-        dppo = {"workload": f"DPPO minibatch update, B_total={B_PER_GPU} sharded over {world} GPU(s): 197-1024-512 actor+critic trunk (tcgen05 3xTF32 GEMMs), PFPN head, local clip, NCCL all-reduce of the 8.4 MB bucket, Adam",
+        dppo = {"workload": f"DPPO minibatch update, B_total={B_PER_GPU} sharded over {world} GPU(s): 197-1024-512 actor+critic trunk (tcgen05 3xTF32 GEMMs), PFPN head, local clip, all-reduce of the 8.4 MB bucket fused into Adam over NVLink peer memory (N>1)",
                 "ms_per_update": float(um.item()), "samples_per_s": B_PER_GPU / (float(um.item()) * 1e-3), "scaling": "strong",
                 "trunk_tflops": 12.6e6 * B_PER_GPU / (float(um.item()) * 1e-3) / 1e12}
     clocks = sampler.stop() if sampler else None
@@ -308,7 +319,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "B_per_gpu": B, "A": A, "P": P,
                        "l2": "inputs larger than L2: 330 MB logits in + 330 MB dlogits out per step vs 126 MB L2",
-                       "step_ms_median": per[len(per) // 2], "parallelism": f"dp{world} (states sharded, [2,A,P] all-reduce)"},
+                       "step_ms_median": per[len(per) // 2], "parallelism": f"dp{world} (states sharded, [2,A,P] particle-gradient exchange" + (" over NVLink peer memory, one kernel)" if use_peer else ", NCCL all-reduce)" if world > 1 else ")")},
             "clocks": clocks,
             "e2e": {"value": e2e_rate, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
                     "d2h_bytes_per_step": pipe.d2h_bytes, "steps": args.e2e_steps,

@@ -297,6 +297,11 @@ int pfpn_peer_allreduce_adam(const float* const* buckets, int32_t* const* flags,
                              int32_t value, size_t n_params, size_t n_total, float* params, float* m, float* v,
                              float* avg_out, float lr, float beta1, float beta2, float eps, int64_t step,
                              pfpn_stream_t stream);
+/* The sharded head's only exchange: out[n] = scale * sum_r buckets[r][n] for the [2,A,P] particle
+ * gradients -- signal, wait and the rank-ordered sum in ONE kernel over peer memory (same staging / flag
+ * protocol as above; `value` = call counter, +1 per call, buffers alternate by its parity). */
+int pfpn_peer_allreduce_sum(const float* const* buckets, int32_t* const* flags, int32_t rank, int32_t nranks,
+                            int32_t value, size_t n, float* out, float scale, pfpn_stream_t stream);
 
 #ifdef __cplusplus
 }

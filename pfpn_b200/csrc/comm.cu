@@ -72,6 +72,33 @@ __global__ void __launch_bounds__(256) peer_allreduce_adam_kernel(PeerPtrs pp, i
   }
 }
 
+// Small exchange of the head's [2, A, P] particle gradients (the only collective of the
+// sharded head path): signal + wait + ordered sum in ONE kernel.  The bucket was written by the kernel
+// before this one on the stream (head_finalize writes straight into the staging buffer).
+__global__ void __launch_bounds__(256) peer_sum_kernel(PeerPtrs pp, int rank, int nranks, int value, size_t n4,
+                                                       float* __restrict__ out, float scale) {
+  if (blockIdx.x == 0 && threadIdx.x < nranks) {
+    __threadfence_system();
+    *reinterpret_cast<volatile int*>(pp.flags[threadIdx.x] + rank) = value;  // publish to every peer (and self)
+  }
+  if (threadIdx.x < nranks) {
+    const volatile int* f = reinterpret_cast<const volatile int*>(pp.flags[rank]) + threadIdx.x;
+    while (*f < value) {
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < nranks; ++p) {  // fixed order: identical result on every rank
+      const float4 g = __ldcg(reinterpret_cast<const float4*>(pp.bucket[p]) + i);
+      s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+    }
+    s.x *= scale; s.y *= scale; s.z *= scale; s.w *= scale;
+    reinterpret_cast<float4*>(out)[i] = s;
+  }
+}
+
 }  // namespace pfpn
 
 using namespace pfpn;
@@ -123,6 +150,22 @@ extern "C" int pfpn_peer_allreduce_adam(const float* const* buckets, int32_t* co
   const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
   peer_allreduce_adam_kernel<<<296, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
       pp, rank, nranks, value, n_params, n_total, params, m, v, avg_out, (float)lr_t, beta1, beta2, eps);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}
+
+// out[n] = scale * sum over ranks (rank order) of buckets[r][n]; n % 4 == 0, n small (one wave of CTAs: every CTA
+// spins on the local flags, so the grid must be co-resident).  `value` must increase by one per call.
+extern "C" int pfpn_peer_allreduce_sum(const float* const* buckets, int32_t* const* flags, int32_t rank, int32_t nranks,
+                                       int32_t value, size_t n, float* out, float scale, pfpn_stream_t stream_) {
+  PeerPtrs pp;
+  int rc = fill_peers(&pp, buckets, flags, nranks);
+  if (rc != PFPN_OK) return rc;
+  if (!out || (n & 3) || n == 0 || rank < 0 || rank >= nranks) return PFPN_ERR_ARG;
+  const size_t n4 = n / 4;
+  size_t grid = (n4 + 255) / 256;
+  if (grid > 148) grid = 148;
+  peer_sum_kernel<<<(unsigned)grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(pp, rank, nranks, value, n4, out, scale);
   PFPN_CUDA_OK(cudaGetLastError());
   return PFPN_OK;
 }

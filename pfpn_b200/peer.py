@@ -56,3 +56,25 @@ class PeerBuckets:
 
     def ptrs(self, parity: int):
         return self._bucket_ptrs[parity], self._flag_ptrs
+
+
+class PeerSum:
+    """The sharded head's [2, A, P] exchange over peer memory (`pfpn_peer_allreduce_sum`): the caller lets
+    K1's finalize kernel write dloc / dlogstd straight into ``slot(parity)`` and then calls ``reduce``."""
+
+    def __init__(self, n: int, device: torch.device, group=None):
+        if n % 4:
+            raise ValueError("n must be a multiple of 4 floats")
+        self.pb = PeerBuckets(n, device, group)
+        self.n, self.calls = n, 0
+
+    def slot(self) -> torch.Tensor:
+        """Staging buffer [n] the NEXT ``reduce`` call will publish."""
+        return self.pb.stage[(self.calls + 1) & 1]
+
+    def reduce(self, out: torch.Tensor, scale: float = 1.0, stream_ptr: int = 0):
+        self.calls += 1
+        buckets, flags = self.pb.ptrs(self.calls & 1)
+        _cabi.check(_cabi.pfpn_peer_allreduce_sum(buckets, flags, self.pb.rank, self.pb.world, self.calls, self.n,
+                                                  out.data_ptr(), scale, stream_ptr))
+        return out

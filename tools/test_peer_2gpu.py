@@ -44,5 +44,30 @@ d = (res["fused"]["params"] - res["nccl"]["params"]).abs().max().item()
 out = dict(rank=rank, world=world, max_abs_param_diff_fused_vs_nccl=d, replica_equal=(res["nccl"]["replica_equal"], res["fused"]["replica_equal"]),
            stats_equal=bool(torch.allclose(res["fused"]["mean"], res["nccl"]["mean"], rtol=1e-6, atol=1e-7)),
            ms_apply_nccl=round(res["nccl"]["ms"], 4), ms_apply_fused=round(res["fused"]["ms"], 4))
+# ---- the sharded head's [2, A, P] exchange in one kernel (pfpn_peer_allreduce_sum) vs NCCL ----------------
+from pfpn_b200.peer import PeerSum
+from pfpn_b200.head import _stream_ptr
+n = 2 * A * P
+ps = PeerSum(n, dev)
+ok_sum, t_peer, t_nccl = True, 0.0, 0.0
+outp = torch.empty(n, device=dev)
+for it in range(6):
+    src = torch.randn(n, device=dev, generator=g)
+    ps.slot().copy_(src)
+    ps.reduce(outp, 1.0, _stream_ptr())
+    ref = src.clone(); dist.all_reduce(ref)
+    ok_sum = ok_sum and bool(torch.allclose(outp, ref, rtol=1e-6, atol=1e-6))
+    chk = outp.clone(); dist.broadcast(chk, 0)
+    ok_sum = ok_sum and bool(torch.equal(chk, outp))  # rank-ordered sum: bit-identical on every rank
+torch.cuda.synchronize(); dist.barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(50): ps.reduce(outp, 1.0, _stream_ptr())
+e1.record(); torch.cuda.synchronize(); t_peer = e0.elapsed_time(e1) / 50
+buf = torch.randn(n, device=dev)
+dist.barrier(); e0.record()
+for _ in range(50): dist.all_reduce(buf)
+e1.record(); torch.cuda.synchronize(); t_nccl = e0.elapsed_time(e1) / 50
+out.update(small_sum_ok=ok_sum, ms_small_sum_peer=round(t_peer, 4), ms_small_sum_nccl=round(t_nccl, 4))
 print(json.dumps(out), flush=True)
 dist.barrier(); dist.destroy_process_group()
