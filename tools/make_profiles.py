@@ -70,3 +70,32 @@ if os.path.exists(rep):
     mix = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_opmix.py"), tmp], capture_output=True, text=True).stdout
     open(os.path.join(out, f"{rnd}_head_kernel.md"), "a").write("\n## SASS opcode mix (warp-instructions executed) and stall samples\n\n```\n" + mix + "```\n")
     print("head kernel summary written")
+
+# ---- K6 tcgen05 GEMM (tc_full.ncu-rep: one forward-layer launch, M=65536, N=512, K=1024) -----------------------------
+rep = os.path.join(src, "tc_full.ncu-rep")
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines())); hdr, units, vals = rows[0], rows[1], rows[2]
+    keys = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+            "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.max", "smsp__inst_executed.sum"] + \
+           [k for k in hdr if k.startswith("smsp__average_warps_issue_stalled") and k.endswith("_per_issue_active.ratio")]
+    with open(os.path.join(out, f"{rnd}_tc_gemm_kernel.md"), "w") as f:
+        f.write(f"# {rnd}: `ncu --set full` of the K6 tcgen05 3xTF32 GEMM (forward layer, M=65536, N=512, K=1024, bias+relu6)\n\n"
+                "| metric | unit | value |\n|---|---|---|\n")
+        for k in keys:
+            if k in hdr:
+                f.write(f"| {k} | {units[hdr.index(k)]} | {vals[hdr.index(k)]} |\n")
+    srcp = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+    tmp = os.path.join(src, "tc_full_src.csv"); open(tmp, "w").write(srcp)
+    mix = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_opmix.py"), tmp], capture_output=True, text=True).stdout
+    open(os.path.join(out, f"{rnd}_tc_gemm_kernel.md"), "a").write("\n## SASS opcode mix (UTCHMMA = tcgen05.mma, UTMALDG = TMA load) and stall samples\n\n```\n" + mix + "```\n")
+    print("tc gemm summary written")
+for extra in ("configs_r01.json",):
+    pth = os.path.join(src, extra)
+    if os.path.exists(pth):
+        open(os.path.join(out, f"{rnd}_configs.json"), "w").write(open(pth).read())
