@@ -42,6 +42,21 @@ class _Linear:
         return self.k * self.n_out + self.n_out
 
 
+def initial_particles(A: int, P: int, tanh: bool):
+    """a2c.py:476-535 with the bounds forced to +-1 (:479-480): (loc [A,P], logstd [A,P]) fp32 on the host.
+    Plain: linspace(-1, 1, P), std = 2/(P-1).  tanh (normalize_policy_output_): cell-centred grid mapped through
+    arctanh, std = the larger neighbour gap (:486,501-512)."""
+    if tanh:
+        assert P > 3
+        c = -1.0 + (2.0 / P) * (np.arange(P) + 0.5)
+        mu = np.arctanh(c)
+        sd = np.array([max(mu[j] - mu[max(0, j - 1)], mu[min(P - 1, j + 1)] - mu[j]) for j in range(P)])
+    else:
+        mu = -1.0 + 2.0 / (P - 1) * np.arange(P)
+        sd = np.full(P, 2.0 / (P - 1))
+    return (torch.tensor(mu, dtype=torch.float32).repeat(A, 1), torch.tensor(np.log(sd), dtype=torch.float32).repeat(A, 1))
+
+
 class ParticleFilteringClipPPONetwork:
     GLOBAL_STEP0 = 0
 
@@ -151,16 +166,9 @@ class ParticleFilteringClipPPONetwork:
         """a2c.py:476-535 particle grid (bounds forced to +-1) + truncated_normal(0, .01) weights."""
         A, P = self.A, self.P
         g = torch.Generator().manual_seed(self.seed)
-        if self.normalize_policy_output_:
-            assert P > 3
-            c = -1.0 + (2.0 / P) * (np.arange(P) + 0.5)
-            mu = np.arctanh(c)
-            sd = np.array([max(mu[j] - mu[max(0, j - 1)], mu[min(P - 1, j + 1)] - mu[j]) for j in range(P)])
-        else:
-            mu = -1.0 + 2.0 / (P - 1) * np.arange(P)
-            sd = np.full(P, 2.0 / (P - 1))
-        self.loc.copy_(torch.tensor(mu, dtype=torch.float32).repeat(A, 1))
-        self.logstd.copy_(torch.tensor(np.log(sd), dtype=torch.float32).repeat(A, 1))
+        loc, logstd = initial_particles(A, P, self.normalize_policy_output_)
+        self.loc.copy_(loc)
+        self.logstd.copy_(logstd)
         for l in self.actor + [self.fc_policy] + self.critic:
             w = torch.empty(l.k_in, l.n_out)
             torch.nn.init.trunc_normal_(w, mean=0.0, std=0.01, a=-0.02, b=0.02, generator=g)

@@ -59,9 +59,8 @@ for P3 in (10, 35, 100):
 out["c3_resample_A36_H512"] = dict(res, note="latency-bound (one plan CTA + two column-copy launches); roofline fraction not meaningful")
 # ---------------------------------------------------------------- c5
 A5, P5 = 36, 100
-from oracle.head import init_particles  # particle grid values only (host numpy); not on the timed path
-loc_np, ls_np = init_particles(A5, P5, tanh=True)
-loc5, ls5 = torch.tensor(loc_np, dtype=torch.float32, device=dev), torch.tensor(ls_np, dtype=torch.float32, device=dev)
+from pfpn_b200.network import initial_particles
+loc5, ls5 = (t.to(dev) for t in initial_particles(A5, P5, True))
 sweep = {}
 for B5 in (65536, 262144, 1000000):
     g = torch.Generator(device="cuda"); g.manual_seed(12831)
