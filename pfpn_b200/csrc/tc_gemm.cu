@@ -480,6 +480,14 @@ extern "C" int pfpn_tc_gemm_nn(const float* A, int32_t lda, const float* B, int3
 // ------------------------------------------------------------------------------------------------
 namespace pfpn {
 constexpr int TC_WGRAD_CHUNK = 2048;
+// batch rows per split: 2048 at scale (<= 128 accumulations per TMEM accumulator); halved while the launch
+// would leave SMs idle (small per-GPU minibatches of the strong-scaled DPPO update), never below 256
+static int wgrad_chunk(int M, int K, int N) {
+  const long long tiles = (long long)((N + TC_BN - 1) / TC_BN) * ((K + TC_BM - 1) / TC_BM);
+  int chunk = TC_WGRAD_CHUNK;
+  while (chunk > 256 && tiles * ((M + chunk - 1) / chunk) < 148) chunk >>= 1;
+  return chunk;
+}
 __global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, size_t n4, int splits,
                                         size_t stride) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -495,7 +503,8 @@ __global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, float* _
 
 extern "C" int pfpn_tc_wgrad_workspace_bytes(int32_t M, int32_t K, int32_t N, size_t* bytes) {
   if (!bytes || M <= 0 || K <= 0 || N <= 0) return PFPN_ERR_ARG;
-  const size_t splits = ((size_t)M + TC_WGRAD_CHUNK - 1) / TC_WGRAD_CHUNK;
+  const int chunk = wgrad_chunk(M, K, N);
+  const size_t splits = ((size_t)M + chunk - 1) / chunk;
   *bytes = splits * ((size_t)K * N + N) * sizeof(float) + 256;
   return PFPN_OK;
 }
@@ -506,7 +515,8 @@ extern "C" int pfpn_tc_linear_bwd_weight(const float* X, int32_t ldx, const floa
   if (!X || !dY || !dW || M <= 0 || K <= 0 || N <= 0) return PFPN_ERR_ARG;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   if ((ldx & 3) || (ldy & 3) || (N & 3) || !al16(X) || !al16(dY) || !al16(dW) || !al16(db) || !al16(workspace)) return PFPN_ERR_ALIGN;
-  const int splits = (M + TC_WGRAD_CHUNK - 1) / TC_WGRAD_CHUNK;
+  const int chunk = wgrad_chunk(M, K, N);
+  const int splits = (M + chunk - 1) / chunk;
   size_t need;
   pfpn_tc_wgrad_workspace_bytes(M, K, N, &need);
   if ((splits > 1 || db) && (!workspace || workspace_bytes < need)) return PFPN_ERR_WORKSPACE;
@@ -518,7 +528,7 @@ extern "C" int pfpn_tc_linear_bwd_weight(const float* X, int32_t ldx, const floa
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   float* out = splits > 1 ? reinterpret_cast<float*>(workspace) : dW;
   float* cs_part = db ? reinterpret_cast<float*>(workspace) + (size_t)splits * K * N : nullptr;
-  TcParams p{out, nullptr, nullptr, K, N, M, N, 0, TC_EPI_NONE, TC_WGRAD_CHUNK, cs_part};
+  TcParams p{out, nullptr, nullptr, K, N, M, N, 0, TC_EPI_NONE, chunk, cs_part};
   dim3 grid((N + TC_BN - 1) / TC_BN, (K + TC_BM - 1) / TC_BM, splits);
   rc = tc_launch<true, true>(mapA, mapB, p, grid, st);
   if (rc != PFPN_OK) return rc;

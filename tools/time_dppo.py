@@ -27,14 +27,17 @@ torch.cuda.synchronize()
 if world > 1: dist.barrier()
 n = 10
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
+import time
+e0.record(); w0 = time.perf_counter()
 for _ in range(n): step()
+w1 = time.perf_counter()  # host time to ISSUE the n steps (no sync): launch-bound if close to the device time
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
+cpu_issue_ms = (w1 - w0) * 1e3 / n
 t = torch.tensor([ms], device=dev)
 if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     flops = 12.6e6 * B_total
     print(json.dumps({"world": world, "B_total": B_total, "ms_per_update": round(float(t), 3), "samples_per_s": round(B_total / float(t) * 1e3),
-                      "trunk_TFLOPs": round(flops / float(t) / 1e9, 1), "params_equal_hash": float(net.params.double().sum())}))
+                      "trunk_TFLOPs": round(flops / float(t) / 1e9, 1), "host_issue_ms_per_update": round(cpu_issue_ms, 3), "params_equal_hash": float(net.params.double().sum())}))
 if world > 1: dist.destroy_process_group()
