@@ -264,6 +264,14 @@ int pfpn_normalizer_update(const float* state, float* mean, float* std, int32_t 
  * Replaces: ClipPPONetwork.build_value_loss / setup_value_target_tensor   ppo.py:31-42 */
 int pfpn_value_loss(const float* v, const float* adv, const float* v_old, float* dv, float* loss, int32_t B,
                     float coef, float scale, pfpn_stream_t stream);
+/* Rollout side: generalised advantage estimate and value target of E trajectories of T steps,
+ * reward [E,T], value [E,T+1] (bootstrap value last): td_t = r_t + gamma v_{t+1} - v_t, adv_t = td_t + gae_gamma adv_{t+1}
+ * (gae_gamma = gamma*lambda; 0 -> adv = td), vtarget = v + adv (nullable).  Sequential fp32 scan per trajectory in the
+ * reference's op order -> bit-exact.
+ * Replaces: A2CNetwork.generalized_advantage_estimate / value_target_estimate  networks/actor_critic/a2c.py:30-49,
+ *           discount  networks/utils.py:5-15 */
+int pfpn_gae(const float* reward, const float* value, float* adv, float* vtarget, int32_t E, int32_t T, float gamma,
+             float gae_gamma, pfpn_stream_t stream);
 /* grads *= clip * min(1/||grads||, 1/clip) (NaN if the norm is not finite); norm_scale = {norm, scale};
  * clip <= 0 only computes the norm.  scratch >= 296 doubles.
  * Replaces: clip_grads -> tf.clip_by_global_norm      models/workers/base_worker.py:97-102 */

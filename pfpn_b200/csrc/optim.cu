@@ -191,6 +191,42 @@ extern "C" int pfpn_value_loss(const float* v, const float* adv, const float* v_
   return PFPN_OK;
 }
 
+// ---- rollout side: generalised advantage estimate + value target for E trajectories of T steps -------
+// Reference: A2CNetwork.generalized_advantage_estimate / value_target_estimate (networks/actor_critic/
+// a2c.py:30-49) over `discount` (networks/utils.py:5-15): td_t = r_t + gamma v_{t+1} - v_t (fp32, numpy op
+// order), adv_t = td_t + gae_gamma adv_{t+1} scanned backwards from 0; gae_gamma == 0 -> adv = td.
+// One thread per trajectory: the scan is sequential in the reference too, so the result is bit-exact
+// (explicit _rn operations: no FMA contraction).  Layout [E, T] / [E, T+1] row-major.
+namespace pfpn {
+__global__ void gae_kernel(const float* __restrict__ reward, const float* __restrict__ value, float* __restrict__ adv,
+                           float* __restrict__ vtarget, int E, int T, float gamma, float gae_gamma) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const float* r = reward + (size_t)e * T;
+  const float* v = value + (size_t)e * (T + 1);
+  float run = 0.f;
+  float v_next = v[T];
+  for (int t = T - 1; t >= 0; --t) {
+    const float vt = v[t];
+    const float td = __fsub_rn(__fadd_rn(r[t], __fmul_rn(gamma, v_next)), vt);
+    run = gae_gamma != 0.f ? __fadd_rn(td, __fmul_rn(gae_gamma, run)) : td;
+    adv[(size_t)e * T + t] = run;
+    if (vtarget != nullptr) vtarget[(size_t)e * T + t] = __fadd_rn(vt, run);
+    v_next = vt;
+  }
+}
+}  // namespace pfpn
+
+extern "C" int pfpn_gae(const float* reward, const float* value, float* adv, float* vtarget, int32_t E, int32_t T, float gamma,
+                        float gae_gamma, pfpn_stream_t stream_) {
+  if (!reward || !value || !adv || E < 0 || T < 0) return PFPN_ERR_ARG;
+  if (E == 0 || T == 0) return PFPN_OK;
+  pfpn::gae_kernel<<<(E + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(reward, value, adv, vtarget, E, T, gamma,
+                                                                                         gae_gamma);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}
+
 // norm_scale[2] = {global norm, applied scale}; scratch: kNormBlocks doubles.  In place on `grads`.
 extern "C" int pfpn_clip_by_global_norm(float* grads, size_t n, float clip, float* norm_scale, void* scratch,
                                         size_t scratch_bytes, pfpn_stream_t stream_) {

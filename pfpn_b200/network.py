@@ -264,6 +264,36 @@ class ParticleFilteringClipPPONetwork:
         _, _, value, _ = self._forward(self._dev_state(np.asarray(state, dtype=np.float32)[None]))
         return float(value[0])
 
+    # ------------------------------------------------------------- rollout post-processing ----
+    def generalized_advantage_estimate(self, reward, value, normalize=False):
+        """a2c.py:30-40 on the device, batched over trajectories: reward [E,T] (or [T]), value [E,T+1] (or [T+1],
+        bootstrap value last) -> advantage with the same leading shape.  ``gae_gamma = gamma*lambd`` as in a2c.py:21."""
+        adv, _ = self._gae(reward, value, want_target=False)
+        if normalize:  # a2c.py:36-40 normalises over the whole trajectory (host-side option, unused by DPPO)
+            adv = (adv - adv.mean()) / (adv.std(unbiased=False) + (1e-6 if self.gae_gamma else 1e-8))
+        return adv
+
+    def advantage_and_value_target(self, reward, value):
+        """(advantage, value_target = value[:-1] + advantage): what the PPO worker feeds as `advantage` and
+        what setup_value_target_tensor rebuilds as adv + v_old (workers/ppo.py:43-73, ppo.py:31-34)."""
+        return self._gae(reward, value, want_target=True)
+
+    def _gae(self, reward, value, want_target):
+        r = torch.as_tensor(reward, dtype=torch.float32).to(self.device)
+        v = torch.as_tensor(value, dtype=torch.float32).to(self.device)
+        squeeze = r.dim() == 1
+        r, v = r.reshape(-1, r.shape[-1]).contiguous(), v.reshape(-1, v.shape[-1]).contiguous()
+        E, T = r.shape
+        if v.shape != (E, T + 1):
+            raise ValueError("value must hold one more entry per trajectory than reward (the bootstrap value)")
+        adv = torch.empty_like(r)
+        tgt = torch.empty_like(r) if want_target else None
+        _cabi.check(_cabi.pfpn_gae(r.data_ptr(), v.data_ptr(), adv.data_ptr(), tgt.data_ptr() if want_target else None, E, T,
+                                   float(self.gamma), float(self.gae_gamma or 0.0), _stream_ptr()))
+        if squeeze:
+            adv, tgt = adv[0], (tgt[0] if want_target else None)
+        return adv, tgt
+
     # ------------------------------------------------------------------------ train step ----
     def compute_gradients(self, state, action, value, log_prob, advantage, loss_scale: Optional[float] = None):
         """Forward + backward of loss = policy_loss + value_loss_coef * value_loss on this rank's
