@@ -305,6 +305,14 @@ int pfpn_peer_allreduce_adam(const float* const* buckets, int32_t* const* flags,
                              int32_t value, size_t n_params, size_t n_total, float* params, float* m, float* v,
                              float* avg_out, float lr, float beta1, float beta2, float eps, int64_t step,
                              pfpn_stream_t stream);
+/* Two-phase form for N >= 3 GPUs (reduce-scatter + all-gather inside ONE kernel; 2(N-1)/N instead of N-1 bucket
+ * volumes per GPU over NVLink): rank r averages its 1/N slice in rank order, publishes it in `reduced[r]`, every rank
+ * gathers the N averaged slices and applies Adam to all parameters.  `reduced`: HOST array of nranks peer-mapped
+ * buffers of n_total floats; the flag buffers must hold >= 64 zero-initialised ints; `value` = 1, 2, 3, ... per call. */
+int pfpn_peer_allreduce_adam_rs(const float* const* buckets, float* const* reduced, int32_t* const* flags, int32_t rank,
+                                int32_t nranks, int32_t value, size_t n_params, size_t n_total, float* params, float* m,
+                                float* v, float* avg_out, float lr, float beta1, float beta2, float eps, int64_t step,
+                                pfpn_stream_t stream);
 /* The sharded head's only exchange: out[n] = scale * sum_r buckets[r][n] for the [2,A,P] particle
  * gradients -- signal, wait and the rank-ordered sum in ONE kernel over peer memory (same staging / flag
  * protocol as above; `value` = call counter, +1 per call, buffers alternate by its parity). */

@@ -156,6 +156,9 @@ pfpn_peer_signal = _sig("pfpn_peer_signal", C.c_int, [_vp, _vp, _i32, _i32, _i32
 pfpn_peer_allreduce_adam = _sig("pfpn_peer_allreduce_adam", C.c_int,
                                 [_vp, _vp, _i32, _i32, _i32, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _vp, _f, _f, _f, _f,
                                  C.c_int64, _vp])
+pfpn_peer_allreduce_adam_rs = _sig("pfpn_peer_allreduce_adam_rs", C.c_int,
+                                   [_vp, _vp, _vp, _i32, _i32, _i32, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _vp, _f, _f, _f, _f,
+                                    C.c_int64, _vp])
 pfpn_peer_allreduce_sum = _sig("pfpn_peer_allreduce_sum", C.c_int, [_vp, _vp, _i32, _i32, _i32, C.c_size_t, _vp, _f, _vp])
 pfpn_peer_alloc = _sig("pfpn_peer_alloc", C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p])
 pfpn_peer_open = _sig("pfpn_peer_open", C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)])

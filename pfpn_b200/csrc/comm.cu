@@ -72,6 +72,84 @@ __global__ void __launch_bounds__(256) peer_allreduce_adam_kernel(PeerPtrs pp, i
   }
 }
 
+// Two-phase variant for N >= 3 (reduce-scatter + all-gather inside one kernel): reading all N buckets on every
+// rank moves (N-1) x 8.4 MB per GPU over NVLink; here rank r sums only its 1/N slice (phase 1), publishes the
+// averaged slice in its own peer-visible `red` buffer, and every rank then gathers the N averaged slices and
+// applies Adam to all parameters (phase 2): 2 (N-1)/N x 8.4 MB per GPU.  Flag words per rank: [0,8) bucket
+// published (by peer), [8,16) averaged slice published (by peer), [32] local CTA-arrival counter.
+// Replicas stay bit-identical: every element is summed once, in rank order, by its owning rank.
+struct PeerPtrs2 {
+  const float* bucket[kMaxPeers];
+  float* red[kMaxPeers];
+  int* flags[kMaxPeers];
+};
+__global__ void __launch_bounds__(256) peer_allreduce_adam_rs_kernel(PeerPtrs2 pp, int rank, int nranks, int value, size_t n_params,
+                                                                     size_t n_total, size_t slice4, float* __restrict__ params,
+                                                                     float* __restrict__ m, float* __restrict__ v,
+                                                                     float* __restrict__ avg_out, float lr_t, float b1, float b2,
+                                                                     float eps) {
+  const size_t n4 = n_total / 4;
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+  // ---- phase 0: every peer has published its clipped bucket of this step
+  if (threadIdx.x < nranks) {
+    const volatile int* f = reinterpret_cast<const volatile int*>(pp.flags[rank]) + threadIdx.x;
+    while (*f < value) {
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  // ---- phase 1: mean of my slice, in rank order
+  const float inv_n = 1.f / (float)nranks;
+  const size_t lo = (size_t)rank * slice4, hi = min(n4, lo + slice4);
+  for (size_t i = lo + gtid; i < hi; i += gsz) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < nranks; ++p) {
+      const float4 g = __ldcg(reinterpret_cast<const float4*>(pp.bucket[p]) + i);
+      s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+    }
+    s.x *= inv_n; s.y *= inv_n; s.z *= inv_n; s.w *= inv_n;
+    reinterpret_cast<float4*>(pp.red[rank])[i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    int* ctr = pp.flags[rank] + 32;
+    const int arrived = atomicAdd(ctr, 1) + 1;
+    if (arrived == (int)gridDim.x * value) {  // last CTA of this call (the counter is never reset; value = call index)
+      __threadfence_system();
+      for (int p = 0; p < nranks; ++p) *reinterpret_cast<volatile int*>(pp.flags[p] + 8 + rank) = value;
+    }
+  }
+  // ---- phase 2: gather the averaged slices (own slice first, then the peers round-robin) + Adam on everything
+  for (int k = 0; k < nranks; ++k) {
+    const int q = (rank + k) % nranks;
+    if (threadIdx.x == 0) {
+      const volatile int* f = reinterpret_cast<const volatile int*>(pp.flags[rank]) + 8 + q;
+      while (*f < value) {
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    const size_t qlo = (size_t)q * slice4, qhi = min(n4, qlo + slice4);
+    for (size_t i = qlo + gtid; i < qhi; i += gsz) {
+      const float4 s = __ldcg(reinterpret_cast<const float4*>(pp.red[q]) + i);
+      reinterpret_cast<float4*>(avg_out)[i] = s;
+      if (i * 4 < n_params) {
+        float4 mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i], pi = reinterpret_cast<float4*>(params)[i];
+#define PFPN_ADAM1(c)                                   \
+  mi.c = b1 * mi.c + (1.f - b1) * s.c;                  \
+  vi.c = b2 * vi.c + (1.f - b2) * s.c * s.c;            \
+  pi.c -= lr_t * mi.c / (sqrtf(vi.c) + eps);
+        PFPN_ADAM1(x) PFPN_ADAM1(y) PFPN_ADAM1(z) PFPN_ADAM1(w)
+#undef PFPN_ADAM1
+        reinterpret_cast<float4*>(m)[i] = mi;
+        reinterpret_cast<float4*>(v)[i] = vi;
+        reinterpret_cast<float4*>(params)[i] = pi;
+      }
+    }
+  }
+}
+
 // Small exchange of the head's [2, A, P] particle gradients (the only collective of the
 // sharded head path): signal + wait + ordered sum in ONE kernel.  The bucket was written by the kernel
 // before this one on the stream (head_finalize writes straight into the staging buffer).
@@ -150,6 +228,34 @@ extern "C" int pfpn_peer_allreduce_adam(const float* const* buckets, int32_t* co
   const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
   peer_allreduce_adam_kernel<<<296, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
       pp, rank, nranks, value, n_params, n_total, params, m, v, avg_out, (float)lr_t, beta1, beta2, eps);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}
+
+// Two-phase (reduce-scatter + all-gather) form of pfpn_peer_allreduce_adam for N >= 3.  `reduced`: HOST array of nranks
+// peer-mapped device buffers of n_total floats (one per rank, written only by its owner); `flags` buffers must hold >= 64
+// ints, zero-initialised; `value` must be 1, 2, 3, ... on successive calls (it is also the call index of the CTA counter).
+extern "C" int pfpn_peer_allreduce_adam_rs(const float* const* buckets, float* const* reduced, int32_t* const* flags, int32_t rank,
+                                           int32_t nranks, int32_t value, size_t n_params, size_t n_total, float* params, float* m,
+                                           float* v, float* avg_out, float lr, float beta1, float beta2, float eps, int64_t step,
+                                           pfpn_stream_t stream_) {
+  PeerPtrs pp1;
+  int rc = fill_peers(&pp1, buckets, flags, nranks);
+  if (rc != PFPN_OK) return rc;
+  if (!reduced || !params || !m || !v || !avg_out || (n_params & 3) || (n_total & 3) || n_params > n_total || step < 1 || value < 1)
+    return PFPN_ERR_ARG;
+  PeerPtrs2 pp;
+  for (int p = 0; p < kMaxPeers; ++p) {
+    pp.bucket[p] = pp1.bucket[p];
+    pp.flags[p] = pp1.flags[p];
+    pp.red[p] = p < nranks ? reduced[p] : nullptr;
+    if (p < nranks && !reduced[p]) return PFPN_ERR_ARG;
+  }
+  const size_t n4 = n_total / 4;
+  const size_t slice4 = (n4 + nranks - 1) / nranks;
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
+  peer_allreduce_adam_rs_kernel<<<296, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      pp, rank, nranks, value, n_params, n_total, slice4, params, m, v, avg_out, (float)lr_t, beta1, beta2, eps);
   PFPN_CUDA_OK(cudaGetLastError());
   return PFPN_OK;
 }

@@ -16,6 +16,8 @@ from __future__ import annotations
 
 from typing import Optional, Tuple
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -119,17 +121,27 @@ class SyncReplicasAdam:
         """Steps 2-5 in one kernel over peer memory: sum in rank order, mean, Adam, averaged statistics."""
         from .peer import PeerBuckets
         if self._peers is None:
-            self._peers = PeerBuckets(net.bucket.numel(), net.params.device, self.group)
+            self._peers = PeerBuckets(net.bucket.numel(), net.params.device, self.group, with_reduced=True)
         pb = self._peers
         self.step += 1
-        parity = self.step & 1
+        # the exchange protocol counts ITS OWN calls (1, 2, 3, ... since the buffers were created); the Adam
+        # step may start anywhere (checkpoint resume)
+        pb.calls += 1
+        val, parity = pb.calls, pb.calls & 1
         pb.stage[parity].copy_(net.bucket)  # publish this rank's clipped bucket (device-to-device, 8.4 MB)
         buckets, flags = pb.ptrs(parity)
-        _cabi.check(_cabi.pfpn_peer_signal(buckets, flags, pb.rank, pb.world, self.step, st))
-        _cabi.check(_cabi.pfpn_peer_allreduce_adam(buckets, flags, pb.rank, pb.world, self.step, net.n_params,
-                                                   net.bucket.numel(), net.params.data_ptr(), self.m.data_ptr(),
-                                                   self.v.data_ptr(), net.bucket.data_ptr(), self.lr, self.beta1, self.beta2,
-                                                   self.eps, self.step, st))
+        _cabi.check(_cabi.pfpn_peer_signal(buckets, flags, pb.rank, pb.world, val, st))
+        if pb.world >= int(os.environ.get("PFPN_PEER_TWO_PHASE_MIN", "6")):
+            # reduce-scatter + all-gather inside the kernel: 2(N-1)/N bucket volumes per GPU instead of N-1
+            _cabi.check(_cabi.pfpn_peer_allreduce_adam_rs(buckets, pb.reduced_ptrs, flags, pb.rank, pb.world, val,
+                                                          net.n_params, net.bucket.numel(), net.params.data_ptr(),
+                                                          self.m.data_ptr(), self.v.data_ptr(), net.bucket.data_ptr(), self.lr,
+                                                          self.beta1, self.beta2, self.eps, self.step, st))
+        else:
+            _cabi.check(_cabi.pfpn_peer_allreduce_adam(buckets, flags, pb.rank, pb.world, val, net.n_params,
+                                                       net.bucket.numel(), net.params.data_ptr(), self.m.data_ptr(),
+                                                       self.v.data_ptr(), net.bucket.data_ptr(), self.lr, self.beta1, self.beta2,
+                                                       self.eps, self.step, st))
         self.unpack_stats(net, 1.0)  # the kernel wrote the averaged bucket back
         net.global_step += 1
         for op in net.train_ops:

@@ -28,30 +28,37 @@ def _alloc(nbytes: int):
 
 
 class PeerBuckets:
-    def __init__(self, n_total: int, device: torch.device, group=None):
+    def __init__(self, n_total: int, device: torch.device, group=None, with_reduced: bool = False):
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if self.world > 8:
             raise ValueError("peer all-reduce covers one NVSwitch node (<= 8 ranks)")
         self.n_total, self.dev, self.group = n_total, device, group
         with torch.cuda.device(device):
             self._stage_ptr, h_stage = _alloc(2 * n_total * 4)
-            self._flag_ptr, h_flag = _alloc(16 * 4)
+            self._flag_ptr, h_flag = _alloc(64 * 4)
+            # averaged-slice buffer of the two-phase all-reduce (pfpn_peer_allreduce_adam_rs); tiny dummy otherwise
+            self._red_ptr, h_red = _alloc((n_total if with_reduced else 4) * 4)
             self.stage = torch.as_tensor(_CudaArray(self._stage_ptr, 2 * n_total, "<f4"), device=device).view(2, n_total)
             gathered: List = [None] * self.world
-            dist.all_gather_object(gathered, (h_stage, h_flag), group=group)
-            stage_ptrs, flag_ptrs = [], []
-            for r, (hs, hf) in enumerate(gathered):
+            dist.all_gather_object(gathered, (h_stage, h_flag, h_red), group=group)
+            stage_ptrs, flag_ptrs, red_ptrs = [], [], []
+            for r, (hs, hf, hr) in enumerate(gathered):
                 if r == self.rank:
                     stage_ptrs.append(self._stage_ptr)
                     flag_ptrs.append(self._flag_ptr)
+                    red_ptrs.append(self._red_ptr)
                     continue
-                ps, pf = C.c_void_p(), C.c_void_p()
+                ps, pf, pr = C.c_void_p(), C.c_void_p(), C.c_void_p()
                 _cabi.check(_cabi.pfpn_peer_open(hs, C.byref(ps)))
                 _cabi.check(_cabi.pfpn_peer_open(hf, C.byref(pf)))
+                _cabi.check(_cabi.pfpn_peer_open(hr, C.byref(pr)))
                 stage_ptrs.append(ps.value)
                 flag_ptrs.append(pf.value)
+                red_ptrs.append(pr.value)
         dist.barrier(group=group)
         self._flag_ptrs = (C.c_void_p * self.world)(*flag_ptrs)
+        self.calls = 0  # exchange calls issued on these buffers (flag value / buffer parity / CTA-counter epoch)
+        self.reduced_ptrs = (C.c_void_p * self.world)(*red_ptrs)
         self._bucket_ptrs = [(C.c_void_p * self.world)(*[p + par * n_total * 4 for p in stage_ptrs]) for par in (0, 1)]
 
     def ptrs(self, parity: int):
