@@ -326,7 +326,7 @@ def main():
                     "api": "pfpn_b200.host.HostHeadPipeline.run (pinned host buffers, 3-stream chunked)"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "pfpn::head_kernel<4,9,..,BWD> (+head_finalize)",
+                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "pfpn::head_kernel<.., KM=PPO> (+head_finalize)",
                          "alg_bytes_per_state": ALG_BYTES_PER_STATE, "kernel_ms_avg": k_avg_ms,
                          "kernel_ms_median": kms[len(kms) // 2]},
         }

@@ -59,10 +59,16 @@ __device__ __forceinline__ float softplusf_acc(float x) {
 // KM (kernel mode): 0 = forward only; 1 = backward, every feature decided at run time;
 // 2 / 3 = lean PPO / GRAD backward (no tanh, no entropy gradient, no dvalue, no ent_ba:
 // the DPPO train step) with those branches compiled out.
-// CSM: per-(a,k) constants live in shared memory instead of registers.
-template <int LPR, int EPL, int RPT, int NSTAGE, int KM, int MAXT, int NREG, int PT, int AT, bool CSM>
+// OPT bit 0 (CSM): per-(a,k) constants live in shared memory instead of registers.
+// OPT bit 1 (RC):  the backward pass does not carry the particle terms e1_k, e2_k of a tile in registers
+//                  across the pipeline step; pass C re-reads the (still intact) logits from the stage and
+//                  recomputes them (+4 MUFU.EX2 per pair on a 30 %-busy pipe).  That frees the registers a
+//                  2-lanes-per-row mapping needs (18 particles per lane), which halves the per-row fixed work.
+template <int LPR, int EPL, int RPT, int NSTAGE, int KM, int MAXT, int NREG, int PT, int AT, int OPT>
 __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG) head_kernel(const HeadKParams kp) {
   constexpr bool BWD = KM != 0;
+  constexpr bool CSM = (OPT & 1) != 0;
+  constexpr bool RC = (OPT & 2) != 0 && BWD;
   constexpr bool LEAN = KM >= 2;
   constexpr int EP2 = (EPL + 1) / 2;  // packed pairs per lane
   // Software pipeline: iteration `it` runs pass A/B of tile it and pass C of tile it-1; the
@@ -265,8 +271,8 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
   // state carried from pass A/B (iteration it) to pass C (iteration it+1); two copies that
   // swap roles every iteration (the loop is unrolled by two so both stay in registers)
   struct RowState {
-    float2 e1[RPT][EP2], e2[RPT][EP2];
-    float inv_s1[RPT], s2r[RPT], Hrow[RPT], l2s1[RPT], v_c[RPT], sc0_c[RPT], sc1_c[RPT];
+    float2 e1[RPT][RC ? 1 : EP2], e2[RPT][RC ? 1 : EP2];
+    float inv_s1[RPT], s2r[RPT], Hrow[RPT], l2s1[RPT], v_c[RPT], sc0_c[RPT], sc1_c[RPT], nmL_c[RPT];
   };
   RowState stA, stB;
 
@@ -343,9 +349,12 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
           s1 = add2(s1, x1);
           s2 = add2(s2, x2);
           h = fma2(x1, t, h);
-          nw.e1[j][i2] = x1;
-          nw.e2[j][i2] = x2;
+          if (!RC) {
+            nw.e1[j][RC ? 0 : i2] = x1;
+            nw.e2[j][RC ? 0 : i2] = x2;
+          }
         }
+        nw.nmL_c[j] = nmL.x;
         const float S1 = row_sum<LPR>(s1.x + s1.y);
         const float S2 = row_sum<LPR>(s2.x + s2.y);
         const float Hs = row_sum<LPR>(h.x + h.y);
@@ -436,6 +445,32 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
         if (!row_ok) g = 0.f;
 
         float* stp = row_ok ? (sbuf + row_off[j] * P + c) : (dummy + c);
+        // RC: same addresses and the same instruction sequence as pass A/B -> bit-identical e1, e2
+        const float* ldp = sbuf + (row_ok ? row_off[j] : a) * P + c;
+        const float2 nmLc = splat2(od.nmL_c[j]);
+        const float2 vRC = splat2(od.v_c[j]);
+        auto terms = [&](const int i2, float2& x1, float2& x2) {
+          if (!RC) {
+            x1 = od.e1[j][RC ? 0 : i2];
+            x2 = od.e2[j][RC ? 0 : i2];
+            return;
+          }
+          const int i0 = 2 * i2, i1 = 2 * i2 + 1;
+          float2 l;
+          l.x = (i0 < nfull) ? ldp[LPR * i0] : ((i0 == nfull && part_ok) ? ldp[LPR * i0] : kNegBig);
+          l.y = (i1 >= EPL) ? kNegBig
+                            : ((i1 < nfull) ? ldp[LPR * i1] : ((i1 == nfull && part_ok) ? ldp[LPR * i1] : kNegBig));
+          const float2 t = fma2(l, L2, nmLc);
+          x1.x = ex2f(t.x);
+          x1.y = ex2f(t.y);
+          const float2 z = fma2(vRC, c_isig(i2), c_nmisig(i2));
+          const float2 q = mul2(z, z);
+          const float2 u = add2(t, c_cst(i2));
+          const float2 t2 = fma2(q, nhl, u);
+          x2.x = ex2f(t2.x);
+          x2.y = ex2f(t2.y);
+        };
+        float dv_rc = 0.f;
         const bool p_ok = od.s2r[j] > 0.f;
         // guard of utils.py:109-117: dL/dp is Inf/NaN when p == 0 -> zeroed
         const float g_row = p_ok ? g : 0.f;
@@ -446,12 +481,18 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
           const float2 nc0 = splat2(-g_row * od.inv_s1[j]);
 #pragma unroll
           for (int i2 = 0; i2 < EP2; ++i2) {
-            const float2 rr = mul2(od.e2[j][i2], gs2v);  // g * r_k
-            const float2 d = fma2(od.e1[j][i2], nc0, rr);
+            float2 e1v, e2v;
+            terms(i2, e1v, e2v);
+            const float2 rr = mul2(e2v, gs2v);  // g * r_k
+            const float2 d = fma2(e1v, nc0, rr);
             const float2 z = fma2(v2, c_isig(i2), c_nmisig(i2));
             const float2 q1 = fma2(z, z, neg1);
             acc1[i2] = fma2(rr, z, acc1[i2]);
             acc2[i2] = fma2(rr, q1, acc2[i2]);
+            if (!LEAN && RC && g_dvalue != nullptr) {  // (RC: the logits are gone after this loop)
+              const float2 w = mul2(mul2(rr, z), c_isig(i2));
+              dv_rc += w.x + w.y;
+            }
             const int i0 = 2 * i2, i1 = 2 * i2 + 1;
             if (i0 < nfull) stp[LPR * i0] = d.x;
             else if (i0 == nfull && part_ok) stp[LPR * i0] = d.x;
@@ -468,17 +509,23 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
           const float2 nc1 = splat2(-ge * kLn2 * od.inv_s1[j]);
 #pragma unroll
           for (int i2 = 0; i2 < EP2; ++i2) {
-            const float2 rr = mul2(od.e2[j][i2], gs2v);
+            float2 e1v, e2v;
+            terms(i2, e1v, e2v);
+            const float2 rr = mul2(e2v, gs2v);
             // t_k = (l_k - m) log2e recovered as log2(e1_k); e1 == 0 contributes nothing
             float2 t;
-            t.x = lg2f(fmaxf(od.e1[j][i2].x, 1e-37f));
-            t.y = lg2f(fmaxf(od.e1[j][i2].y, 1e-37f));
+            t.x = lg2f(fmaxf(e1v.x, 1e-37f));
+            t.y = lg2f(fmaxf(e1v.y, 1e-37f));
             const float2 coef = fma2(t, nc1, nc0);
-            const float2 d = fma2(od.e1[j][i2], coef, rr);
+            const float2 d = fma2(e1v, coef, rr);
             const float2 z = fma2(v2, c_isig(i2), c_nmisig(i2));
             const float2 q1 = fma2(z, z, neg1);
             acc1[i2] = fma2(rr, z, acc1[i2]);
             acc2[i2] = fma2(rr, q1, acc2[i2]);
+            if (!LEAN && RC && g_dvalue != nullptr) {  // (RC: the logits are gone after this loop)
+              const float2 w = mul2(mul2(rr, z), c_isig(i2));
+              dv_rc += w.x + w.y;
+            }
             const int i0 = 2 * i2, i1 = 2 * i2 + 1;
             if (i0 < nfull) stp[LPR * i0] = d.x;
             else if (i0 == nfull && part_ok) stp[LPR * i0] = d.x;
@@ -489,13 +536,15 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
           }
         }
         if (g_dvalue != nullptr) {
-          float dv = 0.f;
+          float dv = dv_rc;
+          if (!RC) {
 #pragma unroll
-          for (int i2 = 0; i2 < EP2; ++i2) {
-            const float2 rr = mul2(od.e2[j][i2], gs2v);
-            const float2 z = fma2(v2, c_isig(i2), c_nmisig(i2));
-            const float2 w = mul2(mul2(rr, z), c_isig(i2));
-            dv += w.x + w.y;
+            for (int i2 = 0; i2 < EP2; ++i2) {
+              const float2 rr = mul2(od.e2[j][RC ? 0 : i2], gs2v);
+              const float2 z = fma2(v2, c_isig(i2), c_nmisig(i2));
+              const float2 w = mul2(mul2(rr, z), c_isig(i2));
+              dv += w.x + w.y;
+            }
           }
           dv = row_sum<LPR>(dv);
           if (row_ok && c == 0) {
@@ -662,11 +711,11 @@ typedef void (*head_kernel_t)(const HeadKParams);
 // first matching entry whose `kmmask` has the kernel mode's bit is the default for that
 // mode, PFPN_HEAD_VARIANT=<n> picks the n-th matching entry instead (tuning aid, read once).
 struct HeadVariant {
-  int pmin, pmax, lpr, epl, rpt, nstage, maxt, nreg, pt, at, csm;
+  int pmin, pmax, lpr, epl, rpt, nstage, maxt, nreg, pt, at, csm;  // csm = OPT bits (1: constants in smem, 2: recompute)
   int kmmask;           // bit KM set: this entry may be the default for kernel mode KM (0 = tuning alternate only)
   head_kernel_t fn[4];  // indexed by KM
 };
-#define PFPN_HK(LPR, EPL, RPT, NST, KM, MAXT, NREG, PT, AT, CSM) head_kernel<LPR, EPL, RPT, NST, KM, MAXT, NREG, PT, AT, CSM>
+#define PFPN_HK(LPR, EPL, RPT, NST, KM, MAXT, NREG, PT, AT, OPT) head_kernel<LPR, EPL, RPT, NST, KM, MAXT, NREG, PT, AT, OPT>
 #define PFPN_HEAD_VARIANT_ENTRY(PMIN, PMAX, LPR, EPL, RPT, NST, MAXT, NREG, PT, AT, CSM, KMM)                  \
   {                                                                                                            \
     PMIN, PMAX, LPR, EPL, RPT, NST, MAXT, NREG, PT, AT, CSM, KMM, {                                                 \
@@ -678,26 +727,30 @@ struct HeadVariant {
 // exactly (P, A) == (PT, AT) -- the shapes BASELINE.json names (A = 36 DeepMimic action
 // dims, P in {10, 35, 100}); PT == AT == 0 entries take both at run time.
 static const HeadVariant kHeadVariants[] = {
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, true, 15),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 6, 288, 96, 35, 36, true, 0),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, false, 0),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 5, 144, 128, 35, 36, true, 0),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 2, 5, 288, 96, 35, 36, true, 0),
-    // P = 100 (SAC sweep): 13 particles per lane spill in the backward modes at 96 registers, so those run
-    // 16 lanes per row (7 per lane, one 19-warp CTA per SM); the forward keeps 8 lanes and two CTAs per SM.
-    // Measured at B = 65536 (ms): FWD .252 (8 lanes) vs .51; PPO .64 vs .70; GRAD .59 vs .63; full .88 vs .91.
-    PFPN_HEAD_VARIANT_ENTRY(100, 100, 16, 7, 1, 6, 576, 96, 100, 36, true, 2 | 4),
-    PFPN_HEAD_VARIANT_ENTRY(100, 100, 16, 7, 1, 5, 576, 96, 100, 36, false, 8),
-    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 5, 288, 96, 100, 36, false, 1),
-    PFPN_HEAD_VARIANT_ENTRY(100, 100, 16, 7, 1, 5, 576, 96, 100, 36, true, 0),
-    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 4, 288, 96, 100, 36, true, 0),
-    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 4, 288, 72, 100, 36, true, 0),
-    PFPN_HEAD_VARIANT_ENTRY(10, 10, 4, 3, 2, 5, 288, 72, 10, 36, false, 15),
-    PFPN_HEAD_VARIANT_ENTRY(1, 12, 4, 3, 2, 5, 320, 96, 0, 0, false, 15),
-    PFPN_HEAD_VARIANT_ENTRY(13, 36, 4, 9, 1, 5, 288, 96, 0, 0, false, 15),
-    PFPN_HEAD_VARIANT_ENTRY(37, 64, 8, 8, 1, 5, 320, 96, 0, 0, false, 15),
-    PFPN_HEAD_VARIANT_ENTRY(65, 104, 8, 13, 1, 5, 288, 96, 0, 0, false, 15),
-    PFPN_HEAD_VARIANT_ENTRY(105, 256, 16, 16, 1, 4, 320, 168, 0, 0, false, 15),
+    // P = 35 (DPPO): 2 lanes per row / 18 particles per lane with recompute (OPT 3) halves the per-row fixed work;
+    // it wins wherever pass C is absent or heavy (B = 65536, ms: FWD .090 vs .117, tanh+dvalue .198 vs .247,
+    // PPO .183 vs .185); the lean GRAD mode stays on 4 lanes per row with carried terms (.179 vs .183).
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 4, 288, 96, 35, 36, 3, 1 | 2 | 4),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, 1, 8),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 6, 288, 96, 35, 36, 1, 0),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, 0, 0),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 5, 144, 128, 35, 36, 1, 0),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 2, 5, 288, 96, 35, 36, 1, 0),
+    // P = 100 (SAC sweep): 13 particles per lane spill in the backward modes when the particle terms are carried,
+    // so the backward runs 8 lanes per row WITH recompute (OPT 3: no carried terms, no spills, two CTAs per SM);
+    // 16 lanes per row / 7 per lane (one 19-warp CTA per SM) is the carried-terms alternative.  Forward: 8 lanes,
+    // constants in registers.  Measured at B = 65536 (ms): PPO .52 (16 lanes .63), GRAD .54 (.56), tanh+dvalue .61
+    // (.86), FWD .25.
+    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 4, 288, 96, 100, 36, 3, 2 | 4 | 8),
+    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 5, 288, 96, 100, 36, 0, 1),
+    PFPN_HEAD_VARIANT_ENTRY(100, 100, 16, 7, 1, 6, 576, 96, 100, 36, 1, 0),
+    PFPN_HEAD_VARIANT_ENTRY(100, 100, 16, 7, 1, 5, 576, 96, 100, 36, 0, 0),
+    PFPN_HEAD_VARIANT_ENTRY(10, 10, 4, 3, 2, 5, 288, 72, 10, 36, 0, 15),
+    PFPN_HEAD_VARIANT_ENTRY(1, 12, 4, 3, 2, 5, 320, 96, 0, 0, 0, 15),
+    PFPN_HEAD_VARIANT_ENTRY(13, 36, 4, 9, 1, 5, 288, 96, 0, 0, 0, 15),
+    PFPN_HEAD_VARIANT_ENTRY(37, 64, 8, 8, 1, 5, 320, 96, 0, 0, 0, 15),
+    PFPN_HEAD_VARIANT_ENTRY(65, 104, 8, 13, 1, 5, 288, 96, 0, 0, 0, 15),
+    PFPN_HEAD_VARIANT_ENTRY(105, 256, 16, 16, 1, 4, 320, 168, 0, 0, 0, 15),
 };
 
 static const HeadVariant* pick_variant(int A, int P, int km) {
@@ -743,7 +796,7 @@ static int plan_head(int A, int P, int km, HeadLaunch* L) {
   L->threads = ((slots * per_slot + 31) & ~31) + 32;  // + the TMA producer warp
   const int stage_bytes = (L->ts * A * P * 4 + L->ts * A * 4 + 127) & ~127;  // logits tile + its action values
   L->smem_bytes = v.nstage * stage_bytes + 8 * (v.nstage + 1) + 3 * L->ts * A * 8 + kHeadMaxWarps * 4 +
-                  (v.lpr * v.epl + 1) * 4 + 16 + (v.csm ? ((v.epl + 1) / 2) * 3 * per_slot * 8 : 0);
+                  (v.lpr * v.epl + 1) * 4 + 16 + ((v.csm & 1) ? ((v.epl + 1) / 2) * 3 * per_slot * 8 : 0);
   L->fn = v.fn[km];
   int dev = 0;
   PFPN_CUDA_OK(cudaGetDevice(&dev));
