@@ -125,6 +125,9 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
     mbar_init(smem_u32(cta_bar), (uint32_t)nthr);
     mbar_fence_init();
   }
+  // programmatic dependent launch: everything above overlaps the tail of the previous kernel on the stream
+  // (adv_stats in the PPO step); no global memory is touched before this point
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // ---- fixed thread -> (slot, a, particle set) mapping ---------------------
   // lane c of a row owns particles k = c + LPR*i, i = 0..EPL-1.  Slots i < nfull are
@@ -567,6 +570,7 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
     }
   }
 
+  asm volatile("griddepcontrol.launch_dependents;");  // let head_finalize's CTAs get resident behind the drain
   // ---------------- drain: the last tile's gradient ------------------------------------
   mbar_wait(cta_bar_a, (uint32_t)(my_tiles & 1));
   const int prev_tile = my_tiles >= 1 ? first_tile + (my_tiles - 1) * tile_step : -1;
@@ -634,6 +638,7 @@ __global__ void __launch_bounds__(256) head_finalize_kernel(const float* __restr
   __shared__ float sh[8][33];
   const int col = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int idx = blockIdx.x * 32 + col;  // column in the [2*AP] partial row
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the head kernel's partials are complete and visible
   float s = 0.f;
   if (idx < 2 * AP)
     for (int p = grp; p < nparts; p += 8) s += part[(size_t)p * 2 * AP + idx];
@@ -658,6 +663,7 @@ __global__ void __launch_bounds__(256) head_finalize_kernel(const float* __restr
 // Eight independent loads per thread per trip keep the single SM's memory pipe busy
 // (a dependent one-load loop costs ~20 us at B = 65536, this ~3 us).
 __global__ void __launch_bounds__(1024) adv_stats_kernel(const float* __restrict__ adv, int B, float* __restrict__ stats) {
+  asm volatile("griddepcontrol.launch_dependents;");  // the head kernel may set up while this one CTA reduces
   __shared__ double sh[2][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double s = 0.0, ss = 0.0;
@@ -813,6 +819,23 @@ static int plan_head(int A, int P, int km, HeadLaunch* L) {
 
 constexpr int kMaxPartCtas = 148 * 8 + 64;
 
+// Launch with programmatic stream serialization (PDL): the kernel may become resident while its predecessor on the
+// stream drains; it orders itself with griddepcontrol.wait before touching global memory.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace pfpn
 
 using namespace pfpn;
@@ -877,13 +900,13 @@ extern "C" int pfpn_head_logprob(const pfpn_head_args* args, void* workspace, si
     kp.part = reinterpret_cast<float*>(workspace);
     kp.loss_part = kp.part + (size_t)grid * 2 * AP;
   }
-  L.fn<<<grid, L.threads, L.smem_bytes, stream>>>(kp);
-  PFPN_CUDA_OK(cudaGetLastError());
+  PFPN_CUDA_OK(launch_pdl(L.fn, dim3(grid), dim3(L.threads), (size_t)L.smem_bytes, stream, kp));
   if (bwd) {
     const int blocks = (int)((2 * AP + 31) / 32);
-    head_finalize_kernel<<<blocks, 256, 0, stream>>>(kp.part, kp.loss_part, a.logstd, a.dloc, a.dlogstd,
-                                                     a.mode == PFPN_HEAD_PPO ? a.loss : nullptr, (int)AP, grid);
-    PFPN_CUDA_OK(cudaGetLastError());
+    PFPN_CUDA_OK(launch_pdl(head_finalize_kernel, dim3(blocks), dim3(256), (size_t)0, stream, (const float*)kp.part,
+                            (const float*)kp.loss_part, (const float*)a.logstd, a.dloc, a.dlogstd,
+                            a.mode == PFPN_HEAD_PPO ? a.loss : (float*)nullptr, (int)AP, grid));
+    
   }
   return PFPN_OK;
 }
