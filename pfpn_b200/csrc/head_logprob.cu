@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
   float* dummy = lossbuf + kHeadMaxWarps;                           // [LPR*EPL] sink for masked rows
   float2* cs = reinterpret_cast<float2*>(dummy + LPR * EPL + ((LPR * EPL) & 1));  // CSM: [EP2*3][A*LPR]
 
-  if (tid == 0) {
+  if (is_producer && lane == 0) {  // the thread that also issues the first loads below, before anyone else is ready
 #pragma unroll
     for (int s = 0; s < NSTAGE; ++s) mbar_init(smem_u32(&full_bar[s]), 1);
     mbar_init(smem_u32(cta_bar), (uint32_t)nthr);
@@ -128,6 +128,32 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
   // programmatic dependent launch: everything above overlaps the tail of the previous kernel on the stream
   // (adv_stats in the PPO step); no global memory is touched before this point
   asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  const bool tail_exists = (B % TS) != 0;
+  const int tail_tile = kp.num_tiles - 1;
+  const int first_tile = blockIdx.x;
+  const int tile_step = gridDim.x;
+  int my_tiles = 0;
+  if (first_tile < kp.num_tiles) my_tiles = (kp.num_tiles - 1 - first_tile) / tile_step + 1;
+
+  auto issue_load = [&](int it) {  // producer lane 0 only
+    const int tile = first_tile + it * tile_step;
+    if (it >= my_tiles) return;
+    if (tail_exists && tile == tail_tile) return;  // tail is copied cooperatively
+    const int st = it % NSTAGE;
+    const uint32_t bar = smem_u32(&full_bar[st]);
+    mbar_expect_tx(bar, (uint32_t)(tile_floats * 4 + (VAL_TMA ? TS * A * 4 : 0)));
+    bulk_g2s(smem_u32(stage_base) + st * stage_bytes, g_logits + (size_t)tile * tile_floats,
+             (uint32_t)(tile_floats * 4), bar);
+    if (VAL_TMA)
+      bulk_g2s(smem_u32(stage_base) + st * stage_bytes + tile_floats * 4, g_value + (size_t)tile * TS * A,
+               (uint32_t)(TS * A * 4), bar);
+  };
+  // the first tiles are in flight while every thread computes its per-(a,k) constants below
+  if (is_producer && lane == 0) {
+#pragma unroll
+    for (int d = 0; d <= DIST; ++d) issue_load(d);
+  }
 
   // ---- fixed thread -> (slot, a, particle set) mapping ---------------------
   // lane c of a row owns particles k = c + LPR*i, i = 0..EPL-1.  Slots i < nfull are
@@ -180,8 +206,6 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
   auto c_nmisig = [&](int i2) -> float2 { return CSM ? csp[(i2 * 3 + 1) * tps] : nmisig_r[CSM ? 0 : i2]; };
   auto c_cst = [&](int i2) -> float2 { return CSM ? csp[(i2 * 3 + 2) * tps] : cst_r[CSM ? 0 : i2]; };
   const bool tanh_flag = LEAN ? false : (kp.a.flags & PFPN_HEAD_FLAG_TANH) != 0;
-  const bool tail_exists = (B % TS) != 0;
-  const int tail_tile = kp.num_tiles - 1;
   const bool has_ent_grad = LEAN ? false : kp.has_ent_grad != 0;
   const float eps_clip = kp.a.eps_clip, loss_scale = kp.a.loss_scale;
 
@@ -194,24 +218,6 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
 
   __syncthreads();  // mbarrier init visible
 
-  const int first_tile = blockIdx.x;
-  const int tile_step = gridDim.x;
-  int my_tiles = 0;
-  if (first_tile < kp.num_tiles) my_tiles = (kp.num_tiles - 1 - first_tile) / tile_step + 1;
-
-  auto issue_load = [&](int it) {  // producer lane 0 only
-    const int tile = first_tile + it * tile_step;
-    if (it >= my_tiles) return;
-    if (tail_exists && tile == tail_tile) return;  // tail is copied cooperatively
-    const int st = it % NSTAGE;
-    const uint32_t bar = smem_u32(&full_bar[st]);
-    mbar_expect_tx(bar, (uint32_t)(tile_floats * 4 + (VAL_TMA ? TS * A * 4 : 0)));
-    bulk_g2s(smem_u32(stage_base) + st * stage_bytes, g_logits + (size_t)tile * tile_floats,
-             (uint32_t)(tile_floats * 4), bar);
-    if (VAL_TMA)
-      bulk_g2s(smem_u32(stage_base) + st * stage_bytes + tile_floats * 4, g_value + (size_t)tile * TS * A,
-               (uint32_t)(TS * A * 4), bar);
-  };
   const uint32_t cta_bar_a = smem_u32(cta_bar);
   if (is_producer) {
     // ===================== TMA producer warp ===========================================
@@ -219,10 +225,6 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
     // compute thread has fenced its gradient STS of tile it-2, so that tile can leave; the
     // stage that load(it+DIST) refills held tile it+DIST-NSTAGE, whose store is older than the
     // NSTAGE-DIST-2 most recent bulk groups.  Only this warp ever blocks on TMA traffic.
-    if (lane == 0) {
-#pragma unroll
-      for (int d = 0; d <= DIST; ++d) issue_load(d);
-    }
     for (int it = 1; it <= my_tiles; ++it) {
       mbar_wait(cta_bar_a, (uint32_t)((it - 1) & 1));
       if (lane == 0) {
