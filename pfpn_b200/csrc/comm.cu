@@ -22,6 +22,15 @@
 namespace pfpn {
 
 constexpr int kMaxPeers = 8;
+// A peer that never publishes (crashed rank, mismatched call counts) must not wedge the GPU: after ~10 s of polling
+// the kernel traps, which surfaces as a launch failure on the host instead of a hang.
+constexpr long long kSpinTimeoutCycles = 20000000000LL;
+__device__ __forceinline__ void spin_until_ge(const volatile int* f, int value) {
+  const long long t0 = clock64();
+  while (*f < value) {
+    if (clock64() - t0 > kSpinTimeoutCycles) __trap();
+  }
+}
 struct PeerPtrs {
   const float* bucket[kMaxPeers];
   int* flags[kMaxPeers];
@@ -42,8 +51,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_adam_kernel(PeerPtrs pp, i
                                                                   float eps) {
   if (threadIdx.x < nranks) {
     const volatile int* f = reinterpret_cast<const volatile int*>(pp.flags[rank]) + threadIdx.x;
-    while (*f < value) {
-    }
+    spin_until_ge(f, value);
     __threadfence_system();
   }
   __syncthreads();
@@ -93,8 +101,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_adam_rs_kernel(PeerPtrs2 p
   // ---- phase 0: every peer has published its clipped bucket of this step
   if (threadIdx.x < nranks) {
     const volatile int* f = reinterpret_cast<const volatile int*>(pp.flags[rank]) + threadIdx.x;
-    while (*f < value) {
-    }
+    spin_until_ge(f, value);
     __threadfence_system();
   }
   __syncthreads();
@@ -125,8 +132,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_adam_rs_kernel(PeerPtrs2 p
     const int q = (rank + k) % nranks;
     if (threadIdx.x == 0) {
       const volatile int* f = reinterpret_cast<const volatile int*>(pp.flags[rank]) + 8 + q;
-      while (*f < value) {
-      }
+      spin_until_ge(f, value);
       __threadfence_system();
     }
     __syncthreads();
@@ -161,8 +167,7 @@ __global__ void __launch_bounds__(256) peer_sum_kernel(PeerPtrs pp, int rank, in
   }
   if (threadIdx.x < nranks) {
     const volatile int* f = reinterpret_cast<const volatile int*>(pp.flags[rank]) + threadIdx.x;
-    while (*f < value) {
-    }
+    spin_until_ge(f, value);
     __threadfence_system();
   }
   __syncthreads();

@@ -423,11 +423,13 @@ static int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld,
 
 template <bool A_MN, bool B_MN>
 static int tc_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcParams& p, dim3 grid, cudaStream_t st) {
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  static int attr_dev = -1;  // per instantiation; the attribute is per device
+  int dev = 0;
+  PFPN_CUDA_OK(cudaGetDevice(&dev));
+  if (dev != attr_dev) {
     PFPN_CUDA_OK(cudaFuncSetAttribute((const void*)tc_gemm_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       TC_SMEM_BYTES));
-    attr_set = true;
+    attr_dev = dev;
   }
   tc_gemm_kernel<A_MN, B_MN><<<grid, 256, TC_SMEM_BYTES, st>>>(mapA, mapB, p);
   PFPN_CUDA_OK(cudaGetLastError());
