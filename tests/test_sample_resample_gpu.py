@@ -39,6 +39,32 @@ def test_plain_sample_indices_bit_exact(cuda_dev, B, A, P):
     assert s.shape == (1, B, A) and torch.equal(s[0], act) and torch.equal(gd.dis_action, idx)
 
 
+def test_plain_sample_uniforms_on_cdf_boundaries_take_the_exact_fp64_path(cuda_dev):
+    """K2 finds the CDF interval in fp32 and accepts it only with a safety margin; uniforms placed ON the fp64
+    interval ends (1e-9 .. 1e-6 of the total away from them) must fall back to the literal fp64 algorithm and agree with it."""
+    import numpy as np
+    rows, P = 6000, 35
+    rng = np.random.RandomState(7)
+    logits = (rng.randn(rows, P) * 2).astype(np.float32)
+    logits[5, :4] = -np.inf
+    logits[6, 10] = -120.0  # underflows in fp32, not in fp64
+    mx = logits.max(1, keepdims=True).astype(np.float64)
+    e = np.where(np.isfinite(logits), np.exp(logits.astype(np.float64) - mx), 0.0)
+    cdf = np.cumsum(e, 1)
+    k = rng.randint(0, P - 1, size=rows)
+    # 1e-9 .. 1e-6 away from an interval end, relative to the total: far inside the fp32 uncertainty zone (forces the
+    # fallback), far outside the last-ulp differences between libm implementations of exp(double)
+    off = 10.0 ** rng.uniform(-9, -6, size=rows) * rng.choice([-1.0, 1.0], size=rows)
+    u = np.clip(cdf[np.arange(rows), k] / cdf[:, -1] + off, 0.0, np.nextafter(1.0, 0.0))
+    ref = oh.tf_multinomial_cpu(logits, u[:, None])[:, 0]
+    lg = torch.tensor(logits, device=cuda_dev).view(rows, 1, P)
+    loc = torch.zeros(1, P, device=cuda_dev)
+    ls = torch.zeros(1, P, device=cuda_dev)
+    _, idx = sampling.sample_plain(lg, loc, ls, ext_uniform=torch.tensor(u, device=cuda_dev).view(rows, 1),
+                                   ext_normal=torch.zeros(rows, 1, P, device=cuda_dev))
+    assert np.array_equal(idx.cpu().numpy().reshape(-1), ref)
+
+
 def test_plain_sample_philox_is_distributed_like_the_mixture(cuda_dev):
     B, A, P = 200000, 2, 5
     logits = torch.tensor([[0.0, 1.0, 2.0, -1.0, 0.5], [3.0, 0.0, 0.0, 0.0, -2.0]]).repeat(B, 1, 1).contiguous()
