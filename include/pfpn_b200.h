@@ -158,9 +158,11 @@ int pfpn_head_mean(const float* logits, const float* loc, float* action, int32_t
  * Replaces: ParticleFilteringA2CNetwork.init, `resample` scope   networks/actor_critic/a2c.py:346-365
  *   max_active = max(max_active, max_b softmax(logits)); sum_active += sum_b softmax(logits).
  * probs [B,A,P] may be NULL (only needed when the caller wants `dis_dist.probs`).
+ * Deterministic (register accumulators per (a,k), ordered two-stage combine; no float atomics); P <= 256.
  * ---------------------------------------------------------------------- */
+int pfpn_stats_workspace_bytes(int32_t B, int32_t A, int32_t P, size_t* bytes);
 int pfpn_stats_update(const float* logits, float* probs, float* max_active, float* sum_active, int32_t B,
-                      int32_t A, int32_t P, pfpn_stream_t stream);
+                      int32_t A, int32_t P, void* workspace, size_t workspace_bytes, pfpn_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * K5  dead-particle resampling.

@@ -260,44 +260,96 @@ __global__ void resample_scatter_w(float* __restrict__ W, const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4: max_active = max(max_active, max_b softmax(logits)), sum_active += sum_b softmax(logits)
-// (a2c.py:356-360).  One warp per mixture row; per-CTA column partials in shared memory, then one
-// atomicMax (values are non-negative, so the int ordering equals the float ordering) and one
-// float atomicAdd per column per CTA.  Optionally writes the probabilities.
+// K4: running activity statistics (a2c.py:346-365): max_active = max(max_active, max_b softmax(logits)),
+// sum_active += sum_b softmax(logits).  Grid (batch chunks, A): every warp of CTA (c, a) walks rows (b, a) of its
+// chunk with the row's particles in registers, so the per-(a,k) running max / sum live in registers -- no atomics,
+// and the result is deterministic: warps are combined in order inside the CTA, chunks in order by the second kernel.
+// Optionally writes the probabilities.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) stats_kernel(const float* __restrict__ logits, float* __restrict__ probs,
-                                                    float* __restrict__ max_active, float* __restrict__ sum_active,
-                                                    int B, int A, int P) {
-  extern __shared__ float sm[];  // [2][A*P]
-  const int AP = A * P;
-  float* smax = sm;
-  float* ssum = sm + AP;
-  for (int i = threadIdx.x; i < 2 * AP; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const long long rows = (long long)B * A;
-  for (long long r = (long long)blockIdx.x * nw + warp; r < rows; r += (long long)gridDim.x * nw) {
-    const int a = (int)(r % A);
-    const float* x = logits + r * P;
-    float m = -3.402823466e38f;
-    for (int k = lane; k < P; k += 32) m = fmaxf(m, x[k]);
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    float s = 0.f;
-    for (int k = lane; k < P; k += 32) s += expf(x[k] - m);
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float inv = 1.f / s;
-    for (int k = lane; k < P; k += 32) {
-      const float p = expf(x[k] - m) * inv;
-      if (probs != nullptr) probs[r * P + k] = p;
-      atomicMax(reinterpret_cast<int*>(&smax[a * P + k]), __float_as_int(p));
-      atomicAdd(&ssum[a * P + k], p);
+constexpr int kStatsWarps = 8;
+template <int MAXE>
+__global__ void __launch_bounds__(kStatsWarps * 32) stats_kernel(const float* __restrict__ logits, float* __restrict__ probs,
+                                                                 float* __restrict__ part, int B, int A, int P, int b_per_chunk) {
+  __shared__ float sh[2][kStatsWarps][32 * MAXE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int a = blockIdx.y;
+  const int b_lo = blockIdx.x * b_per_chunk, b_hi = min(B, b_lo + b_per_chunk);
+  float vmax[MAXE], vsum[MAXE];
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) vmax[e] = vsum[e] = 0.f;
+  constexpr int U = 4;  // rows in flight per warp: the rows of one (chunk, a) are A*P floats apart, latency-bound otherwise
+  for (int b0 = b_lo + warp; b0 < b_hi; b0 += kStatsWarps * U) {
+    float ex[U][MAXE];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int b = b0 + u * kStatsWarps;
+      const float* x = logits + ((size_t)b * A + a) * P;
+#pragma unroll
+      for (int e = 0; e < MAXE; ++e) {
+        const int k = lane + 32 * e;
+        ex[u][e] = (b < b_hi && k < P) ? x[k] : -3.402823466e38f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int b = b0 + u * kStatsWarps;
+      if (b >= b_hi) break;  // warp-uniform
+      const size_t r = (size_t)b * A + a;
+      float m = -3.402823466e38f;
+#pragma unroll
+      for (int e = 0; e < MAXE; ++e) m = fmaxf(m, ex[u][e]);
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < MAXE; ++e) {
+        ex[u][e] = (lane + 32 * e < P) ? expf(ex[u][e] - m) : 0.f;
+        s += ex[u][e];
+      }
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float inv = 1.f / s;
+#pragma unroll
+      for (int e = 0; e < MAXE; ++e) {
+        const int k = lane + 32 * e;
+        const float p = ex[u][e] * inv;
+        if (k < P) {
+          if (probs != nullptr) probs[r * P + k] = p;
+          vmax[e] = fmaxf(vmax[e], p);
+          vsum[e] += p;
+        }
+      }
     }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < AP; i += blockDim.x) {
-    atomicMax(reinterpret_cast<int*>(&max_active[i]), __float_as_int(smax[i]));
-    atomicAdd(&sum_active[i], ssum[i]);
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    sh[0][warp][lane + 32 * e] = vmax[e];
+    sh[1][warp][lane + 32 * e] = vsum[e];
   }
+  __syncthreads();
+  for (int k = threadIdx.x; k < P; k += blockDim.x) {
+    float mx = 0.f, sm = 0.f;
+#pragma unroll
+    for (int w = 0; w < kStatsWarps; ++w) {
+      mx = fmaxf(mx, sh[0][w][k]);
+      sm += sh[1][w][k];
+    }
+    float* dst = part + ((size_t)blockIdx.x * A + a) * P * 2;
+    dst[k] = mx;
+    dst[P + k] = sm;
+  }
+}
+__global__ void stats_finalize_kernel(const float* __restrict__ part, float* __restrict__ max_active,
+                                      float* __restrict__ sum_active, int nchunks, int A, int P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A * P) return;
+  const int a = i / P, k = i - a * P;
+  float mx = 0.f, sm = 0.f;
+  for (int c = 0; c < nchunks; ++c) {
+    const float* src = part + ((size_t)c * A + a) * P * 2;
+    mx = fmaxf(mx, src[k]);
+    sm += src[P + k];
+  }
+  max_active[i] = fmaxf(max_active[i], mx);
+  sum_active[i] += sm;
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -369,18 +421,38 @@ extern "C" int pfpn_resample(const pfpn_resample_args* args, void* workspace, si
   return PFPN_OK;
 }
 
+static int stats_chunks(int B, int A) {
+  int nb = (148 * 4 + A - 1) / A;  // ~4 CTAs per SM overall
+  if (nb > B) nb = B;
+  return nb < 1 ? 1 : nb;
+}
+
+extern "C" int pfpn_stats_workspace_bytes(int32_t B, int32_t A, int32_t P, size_t* bytes) {
+  if (!bytes || B < 0 || A <= 0 || P <= 0) return PFPN_ERR_ARG;
+  *bytes = (size_t)stats_chunks(B, A) * A * P * 2 * sizeof(float) + 16;
+  return PFPN_OK;
+}
+
 extern "C" int pfpn_stats_update(const float* logits, float* probs, float* max_active, float* sum_active, int32_t B,
-                                 int32_t A, int32_t P, pfpn_stream_t stream_) {
+                                 int32_t A, int32_t P, void* workspace, size_t workspace_bytes, pfpn_stream_t stream_) {
   if (!logits || !max_active || !sum_active || B < 0 || A <= 0 || P <= 0) return PFPN_ERR_ARG;
   if (B == 0) return PFPN_OK;
-  const size_t smem = 2 * (size_t)A * P * sizeof(float);
-  if (smem > 200 * 1024) return PFPN_ERR_UNSUPPORTED;
-  PFPN_CUDA_OK(cudaFuncSetAttribute((const void*)stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long rows = (long long)B * A;
-  long long want = (rows + 7) / 8;
-  int grid = (int)(want < 148 * 4 ? want : 148 * 4);
-  if (grid < 1) grid = 1;
-  stats_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(logits, probs, max_active, sum_active, B, A, P);
+  if (P > 256) return PFPN_ERR_UNSUPPORTED;
+  size_t need;
+  pfpn_stats_workspace_bytes(B, A, P, &need);
+  if (!workspace || workspace_bytes < need) return PFPN_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) & 15u) return PFPN_ERR_ALIGN;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  float* part = reinterpret_cast<float*>(workspace);
+  const int nb = stats_chunks(B, A);
+  const int bpc = (B + nb - 1) / nb;
+  const int nchunks = (B + bpc - 1) / bpc;
+  dim3 grid(nchunks, A);
+  if (P <= 64) stats_kernel<2><<<grid, kStatsWarps * 32, 0, st>>>(logits, probs, part, B, A, P, bpc);
+  else if (P <= 128) stats_kernel<4><<<grid, kStatsWarps * 32, 0, st>>>(logits, probs, part, B, A, P, bpc);
+  else stats_kernel<8><<<grid, kStatsWarps * 32, 0, st>>>(logits, probs, part, B, A, P, bpc);
+  PFPN_CUDA_OK(cudaGetLastError());
+  stats_finalize_kernel<<<(A * P + 255) / 256, 256, 0, st>>>(part, max_active, sum_active, nchunks, A, P);
   PFPN_CUDA_OK(cudaGetLastError());
   return PFPN_OK;
 }

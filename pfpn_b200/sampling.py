@@ -111,7 +111,17 @@ def stats_update(logits, max_active, sum_active, want_probs: bool = False):
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape == (A, P)):
             raise ValueError(f"{n}: expected contiguous float32 CUDA [A, P]")
     probs = torch.empty_like(logits) if want_probs else None
+    n = C.c_size_t(0)
+    _cabi.check(_cabi.pfpn_stats_workspace_bytes(B, A, P, C.byref(n)))
+    key = (logits.device, n.value)
+    ws = _stats_ws.get(key)
+    if ws is None:
+        ws = _stats_ws[key] = torch.empty(n.value, dtype=torch.uint8, device=logits.device)
     with torch.cuda.device(logits.device):
         _cabi.check(_cabi.pfpn_stats_update(logits.data_ptr(), None if probs is None else probs.data_ptr(),
-                                            max_active.data_ptr(), sum_active.data_ptr(), B, A, P, _stream_ptr()))
+                                            max_active.data_ptr(), sum_active.data_ptr(), B, A, P, ws.data_ptr(), ws.numel(),
+                                            _stream_ptr()))
     return probs
+
+
+_stats_ws: dict = {}

@@ -211,6 +211,21 @@ def test_activity_statistics(cuda_dev):
     assert rel(mx, ref_max) < 1e-6 and rel(sm, ref_sum) < 1e-4
     gd = MixtureGaussianDistribution(d["logits"].to(cuda_dev), d["loc"].to(cuda_dev), d["logstd"].exp().to(cuda_dev), False)
     assert rel(gd.dis_dist.probs, probs) < 1e-6
+    # deterministic (no float atomics): a second pass from the same state reproduces the statistics bit for bit
+    mx2, sm2 = mx0.to(cuda_dev), sm0.to(cuda_dev)
+    sampling.stats_update(d["logits"].to(cuda_dev), mx2, sm2)
+    assert torch.equal(mx, mx2) and torch.equal(sm, sm2)
+
+
+@pytest.mark.parametrize("B,A,P", [(1, 36, 35), (7, 3, 100), (1001, 36, 10), (33, 5, 200)])
+def test_activity_statistics_ragged_shapes(cuda_dev, B, A, P):
+    g = torch.Generator().manual_seed(B + A + P)
+    logits = torch.randn(B, A, P, generator=g) * 3
+    probs = torch.softmax(logits.double(), -1)
+    mx, sm = torch.zeros(A, P, device=cuda_dev), torch.zeros(A, P, device=cuda_dev)
+    sampling.stats_update(logits.to(cuda_dev), mx, sm)
+    sampling.stats_update(logits.to(cuda_dev), mx, sm)  # running update: max stays, sum doubles
+    assert rel(mx, probs.max(0).values) < 1e-6 and rel(sm, 2 * probs.sum(0)) < 1e-5
 
 
 INT_KEYS = ("invalid", "src", "col", "tcol", "idx")
