@@ -274,6 +274,21 @@ int pfpn_value_loss(const float* v, const float* adv, const float* v_old, float*
  *           discount  networks/utils.py:5-15 */
 int pfpn_gae(const float* reward, const float* value, float* adv, float* vtarget, int32_t E, int32_t T, float gamma,
              float gae_gamma, pfpn_stream_t stream);
+/* SAC learner step: every per-state scalar of the two losses in one launch.
+ *   vf' = min(q1t, q2t) - alpha logp_t;  q_target = reward + gamma not_terminal vf'      (target net, stop-gradient)
+ *   value_loss  = coef mean((q_target - q1r)^2 + (q_target - q2r)^2)                    (critics at the replayed action)
+ *   policy_loss = mean(alpha logp - min(q1a, q2a) - log_alpha (logp + target_entropy))  (critics at the sampled action)
+ * alpha = exp(*log_alpha) (device scalar, treated as a constant).  Writes d/dq1a, d/dq2a (tf.minimum: gradient to x where
+ * x <= y), d/dq1r, d/dq2r, d policy_loss/d logp, and out4 = {value_loss, policy_loss, d policy_loss/d log_alpha, alpha}.
+ * Replaces: AbstractSACNetwork.build_q / setup_value_target_tensor / build_value_loss / build_policy_loss
+ *           networks/actor_critic/sac.py:107-126,132-139,160-173 */
+int pfpn_sac_losses(const float* q1a, const float* q2a, const float* q1r, const float* q2r, const float* q1t,
+                    const float* q2t, const float* logp, const float* logp_t, const float* reward,
+                    const float* not_terminal, const float* log_alpha, float gamma, float coef, float target_entropy,
+                    int32_t B, float* dq1a, float* dq2a, float* dq1r, float* dq2r, float* dlogp, float* out4,
+                    pfpn_stream_t stream);
+/* y = a*y + b*x: the soft target-network update v_ <- (1-tau) v_ + tau v   (sac.py:67-73) */
+int pfpn_axpby(float* y, const float* x, size_t n, float a, float b, pfpn_stream_t stream);
 /* grads *= clip * min(1/||grads||, 1/clip) (NaN if the norm is not finite); norm_scale = {norm, scale};
  * clip <= 0 only computes the norm.  scratch >= 296 doubles.
  * Replaces: clip_grads -> tf.clip_by_global_norm      models/workers/base_worker.py:97-102 */

@@ -144,6 +144,8 @@ pfpn_state_normalize = _sig("pfpn_state_normalize", C.c_int, [_vp, _vp, _vp, _vp
 pfpn_normalizer_update = _sig("pfpn_normalizer_update", C.c_int, [_vp, _vp, _vp, _i32, _i32, _f, _vp, _vp])
 pfpn_value_loss = _sig("pfpn_value_loss", C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _f, _f, _vp])
 pfpn_gae = _sig("pfpn_gae", C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _vp])
+pfpn_sac_losses = _sig("pfpn_sac_losses", C.c_int, [_vp] * 11 + [_f, _f, _f, _i32] + [_vp] * 6 + [_vp])
+pfpn_axpby = _sig("pfpn_axpby", C.c_int, [_vp, _vp, C.c_size_t, _f, _f, _vp])
 pfpn_clip_by_global_norm = _sig("pfpn_clip_by_global_norm", C.c_int, [_vp, C.c_size_t, _f, _vp, _vp, C.c_size_t, _vp])
 pfpn_adam_step = _sig("pfpn_adam_step", C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _f, _f, _f, _f, C.c_int64, _f, _vp])
 pfpn_tc_gemm_nt = _sig("pfpn_tc_gemm_nt", C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp])

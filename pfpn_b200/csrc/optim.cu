@@ -88,6 +88,74 @@ __global__ void __launch_bounds__(1024) value_loss_kernel(const float* __restric
   }
 }
 
+// ---- SAC: every per-state scalar of the two losses in one launch ----------------------------------
+// Reference: AbstractSACNetwork.build_q / setup_value_target_tensor / build_value_loss / build_policy_loss
+// (networks/actor_critic/sac.py:107-126,132-139,160-173):
+//   vf' = min(q1', q2')(s', a') - alpha logp(a'|s');  q_target = sg(r + gamma nt vf')
+//   value_loss  = coef mean((q_target - q1(s,a_hist))^2 + (q_target - q2(s,a_hist))^2)
+//   policy_loss = mean(alpha logp - min(q1, q2)(s, a) - log_alpha sg(logp + target_entropy)),  alpha = sg(exp(log_alpha))
+// Outputs the gradients entering the four critic evaluations, the head (dL/dlogp) and log_alpha.
+// tf.minimum routes the gradient to x where x <= y.  One CTA, fixed summation order.
+__global__ void __launch_bounds__(1024) sac_losses_kernel(const float* __restrict__ q1a, const float* __restrict__ q2a,
+                                                          const float* __restrict__ q1r, const float* __restrict__ q2r,
+                                                          const float* __restrict__ q1t, const float* __restrict__ q2t,
+                                                          const float* __restrict__ logp, const float* __restrict__ logp_t,
+                                                          const float* __restrict__ reward, const float* __restrict__ not_terminal,
+                                                          const float* __restrict__ log_alpha_p, float gamma, float coef,
+                                                          float target_entropy, int B, float* __restrict__ dq1a,
+                                                          float* __restrict__ dq2a, float* __restrict__ dq1r,
+                                                          float* __restrict__ dq2r, float* __restrict__ dlogp,
+                                                          float* __restrict__ out) {
+  __shared__ double sh[3][32];
+  const float log_alpha = *log_alpha_p;
+  const float alpha = expf(log_alpha);
+  const float inv_b = 1.f / (float)B;
+  double sv = 0.0, sp = 0.0, sa = 0.0;
+  for (int i = threadIdx.x; i < B; i += 1024) {
+    const float vf = fminf(q1t[i], q2t[i]) - alpha * logp_t[i];
+    const float qt = reward[i] + gamma * not_terminal[i] * vf;
+    const float e1 = qt - q1r[i], e2 = qt - q2r[i];
+    sv += (double)e1 * e1 + (double)e2 * e2;
+    dq1r[i] = -2.f * coef * e1 * inv_b;
+    dq2r[i] = -2.f * coef * e2 * inv_b;
+    const float lp = logp[i];
+    const bool first = q1a[i] <= q2a[i];
+    sp += (double)(alpha * lp - (first ? q1a[i] : q2a[i]) - log_alpha * (lp + target_entropy));
+    sa += (double)(lp + target_entropy);
+    dq1a[i] = first ? -inv_b : 0.f;
+    dq2a[i] = first ? 0.f : -inv_b;
+    dlogp[i] = alpha * inv_b;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    sv += __shfl_xor_sync(0xffffffffu, sv, o);
+    sp += __shfl_xor_sync(0xffffffffu, sp, o);
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = sv;
+    sh[1][threadIdx.x >> 5] = sp;
+    sh[2][threadIdx.x >> 5] = sa;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tv = 0.0, tp = 0.0, ta = 0.0;
+    for (int w = 0; w < 32; ++w) {
+      tv += sh[0][w];
+      tp += sh[1][w];
+      ta += sh[2][w];
+    }
+    out[0] = (float)(coef * tv * inv_b);   // value_loss (already times value_loss_coef, as self.value_loss is after `*=`)
+    out[1] = (float)(tp * inv_b);          // policy_loss
+    out[2] = (float)(-ta * inv_b);         // d policy_loss / d log_alpha
+    out[3] = alpha;
+  }
+}
+// y = a y + b x  (soft target update: sac.py:67-73 with a = 1 - tau, b = tau)
+__global__ void axpby_kernel(float* __restrict__ y, const float* __restrict__ x, size_t n, float a, float b) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = a * y[i] + b * x[i];
+}
+
 constexpr int kNormBlocks = 296;
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, size_t n, double* __restrict__ part) {
   __shared__ double sh[8];
@@ -223,6 +291,31 @@ extern "C" int pfpn_gae(const float* reward, const float* value, float* adv, flo
   if (E == 0 || T == 0) return PFPN_OK;
   pfpn::gae_kernel<<<(E + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(reward, value, adv, vtarget, E, T, gamma,
                                                                                          gae_gamma);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}
+
+extern "C" int pfpn_sac_losses(const float* q1a, const float* q2a, const float* q1r, const float* q2r, const float* q1t,
+                               const float* q2t, const float* logp, const float* logp_t, const float* reward,
+                               const float* not_terminal, const float* log_alpha, float gamma, float coef, float target_entropy,
+                               int32_t B, float* dq1a, float* dq2a, float* dq1r, float* dq2r, float* dlogp, float* out4,
+                               pfpn_stream_t stream_) {
+  if (!q1a || !q2a || !q1r || !q2r || !q1t || !q2t || !logp || !logp_t || !reward || !not_terminal || !log_alpha || !dq1a ||
+      !dq2a || !dq1r || !dq2r || !dlogp || !out4 || B <= 0)
+    return PFPN_ERR_ARG;
+  pfpn::sac_losses_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      q1a, q2a, q1r, q2r, q1t, q2t, logp, logp_t, reward, not_terminal, log_alpha, gamma, coef, target_entropy, B, dq1a, dq2a,
+      dq1r, dq2r, dlogp, out4);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}
+
+extern "C" int pfpn_axpby(float* y, const float* x, size_t n, float a, float b, pfpn_stream_t stream_) {
+  if (!y || !x) return PFPN_ERR_ARG;
+  if (n == 0) return PFPN_OK;
+  size_t grid = (n + 255) / 256;
+  if (grid > 1184) grid = 1184;
+  pfpn::axpby_kernel<<<(unsigned)grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(y, x, n, a, b);
   PFPN_CUDA_OK(cudaGetLastError());
   return PFPN_OK;
 }
