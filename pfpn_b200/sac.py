@@ -167,8 +167,14 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
             l, X = layers[i], acts[i]
             B = X.shape[0]
             dX = self._buf(f"dq{tag}_{i}", B, l.k)
-            _cabi.check(_cabi.pfpn_mlp_linear_bwd_input(dY.data_ptr(), ldy, l.W.data_ptr(), X.data_ptr() if i > 0 else None,
-                                                        dX.data_ptr(), dX.stride(0), B, l.k, l.n_out, st))
+            if self.use_tensor_cores and l.n_out > 1 and B >= 512:
+                # dX = (dY W^T) [.* relu6'(X)]: W [k, n_out] as stored is the K-major operand of the tcgen05 GEMM
+                _cabi.check(_cabi.pfpn_tc_gemm_nt(dY.data_ptr(), ldy, l.W.data_ptr(), l.n_out, dX.data_ptr(), dX.stride(0), None,
+                                                  X.data_ptr() if i > 0 else None, X.stride(0), B, l.k, l.n_out,
+                                                  3 if i > 0 else 0, st))
+            else:
+                _cabi.check(_cabi.pfpn_mlp_linear_bwd_input(dY.data_ptr(), ldy, l.W.data_ptr(), X.data_ptr() if i > 0 else None,
+                                                            dX.data_ptr(), dX.stride(0), B, l.k, l.n_out, st))
             dY, ldy = dX, dX.stride(0)
         return dY
 
@@ -338,3 +344,54 @@ class SACOptimizer:
         net.global_step += 1
         for op in net.train_ops:
             op()
+
+
+class ReplayRing:
+    """The DDPG/SAC worker's experience ring (models/workers/ddpg.py:11-27: `Buffer`, fixed capacity, overwrite at the
+    write pointer) kept resident in device memory, one row per transition: state, action, reward, not_terminal, state_
+    (`exp_buffers`, ddpg.py:44-46).  `sample(n)` is the off-policy minibatch draw of
+    models/distributed_model.py:372-385 (`np.random.choice(len, n)`: uniform WITH replacement) as one gather."""
+
+    FIELDS = ("state", "action", "reward", "not_terminal", "state_")
+
+    def __init__(self, capacity: int, state_dim: int, action_dim: int, device="cuda", seed: int = 0):
+        self.capacity, self.S, self.A = int(capacity), int(state_dim), int(action_dim)
+        self.width = 2 * self.S + self.A + 2
+        self.data = torch.empty(self.capacity, self.width, dtype=torch.float32, device=device)
+        self.pointer = 0
+        self.size = 0
+        self.gen = torch.Generator(device=self.data.device)
+        self.gen.manual_seed(seed)
+
+    def __len__(self):
+        return self.size
+
+    def clear(self):
+        self.pointer = self.size = 0
+
+    def append(self, state, action, reward, not_terminal, state_):
+        """Append one transition or a batch of them (leading dimension), wrapping around at the capacity."""
+        dev = self.data.device
+        f = lambda t, w: torch.as_tensor(t, dtype=torch.float32, device=dev).reshape(-1, w)
+        rows = torch.cat([f(state, self.S), f(action, self.A), f(reward, 1), f(not_terminal, 1), f(state_, self.S)], dim=1)
+        n = rows.shape[0]
+        if n > self.capacity:  # only the last `capacity` rows survive, as with repeated single appends
+            rows = rows[n - self.capacity:]
+            self.pointer = (self.pointer + n - self.capacity) % self.capacity
+            n = self.capacity
+        first = min(n, self.capacity - self.pointer)
+        self.data[self.pointer:self.pointer + first].copy_(rows[:first])
+        if n > first:
+            self.data[:n - first].copy_(rows[first:])
+        self.pointer = (self.pointer + n) % self.capacity
+        self.size = min(self.capacity, self.size + n)
+
+    def sample(self, n: int):
+        """(state [n,S], action [n,A], reward [n], not_terminal [n], state_ [n,S]) drawn uniformly with replacement."""
+        if self.size == 0:
+            raise ValueError("empty replay ring")
+        idx = torch.randint(0, self.size, (n,), device=self.data.device, generator=self.gen)
+        rows = self.data.index_select(0, idx)
+        S, A = self.S, self.A
+        return (rows[:, :S].contiguous(), rows[:, S:S + A].contiguous(), rows[:, S + A].contiguous(),
+                rows[:, S + A + 1].contiguous(), rows[:, S + A + 2:].contiguous())

@@ -48,7 +48,7 @@ def oracle_params(net):
             for k, (p, _) in net.named_parameters().items()}
 
 
-@pytest.mark.parametrize("B", [64, 256])
+@pytest.mark.parametrize("B", [64, 256, 640])
 def test_sac_train_step_matches_oracle(cuda_dev, B):
     from pfpn_b200.sac import SACOptimizer
     net, batch, draws, (S, A, P) = make(cuda_dev, B)
