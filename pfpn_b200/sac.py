@@ -29,6 +29,7 @@ import torch
 from . import _cabi
 from .distribution import MixtureGaussianDistribution
 from .head import _stream_ptr
+from .learner import SyncReplicasAdam
 from .network import ParticleFilteringClipPPONetwork, _Linear, _pad4
 
 
@@ -323,18 +324,14 @@ class SACOptimizer:
             self._scratch = torch.empty(296, dtype=torch.float64, device=net.params.device)
         _cabi.check(_cabi.pfpn_clip_by_global_norm(net.grads.data_ptr(), net.n_params, self.norm_clip, self.norm_scale.data_ptr(),
                                                    self._scratch.data_ptr(), self._scratch.numel() * 8, st))
+        # statistics pushed through the same accumulators as the gradients (normaliser moments of this minibatch and the
+        # activity statistics: sync_model.py:37-45), then the mean over workers
         inv_n = 1.0
-        if net.normalize_state:
-            tail = net.bucket[net.n_params:]
-            tail[:net.S].copy_(net._new_mean)
-            tail[net.S:2 * net.S].copy_(net._new_std)
+        SyncReplicasAdam.pack_stats(self, net)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(net.bucket, group=self.group)
             inv_n = 1.0 / dist.get_world_size(self.group)
-        if net.normalize_state:
-            tail = net.bucket[net.n_params:]
-            net.state_mean.copy_(tail[:net.S] * inv_n)
-            net.state_std.copy_(tail[net.S:2 * net.S] * inv_n)
+        SyncReplicasAdam.unpack_stats(self, net, inv_n)
         self.step += 1
         nc, n = net.n_critic, net.n_params
         for lo, hi, lr in ((0, nc, self.lr_critic), (nc, n, self.lr_actor)):

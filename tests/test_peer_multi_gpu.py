@@ -24,3 +24,16 @@ def test_fused_peer_allreduce_adam_matches_nccl():
         assert d["replica_equal"] == [True, True] and d["stats_equal"]
         assert d["max_abs_param_diff_fused_vs_nccl"] < 1e-7
         assert d["small_sum_ok"]  # the head's [2,A,P] exchange (pfpn_peer_allreduce_sum) vs NCCL, replicas bit-identical
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_sac_learner_replicas_stay_identical_across_a_resample_tick():
+    port = 29300 + os.getpid() % 300
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "test_sac_2gpu.py")],
+                       capture_output=True, text=True, timeout=600)
+    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 2, r.stdout[-2000:] + r.stderr[-2000:]
+    for d in lines:
+        assert d["params_equal"] and d["target_equal"] and d["state_mean_equal"] and d["finite"]
+    assert lines[0]["loc_row0"] == lines[1]["loc_row0"]
