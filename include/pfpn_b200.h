@@ -146,7 +146,10 @@ typedef struct pfpn_rsample_args {
   int32_t B, A, P;
 } pfpn_rsample_args;
 int pfpn_head_rsample_fwd(const pfpn_rsample_args* args, pfpn_stream_t stream);
-int pfpn_head_rsample_bwd(const pfpn_rsample_args* args, pfpn_stream_t stream);
+/* (backward: dloc / dlogstd are ADDED to -- zero or pre-load them; the accumulation runs in per-lane registers and fixed-order
+ *  partials, so it is bit-reproducible; workspace from pfpn_rsample_bwd_workspace_bytes) */
+int pfpn_rsample_bwd_workspace_bytes(int32_t B, int32_t A, int32_t P, size_t* bytes);
+int pfpn_head_rsample_bwd(const pfpn_rsample_args* args, void* workspace, size_t workspace_bytes, pfpn_stream_t stream);
 
 /* Deterministic action (evaluator): MixtureGaussianDistribution.mean  networks/utils.py:202-236.
  * action[b,a] = loc[a, argmax_k logits[b,a,k]]  (tanh of it with PFPN_HEAD_FLAG_TANH). idx may be NULL. */

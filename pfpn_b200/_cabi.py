@@ -120,7 +120,8 @@ class ResampleArgs(C.Structure):
 
 pfpn_head_sample = _sig("pfpn_head_sample", C.c_int, [C.POINTER(SampleArgs), C.c_void_p])
 pfpn_head_rsample_fwd = _sig("pfpn_head_rsample_fwd", C.c_int, [C.POINTER(RSampleArgs), C.c_void_p])
-pfpn_head_rsample_bwd = _sig("pfpn_head_rsample_bwd", C.c_int, [C.POINTER(RSampleArgs), C.c_void_p])
+pfpn_rsample_bwd_workspace_bytes = _sig("pfpn_rsample_bwd_workspace_bytes", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)])
+pfpn_head_rsample_bwd = _sig("pfpn_head_rsample_bwd", C.c_int, [C.POINTER(RSampleArgs), C.c_void_p, C.c_size_t, C.c_void_p])
 pfpn_head_mean = _sig("pfpn_head_mean", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                                   C.c_int32, C.c_int32, C.c_uint32, C.c_void_p])
 pfpn_stats_workspace_bytes = _sig("pfpn_stats_workspace_bytes", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)])

@@ -65,7 +65,12 @@ __device__ __forceinline__ void normal4(const uint4 q, float (&n)[4]) {
 // FAST keeps the noisy logits in the log2 domain and drops the constant -ln(ln 2) that the two-log
 // Gumbel form carries: argmax and softmax are shift invariant.
 template <bool BWD, bool FAST, int MAXE>
-__global__ void __launch_bounds__(kRsWarps * 32) rsample_kernel(const pfpn_rsample_args ar, const int chunk_rows) {
+__global__ void __launch_bounds__(BWD ? 384 : kRsWarps * 32) rsample_kernel(const pfpn_rsample_args ar, const int chunk_rows,
+                                                                            float* __restrict__ part) {
+  // Backward mapping: a CTA walks whole states (A consecutive rows, contiguous in memory) and warp w owns the action
+  // dimensions a = w, w + nw, ... of every state it sees.  The straight-through gradients of the winning particles
+  // therefore reach acc[a][k*] from ONE warp, in state order, as plain read-modify-writes by the lane that owns k* --
+  // no atomics -- and the per-CTA tables are combined in CTA order by rsample_bwd_finalize_kernel: bit-reproducible.
   extern __shared__ float smem_f[];  // BWD: acc[2][A*P] per-CTA dloc / dlogstd partials, then loc[A*P], sd[A*P]
   const int A = ar.A, P = ar.P, AP = A * P;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -83,20 +88,19 @@ __global__ void __launch_bounds__(kRsWarps * 32) rsample_kernel(const pfpn_rsamp
   }
   const long long rows = (long long)ar.B * A;
   const long long nchunks = (rows + chunk_rows - 1) / chunk_rows;
+  const int nw = blockDim.x >> 5;
   const Philox rng(ar.seed);
-  for (long long c = (long long)blockIdx.x * kRsWarps + warp; c < nchunks; c += (long long)gridDim.x * kRsWarps) {
-    const long long r0 = c * chunk_rows;
-    const int nrow = (int)min((long long)chunk_rows, rows - r0);
-    const int a0 = (int)(r0 % A);
-    int a = a0;
-    // per-row scalars live lane-parallel: lane j <-> row r0 + j
-    float my_ga = 0.f, my_gu = 0.f, my_gp = 0.f, my_off = 0.f;
-    int my_arg = 0;
-    if (BWD && lane < nrow) {
-      my_ga = ar.g_sample[r0 + lane];
-      my_gu = ar.g_s_pre != nullptr ? ar.g_s_pre[r0 + lane] : 0.f;
-    }
-    for (int j = 0; j < nrow; ++j) {
+  // forward: c = chunk of consecutive rows per warp; backward: c = state per CTA, its rows split over the warps by a
+  const long long c_begin = BWD ? (long long)blockIdx.x : (long long)blockIdx.x * nw + warp;
+  const long long c_step = BWD ? (long long)gridDim.x : (long long)gridDim.x * nw;
+  const long long c_end = BWD ? (long long)ar.B : nchunks;
+  for (long long c = c_begin; c < c_end; c += c_step) {
+    const long long r0 = BWD ? c * A : c * chunk_rows;
+    const int nrow = BWD ? A : (int)min((long long)chunk_rows, rows - r0);
+    const int a0 = BWD ? 0 : (int)(r0 % A);
+    int a = BWD ? warp : a0;
+    int my_arg = 0;  // forward: per-row result kept lane-parallel (lane j <-> row r0 + j) for the tail
+    for (int j = BWD ? warp : 0; j < nrow; j += BWD ? nw : 1) {
       const long long r = r0 + j;
       const float* x = ar.logits + r * P;
       float y[MAXE], pk[MAXE], ek[MAXE];
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(kRsWarps * 32) rsample_kernel(const pfpn_rsamp
         }
         const float psel = __shfl_sync(kFull, own_p, arg & 31);
         const float esel = __shfl_sync(kFull, own_e, arg & 31);
-        const float g_a = __shfl_sync(kFull, my_ga, j), g_u = __shfl_sync(kFull, my_gu, j);
+        const float g_a = ar.g_sample[r], g_u = ar.g_s_pre != nullptr ? ar.g_s_pre[r] : 0.f;
         // 1 - tanh(u)^2 without the fp32 cancellation of the literal form: sech^2(u) = 4 e^{-2|u|} / (1 + e^{-2|u|})^2
         float t, omt2, coef;
         if (FAST) {
@@ -219,20 +223,24 @@ __global__ void __launch_bounds__(kRsWarps * 32) rsample_kernel(const pfpn_rsamp
           const int k = lane + 32 * e;
           if (k < P) ar.dlogits[r * P + k] = wexp[e] * inv_s * (D[e] - wd);
         }
-        if (lane == j) {
-          my_arg = arg;
-          my_gp = omt2 * g_a + g_u;           // dL/dp_{k*}
-          my_off = sd_s[a * P + arg] * esel;  // d p_{k*} / d logstd_{k*}
+        if (lane == (arg & 31)) {  // this warp is the only writer of row a of the table: plain read-modify-write
+          const float gp = omt2 * g_a + g_u;                               // dL/dp_{k*}
+          acc_s[a * P + arg] += gp;
+          acc_s[AP + a * P + arg] += gp * (sd_s[a * P + arg] * esel);      // d p_{k*} / d logstd_{k*} = scale * eps
         }
       }
-      if (++a == A) a = 0;
+      if (BWD) {
+        a += nw;
+      } else if (++a == A) {
+        a = 0;
+      }
     }
     // ---- lane-parallel tail: lane j finishes row r0 + j ----
-    if (lane < nrow) {
+    if (!BWD && lane < nrow) {
       const long long r = r0 + lane;
       int al = a0 + lane;
       al -= (al / A) * A;
-      if (!BWD) {
+      {
         float eps;
         if (FAST) {
           // the forward only needs the winner's location draw: regenerate just that block
@@ -248,23 +256,31 @@ __global__ void __launch_bounds__(kRsWarps * 32) rsample_kernel(const pfpn_rsamp
         ar.sample[r] = tanhf(psel);
         ar.s_pre[r] = psel;
         ar.idx[r] = my_arg;
-      } else {
-        atomicAdd(&acc_s[al * P + my_arg], my_gp);
-        atomicAdd(&acc_s[AP + al * P + my_arg], my_gp * my_off);
       }
     }
   }
   if (BWD) {
     __syncthreads();
-    for (int i = threadIdx.x; i < AP; i += blockDim.x) {
-      if (acc_s[i] != 0.f) atomicAdd(&ar.dloc[i], acc_s[i]);
-      if (acc_s[AP + i] != 0.f) atomicAdd(&ar.dlogstd[i], acc_s[AP + i]);
-    }
+    for (int i = threadIdx.x; i < 2 * AP; i += blockDim.x) part[(size_t)blockIdx.x * 2 * AP + i] = acc_s[i];
   }
 }
 
+// dloc / dlogstd += the per-CTA tables, summed in CTA order (the caller pre-zeroes or pre-loads the outputs)
+__global__ void rsample_bwd_finalize_kernel(const float* __restrict__ part, float* __restrict__ dloc, float* __restrict__ dlogstd,
+                                            int nparts, int AP) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * AP) return;
+  float t = 0.f;
+  for (int c = 0; c < nparts; ++c) t += part[(size_t)c * 2 * AP + i];
+  if (i < AP) dloc[i] += t;
+  else dlogstd[i - AP] += t;
+}
+
+constexpr int kRsBwdMaxCtas = 148 * 4;
+static int rs_bwd_warps(int A) { return A % 12 == 0 ? 12 : (A % 9 == 0 ? 9 : 8); }  // rows of a state split evenly
+
 template <bool BWD>
-static int rs_launch(const pfpn_rsample_args& a, size_t smem, cudaStream_t st) {
+static int rs_launch(const pfpn_rsample_args& a, size_t smem, float* part, cudaStream_t st) {
   const bool fast = a.ext_uniform == nullptr;
   const long long rows = (long long)a.B * a.A;
   // chunk = rows one warp walks before its lane-parallel tail: 32 at scale, fewer when the batch is
@@ -274,12 +290,20 @@ static int rs_launch(const pfpn_rsample_args& a, size_t smem, cudaStream_t st) {
   const long long nchunks = (rows + chunk - 1) / chunk;
   long long grid = (nchunks + kRsWarps - 1) / kRsWarps;
   if (grid > 148LL * 8) grid = 148LL * 8;
+  const int threads = BWD ? rs_bwd_warps(a.A) * 32 : kRsWarps * 32;
   const int maxe = a.P <= 64 ? 2 : (a.P <= 128 ? 4 : 8);
 #define PFPN_RS(F, E)                                                                                                   \
   do {                                                                                                                  \
-    if (smem) PFPN_CUDA_OK(cudaFuncSetAttribute((const void*)rsample_kernel<BWD, F, E>,                                 \
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-    rsample_kernel<BWD, F, E><<<(int)grid, kRsWarps * 32, smem, st>>>(a, (int)chunk);                                   \
+    if (BWD) {                                                                                                          \
+      PFPN_CUDA_OK(cudaFuncSetAttribute((const void*)rsample_kernel<BWD, F, E>,                                         \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
+      int occ = 0;                                                                                                      \
+      PFPN_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)rsample_kernel<BWD, F, E>, threads, \
+                                                                 smem));                                                \
+      grid = 148LL * (occ < 1 ? 1 : (occ > 4 ? 4 : occ));                                                               \
+      if (grid > a.B) grid = a.B;                                                                                       \
+    }                                                                                                                   \
+    rsample_kernel<BWD, F, E><<<(int)grid, threads, smem, st>>>(a, (int)chunk, part);                                   \
   } while (0)
   if (fast) {
     if (maxe == 2) PFPN_RS(true, 2);
@@ -292,6 +316,11 @@ static int rs_launch(const pfpn_rsample_args& a, size_t smem, cudaStream_t st) {
   }
 #undef PFPN_RS
   PFPN_CUDA_OK(cudaGetLastError());
+  if (BWD) {
+    const int AP = a.A * a.P;
+    rsample_bwd_finalize_kernel<<<(2 * AP + 255) / 256, 256, 0, st>>>(part, a.dloc, a.dlogstd, (int)grid, AP);
+    PFPN_CUDA_OK(cudaGetLastError());
+  }
   return PFPN_OK;
 }
 
@@ -314,10 +343,17 @@ extern "C" int pfpn_head_rsample_fwd(const pfpn_rsample_args* args, pfpn_stream_
   if (rc != PFPN_OK) return rc;
   if (a.B == 0) return PFPN_OK;
   if (!a.sample || !a.s_pre || !a.idx) return PFPN_ERR_ARG;
-  return rs_launch<false>(a, 0, reinterpret_cast<cudaStream_t>(stream_));
+  return rs_launch<false>(a, 0, nullptr, reinterpret_cast<cudaStream_t>(stream_));
 }
 
-extern "C" int pfpn_head_rsample_bwd(const pfpn_rsample_args* args, pfpn_stream_t stream_) {
+extern "C" int pfpn_rsample_bwd_workspace_bytes(int32_t B, int32_t A, int32_t P, size_t* bytes) {
+  if (!bytes || B < 0 || A <= 0 || P <= 0) return PFPN_ERR_ARG;
+  *bytes = (size_t)kRsBwdMaxCtas * 2 * A * P * sizeof(float) + 16;
+  return PFPN_OK;
+}
+
+extern "C" int pfpn_head_rsample_bwd(const pfpn_rsample_args* args, void* workspace, size_t workspace_bytes,
+                                     pfpn_stream_t stream_) {
   if (!args) return PFPN_ERR_ARG;
   const pfpn_rsample_args& a = *args;
   int rc = rsample_common(a);
@@ -326,5 +362,9 @@ extern "C" int pfpn_head_rsample_bwd(const pfpn_rsample_args* args, pfpn_stream_
   if (!a.g_sample || !a.dlogits || !a.dloc || !a.dlogstd) return PFPN_ERR_ARG;
   const size_t smem = 4 * (size_t)a.A * a.P * sizeof(float);  // acc[2], loc, sd
   if (smem > 200 * 1024) return PFPN_ERR_UNSUPPORTED;
-  return rs_launch<true>(a, smem, reinterpret_cast<cudaStream_t>(stream_));
+  size_t need;
+  pfpn_rsample_bwd_workspace_bytes(a.B, a.A, a.P, &need);
+  if (!workspace || workspace_bytes < need) return PFPN_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) & 15u) return PFPN_ERR_ALIGN;
+  return rs_launch<true>(a, smem, reinterpret_cast<float*>(workspace), reinterpret_cast<cudaStream_t>(stream_));
 }

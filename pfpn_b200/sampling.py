@@ -86,8 +86,14 @@ def rsample_bwd(logits, loc, logstd, g_sample, g_s_pre, *, seed=0, offset=0, ext
     dloc = torch.zeros(a.A, a.P, dtype=torch.float32, device=dev)
     dlogstd = torch.zeros_like(dloc)
     a.dlogits, a.dloc, a.dlogstd = dlogits.data_ptr(), dloc.data_ptr(), dlogstd.data_ptr()
+    n = C.c_size_t(0)
+    _cabi.check(_cabi.pfpn_rsample_bwd_workspace_bytes(a.B, a.A, a.P, C.byref(n)))
+    key = (dev, "rs", n.value)
+    ws = _stats_ws.get(key)
+    if ws is None:
+        ws = _stats_ws[key] = torch.empty(n.value, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        _cabi.check(_cabi.pfpn_head_rsample_bwd(C.byref(a), _stream_ptr()))
+        _cabi.check(_cabi.pfpn_head_rsample_bwd(C.byref(a), ws.data_ptr(), ws.numel(), _stream_ptr()))
     return dlogits, dloc, dlogstd
 
 

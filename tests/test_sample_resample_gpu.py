@@ -107,6 +107,9 @@ def test_rsample_forward_backward(cuda_dev, B, A, P):
     assert rel(smp, sample[0]) < TOL and rel(spre, s_[0]) < TOL
     dl, dc, ds = sampling.rsample_bwd(cu(logits), cu(loc), cu(logstd), cu(g_a), cu(g_u), **ext)
     assert rel(dl, lg.grad) < TOL and rel(dc, lc.grad) < TOL and rel(ds, ls.grad) < TOL
+    # no atomics: the particle gradients are reproducible bit for bit
+    dl2, dc2, ds2 = sampling.rsample_bwd(cu(logits), cu(loc), cu(logstd), cu(g_a), cu(g_u), **ext)
+    assert torch.equal(dc, dc2) and torch.equal(ds, ds2) and torch.equal(dl, dl2)
 
 
 @pytest.mark.parametrize("P", [35, 100, 200])
