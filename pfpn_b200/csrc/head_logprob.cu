@@ -89,6 +89,9 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
   constexpr int GL = 4 * LPR;  // lanes of a 4-row group (a state ends on a group boundary when A % 4 == 0)
   constexpr bool SEG = AT > 0 && (AT % 4 == 0) && GL <= 32;
   constexpr int HPS = SEG ? AT / 4 : 1;  // 4-row groups per state
+  // SIP (scalars in the producer): the otherwise idle producer warp sums a state's row partials, writes lp / ent, evaluates
+  // the PPO surrogate and publishes ONE dL/dlp per state; the compute lanes (72..576 per state) no longer each re-derive it.
+  constexpr bool SIP = SEG;
   const int TS = slots * RPT;
   const int tile_floats = TS * AP;
   const uint32_t mode = KM == 2 ? (uint32_t)PFPN_HEAD_PPO : (KM == 3 ? (uint32_t)PFPN_HEAD_GRAD : kp.a.mode);
@@ -114,15 +117,18 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
   unsigned char* tail = smem_raw + (size_t)NSTAGE * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* cta_bar = full_bar + NSTAGE;                            // split-phase CTA barrier
-  float2* rowbuf = reinterpret_cast<float2*>(tail + 8 * (NSTAGE + 1));  // [3][TS*A]
-  float* lossbuf = reinterpret_cast<float*>(rowbuf + 3 * TS * A);       // [kHeadMaxWarps]
-  float* dummy = lossbuf + kHeadMaxWarps;                           // [LPR*EPL] sink for masked rows
+  uint64_t* g_bar = cta_bar + 1;                                    // SIP: producer -> compute, per-state dL/dlp ready
+  float2* rowbuf = reinterpret_cast<float2*>(tail + 8 * (NSTAGE + 2));  // [NSTAGE][TS*A] per-row (log p, H) partials
+  float* lossbuf = reinterpret_cast<float*>(rowbuf + NSTAGE * TS * A);  // [kHeadMaxWarps]
+  float* gbuf = lossbuf + kHeadMaxWarps;                            // [NSTAGE][TS] per-state dL/dlp (SIP), 256 floats
+  float* dummy = gbuf + 256;                                        // [LPR*EPL] sink for masked rows
   float2* cs = reinterpret_cast<float2*>(dummy + LPR * EPL + ((LPR * EPL) & 1));  // CSM: [EP2*3][A*LPR]
 
   if (is_producer && lane == 0) {  // the thread that also issues the first loads below, before anyone else is ready
 #pragma unroll
     for (int s = 0; s < NSTAGE; ++s) mbar_init(smem_u32(&full_bar[s]), 1);
     mbar_init(smem_u32(cta_bar), (uint32_t)nthr);
+    mbar_init(smem_u32(g_bar), 1);
     mbar_fence_init();
   }
   // programmatic dependent launch: everything above overlaps the tail of the previous kernel on the stream
@@ -238,6 +244,45 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
         issue_load(it + DIST);
       }
       __syncwarp();
+      if (SIP) {
+        // ---- per-state scalars of tile it-1 (its row partials are complete: that is what the barrier phase says) ----
+        const int pit = it - 1;
+        const int pb0 = (first_tile + pit * tile_step) * TS;
+        if (lane < TS) {
+          const int jj = lane / slots, sl = lane - jj * slots;
+          const float2* hb = rowbuf + (pit % NSTAGE) * TS * A + jj * (MAXT / GL + 1) + sl * HPS;
+          float lp = 0.f, en = 0.f;
+#pragma unroll
+          for (int h = 0; h < HPS; ++h) {
+            const float2 r = hb[h];
+            lp += r.x;
+            en += r.y;
+          }
+          const int b = pb0 + lane;
+          float g = 0.f;
+          if (b < B) {
+            kp.a.lp[b] = lp;
+            if (kp.a.ent != nullptr) kp.a.ent[b] = en;
+            if (BWD) {
+              if (mode == PFPN_HEAD_PPO) {
+                const float an = (__ldg(&kp.a.adv[b]) - adv_mean) * adv_rstd;
+                const float ratio = ex2f((lp - __ldg(&kp.a.lp_old[b])) * kLog2e);
+                const float surr = ratio * an;
+                const float clipped = fminf(fmaxf(ratio, 1.f - eps_clip), 1.f + eps_clip) * an;
+                loss_acc -= fminf(surr, clipped) * loss_scale;
+                g = (surr <= clipped) ? -loss_scale * ratio * an : 0.f;  // TF Minimum: ties -> x
+              } else {
+                g = __ldg(&kp.a.g_lp[b]);
+              }
+            }
+          }
+          if (BWD) gbuf[(pit % NSTAGE) * TS + lane] = g;
+        }
+        if (BWD) {
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(g_bar)) : "memory");
+        }
+      }
     }
   }
 
@@ -256,7 +301,7 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
       const int b = tile * TS + j * slots + slot;
       const bool ok = it < my_tiles && active && b < B;
       v_nxt[j] = (!VAL_TMA && ok) ? __ldg(&g_value[(size_t)b * A + a]) : 0.f;
-      if (BWD) {
+      if (BWD && !SIP) {
         if (mode == PFPN_HEAD_PPO) {
           sc0_nxt[j] = ok ? __ldg(&kp.a.adv[b]) : 0.f;
           sc1_nxt[j] = ok ? __ldg(&kp.a.lp_old[b]) : 0.f;
@@ -264,6 +309,8 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
           sc0_nxt[j] = ok ? __ldg(&kp.a.g_lp[b]) : 0.f;
           sc1_nxt[j] = 0.f;
         }
+      } else {
+        sc0_nxt[j] = sc1_nxt[j] = 0.f;
       }
     }
   };
@@ -318,7 +365,7 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
         }
       }
 
-      float2* rb = rowbuf + (it % 3) * TS * A;
+      float2* rb = rowbuf + (it % NSTAGE) * TS * A;
 #pragma unroll
       for (int j = 0; j < RPT; ++j) {
         const bool row_ok = active && (b0 + j * slots + slot < B);
@@ -398,18 +445,25 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
       const int st = pit % NSTAGE;
       float* sbuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(stage_base) + (size_t)st * stage_bytes);
       const int b0 = tile * TS;
-      const float2* rb = rowbuf + (pit % 3) * TS * A;
+      const float2* rb = rowbuf + (pit % NSTAGE) * TS * A;
 
-      mbar_wait(cta_bar_a, (uint32_t)(pit & 1));  // every compute thread finished iteration it-1
+      if (SIP && BWD) {
+        mbar_wait(smem_u32(g_bar), (uint32_t)(pit & 1));  // the producer published dL/dlp of tile it-1
+      } else {  // (forward: keeps the compute warps within one step of each other and of the producer)
+        mbar_wait(cta_bar_a, (uint32_t)(pit & 1));  // every compute thread finished iteration it-1
+      }
 
 #pragma unroll
       for (int j = 0; j < RPT; ++j) {
         const int sidx = j * slots + slot;
         const int b = b0 + sidx;
         const bool row_ok = active && (b < B);
+        if (SIP && !BWD) continue;
         // ---- log_prob of the state: sum over a of the per-row log p
         float lp = 0.f, en = 0.f;
-        if (SEG) {
+        if (SIP) {
+          // (done by the producer warp)
+        } else if (SEG) {
           const float2* hb = rb + j * (MAXT / GL + 1) + slot * HPS;
 #pragma unroll
           for (int h = 0; h < HPS; ++h) {
@@ -428,7 +482,7 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
           lp = row_sum<LPR>(lp);
           en = row_sum<LPR>(en);
         }
-        if (writer && row_ok) {
+        if (!SIP && writer && row_ok) {
           kp.a.lp[b] = lp;
           if (kp.a.ent != nullptr) kp.a.ent[b] = en;
         }
@@ -436,7 +490,9 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
 
         float g;
         const float sc0v = od.sc0_c[j];
-        if (mode == PFPN_HEAD_PPO) {
+        if (SIP) {
+          g = gbuf[(pit % NSTAGE) * TS + sidx];
+        } else if (mode == PFPN_HEAD_PPO) {
           const float sc1v = od.sc1_c[j];
           const float an = (sc0v - adv_mean) * adv_rstd;
           const float ratio = ex2f((lp - sc1v) * kLog2e);
@@ -596,7 +652,7 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
   if (is_producer && lane == 0) bulk_wait_read<0>();  // every bulk group was issued by this lane
   if (BWD) {
     // loss terms live in the writer threads; fixed-order two-level sum
-    const float wl = row_sum<32>(is_producer ? 0.f : loss_acc);
+    const float wl = row_sum<32>((is_producer && !SIP) ? 0.f : loss_acc);  // SIP: the producer lanes hold the loss terms
     if (lane == 0) lossbuf[warp] = wl;
     __syncthreads();  // all bulk reads of smem done (the producer waited) before reuse
     float* red = stage_base;  // [slots][2][AP]
@@ -623,7 +679,7 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
     }
     if (tid == 0) {
       float s = 0.f;
-      for (int w = 0; w < nwarps; ++w) s += lossbuf[w];
+      for (int w = 0; w <= nwarps; ++w) s += lossbuf[w];  // (entry nwarps = the producer warp: the SIP loss terms)
       kp.loss_part[blockIdx.x] = s;
     }
   }
@@ -803,7 +859,7 @@ static int plan_head(int A, int P, int km, HeadLaunch* L) {
   L->ts = slots * v.rpt;
   L->threads = ((slots * per_slot + 31) & ~31) + 32;  // + the TMA producer warp
   const int stage_bytes = (L->ts * A * P * 4 + L->ts * A * 4 + 127) & ~127;  // logits tile + its action values
-  L->smem_bytes = v.nstage * stage_bytes + 8 * (v.nstage + 1) + 3 * L->ts * A * 8 + kHeadMaxWarps * 4 +
+  L->smem_bytes = v.nstage * stage_bytes + 8 * (v.nstage + 2) + v.nstage * L->ts * A * 8 + (kHeadMaxWarps + 256) * 4 +
                   (v.lpr * v.epl + 1) * 4 + 16 + ((v.csm & 1) ? ((v.epl + 1) / 2) * 3 * per_slot * 8 : 0);
   L->fn = v.fn[km];
   int dev = 0;
