@@ -36,3 +36,31 @@ def test_head_args_layout_matches_header():
     assert _cabi.HeadArgs.eps_clip.offset == 80 and _cabi.HeadArgs.loss_scale.offset == 84
     assert _cabi.HeadArgs.lp.offset == 88 and _cabi.HeadArgs.loss.offset == 144
     assert _cabi.HeadArgs.B.offset == 152 and C.sizeof(_cabi.HeadArgs) == 176
+
+
+def test_every_header_function_has_a_ctypes_signature():
+    """The host mirror binds the whole boundary: each function of include/pfpn_b200.h has a typed ctypes entry."""
+    missing = []
+    for n in _cabi.exported_symbols():
+        f = getattr(_cabi, n, None)
+        if f is None or getattr(f, "argtypes", None) is None:
+            missing.append(n)
+    assert missing == []
+
+
+def test_other_struct_layouts_match_the_static_asserts_of_capi_cu():
+    assert C.sizeof(_cabi.SampleArgs) == 88 and C.sizeof(_cabi.RSampleArgs) == 136 and C.sizeof(_cabi.ResampleArgs) == 200
+
+
+def test_argument_errors_of_the_widened_entry_points_without_gpu():
+    n = C.c_size_t(0)
+    assert _cabi.pfpn_gae(None, None, None, None, 4, 8, 0.99, 0.94, None) == -1
+    assert _cabi.pfpn_axpby(None, None, 16, 0.5, 0.5, None) == -1
+    assert _cabi.pfpn_sac_losses(*([None] * 11), 0.95, 0.5, -36.0, 8, *([None] * 6), None) == -1
+    assert _cabi.pfpn_stats_workspace_bytes(4096, 36, 35, C.byref(n)) == 0 and n.value > 0
+    assert _cabi.pfpn_stats_update(None, None, None, None, 8, 36, 35, None, 0, None) == -1
+    assert _cabi.pfpn_rsample_bwd_workspace_bytes(4096, 36, 100, C.byref(n)) == 0 and n.value >= 592 * 2 * 3600 * 4
+    assert _cabi.pfpn_tc_wgrad_workspace_bytes(65536, 1024, 512, C.byref(n)) == 0 and n.value >= 32 * (1024 * 512 + 512) * 4
+    assert _cabi.pfpn_tc_wgrad_workspace_bytes(8192, 512, 128, C.byref(n)) == 0  # small batch: finer split-K, larger scratch per row
+    assert n.value >= 8 * (512 * 128 + 128) * 4
+    assert _cabi.pfpn_peer_allreduce_sum(None, None, 0, 2, 1, 16, None, 1.0, None) == -1
