@@ -154,3 +154,37 @@ class SyncReplicasAdam:
         self.step = int(sd["step"])
         if sd["m"] is not None:
             self.m, self.v = sd["m"].clone(), sd["v"].clone()
+
+
+# ---- a20: the on-policy training loop over one rollout (models/distributed_model.py:320-345) ---------------------------
+def minibatch_indices(n: int, batch_size, opt_epochs: int, rng):
+    """Index arrays of the minibatches `flat_train` feeds, in order: per epoch ONE `shuffle` of arange(n) (re-shuffling the
+    previous permutation, as the reference does), then contiguous slices of `batch_size` (the last one may be short);
+    `batch_size` falsy -> the whole permutation as one batch.  `rng` is a numpy RandomState (the reference uses the
+    process-global one, seeded per worker in distributed_model.py:568)."""
+    import numpy as np
+    ids = np.arange(n)
+    for _ in range(opt_epochs):
+        rng.shuffle(ids)
+        if batch_size:
+            for s in range(0, n, batch_size):
+                yield ids[s:s + batch_size].copy()
+        else:
+            yield ids.copy()
+
+
+def flat_train(net, optimizer, exp: dict, batch_size, opt_epochs: int, rng):
+    """`AbstractDistributedWorker.flat_train`, on-policy branch, on device-resident rollout tensors: exp holds
+    state [n,S], action [n,A], value [n], log_prob [n], advantage [n] (the PPO worker's `train_args`, workers/ppo.py:43-73).
+    Every rank runs this over ITS OWN rollout, exactly like a reference worker; the optimizer aggregates.
+    Returns the list of (loss, entropy, policy_loss, value_loss) device scalars, one per minibatch."""
+    keys = ("state", "action", "value", "log_prob", "advantage")
+    dev = net.device
+    data = {k: torch.as_tensor(exp[k], dtype=torch.float32).to(dev) for k in keys}
+    n = data["state"].shape[0]
+    out = []
+    for ids in minibatch_indices(n, batch_size, opt_epochs, rng):
+        sel = torch.as_tensor(ids, dtype=torch.long, device=dev)
+        out.append(net.compute_gradients(*(data[k].index_select(0, sel) for k in keys)))
+        optimizer.apply_gradients(net)
+    return out

@@ -81,3 +81,28 @@ def test_two_rank_bucket_allreduce_equals_sync_replicas_emulation():
     acc, nm, ns, _ = on.sync_update({k: t.clone() for k, t in p.items()}, m, v, 1, shards, mean, std, A, P)
     ref = torch.cat([acc[k].reshape(-1) for k in keys] + [nm, ns])
     assert torch.allclose(bucket, ref, rtol=1e-12, atol=1e-14)
+
+
+def test_minibatch_indices_equal_the_reference_flat_train_loop():
+    """a20: same shuffles, same slices, same order as models/distributed_model.py:320-345 for the same RandomState."""
+    import numpy as np
+    from pfpn_b200.learner import minibatch_indices
+
+    def reference_loop(n, batch_size, opt_epochs, rng):  # literal restatement of the on-policy branch
+        ids = np.arange(n)
+        out, epoch = [], 0
+        while epoch < opt_epochs:
+            rng.shuffle(ids)
+            if batch_size:
+                for s in range(0, n, batch_size):
+                    out.append(ids[s:s + batch_size].copy())
+            else:
+                out.append(ids[ids >= 0].copy())
+            epoch += 1
+        return out
+
+    for n, bs, ep in ((368, 32, 5), (100, 32, 3), (10, None, 2), (7, 7, 1), (5, 8, 2)):
+        a = list(minibatch_indices(n, bs, ep, np.random.RandomState(28949)))
+        b = reference_loop(n, bs, ep, np.random.RandomState(28949))
+        assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
+        assert sum(len(x) for x in a) == n * ep

@@ -148,3 +148,27 @@ def test_resample_tick_fires_at_interval_and_is_replica_deterministic(cuda_dev):
             fired.append(net.update())
         assert fired == [False, False, True] and net.train_flag == 0 and not net.max_active.any()
     assert torch.equal(nets[0].params, nets[1].params)
+
+
+def test_flat_train_runs_the_reference_minibatch_schedule(cuda_dev):
+    """a20: flat_train == looping compute_gradients/apply_gradients over the reference's shuffled slices."""
+    import numpy as np
+    from pfpn_b200.learner import SyncReplicasAdam, flat_train, minibatch_indices
+    from pfpn_b200.network import ParticleFilteringClipPPONetwork
+    S, A, P, n = 197, 36, 35, 96
+
+    def make():
+        return ParticleFilteringClipPPONetwork(True, [S], [A], action_lower_bound=[-1.] * A, action_upper_bound=[1.] * A, particles=P,
+                                               resample=-1, resample_interval=368, normalize_state=True, clip_state=5.0,
+                                               normalize_advantage=True, device=cuda_dev, seed=3).init()
+    g = torch.Generator().manual_seed(0)
+    exp = dict(state=torch.randn(n, S, generator=g), action=torch.rand(n, A, generator=g) * 2 - 1, value=torch.randn(n, generator=g),
+               log_prob=torch.randn(n, generator=g) * 0.1 - 30, advantage=torch.randn(n, generator=g))
+    n1, n2 = make(), make()
+    losses = flat_train(n1, SyncReplicasAdam(lr=1e-4, norm_clip=1.0), exp, 32, 2, np.random.RandomState(5))
+    assert len(losses) == 6 and all(np.isfinite(float(l[0])) for l in losses) and n1.global_step == 6
+    opt = SyncReplicasAdam(lr=1e-4, norm_clip=1.0)
+    for ids in minibatch_indices(n, 32, 2, np.random.RandomState(5)):
+        n2.compute_gradients(*(exp[k][ids] for k in ("state", "action", "value", "log_prob", "advantage")))
+        opt.apply_gradients(n2)
+    assert torch.equal(n1.params, n2.params) and torch.equal(n1.state_mean, n2.state_mean)
