@@ -42,7 +42,9 @@ def ppo_losses(p, state, action, value_old, lp_old, adv, mean, std, A, P, *, eps
     B = state.shape[0]
     dist = oh.MixtureGaussianOracle(logits.reshape(B, A, P), p["global_net/actor/samples"],
                                     torch.exp(p["global_net/actor/samples_std"]), tanh)
-    lp = dist.log_prob((torch.tanh(action), action) if tanh else action)
+    # `action` is the stored action_hist; with normalize_output the reference's log_prob receives it as a plain
+    # tensor and applies atanh itself (utils.py:120-126)
+    lp = dist.log_prob(action)
     adv_n = oh.normalize_advantage(adv).detach() if normalize_adv else adv
     policy_loss = oh.ppo_policy_loss(lp, lp_old, adv_n, eps)
     entropy = None
@@ -50,7 +52,8 @@ def ppo_losses(p, state, action, value_old, lp_old, adv, mean, std, A, P, *, eps
         entropy = torch.mean(torch.sum(dist.entropy(), dim=1))
         policy_loss = policy_loss - entropy_beta * entropy
     value_loss = torch.mean(torch.square(v - (adv + value_old).detach()))  # ppo.py:31-42
-    loss = policy_loss + value_loss_coef * value_loss
+    value_loss = value_loss_coef * value_loss  # actor_critic.py:131-133: self.value_loss *= value_loss_coef (what train() returns)
+    loss = policy_loss + value_loss
     return loss, entropy, policy_loss, value_loss
 
 

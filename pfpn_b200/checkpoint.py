@@ -113,24 +113,35 @@ def _encode_entry(e: BundleEntry) -> bytes:
 
 
 # ---- crc32c (Castagnoli), masked as leveldb / TF store it ---------------------------------------------------------
-def _make_crc_table():
-    tbl = []
+def _make_crc_tables():
+    """Slice-by-8 tables: T[0] is the byte-wise table, T[k][n] = crc of byte n followed by k zero bytes."""
+    t0 = []
     for n in range(256):
         c = n
         for _ in range(8):
             c = (c >> 1) ^ 0x82F63B78 if c & 1 else c >> 1
-        tbl.append(c)
-    return np.array(tbl, dtype=np.uint32)
+        t0.append(c)
+    tabs = [t0]
+    for _ in range(7):
+        prev = tabs[-1]
+        tabs.append([(prev[n] >> 8) ^ t0[prev[n] & 0xFF] for n in range(256)])
+    return tabs
 
 
-_CRC_TABLE = _make_crc_table()
+_CRC_TABLES = _make_crc_tables()
 
 
 def crc32c(data: bytes) -> int:
+    """Castagnoli CRC, slice-by-8 (one Python iteration per 8 bytes; ~6 MB bundles in well under a second)."""
+    t0, t1, t2, t3, t4, t5, t6, t7 = _CRC_TABLES
     c = 0xFFFFFFFF
-    tbl = _CRC_TABLE
-    for byte in data:
-        c = int(tbl[(c ^ byte) & 0xFF]) ^ (c >> 8)
+    n8 = len(data) & ~7
+    for (q,) in struct.iter_unpack("<Q", memoryview(data)[:n8]):
+        q ^= c
+        c = (t7[q & 0xFF] ^ t6[(q >> 8) & 0xFF] ^ t5[(q >> 16) & 0xFF] ^ t4[(q >> 24) & 0xFF] ^
+             t3[(q >> 32) & 0xFF] ^ t2[(q >> 40) & 0xFF] ^ t1[(q >> 48) & 0xFF] ^ t0[q >> 56])
+    for byte in memoryview(data)[n8:]:
+        c = t0[(c ^ byte) & 0xFF] ^ (c >> 8)
     return c ^ 0xFFFFFFFF
 
 

@@ -18,9 +18,10 @@
 //    registers for the whole kernel because a thread's (a, k-set) never changes;
 //  * element math is packed fp32x2 (FFMA2/FMUL2/FADD2) with 2 MUFU.EX2 per
 //    particle; everything is computed in the log2 domain;
-//  * sum over a (log_prob of the state) goes through a tiny smem exchange; every
-//    lane re-derives the state's sum and the PPO dL/dlp redundantly, so there is
-//    exactly ONE block barrier per tile.
+//  * sum over a (log_prob of the state) goes through 4-row group partials in shared memory; the
+//    otherwise idle TMA producer warp sums them per state, writes lp / ent, evaluates the PPO
+//    surrogate and publishes ONE dL/dlp per state through an mbarrier (SIP) -- there is no
+//    block-wide barrier in the steady state.
 #include <stdlib.h>
 
 #include "common.cuh"

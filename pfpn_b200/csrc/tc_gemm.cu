@@ -11,7 +11,7 @@
 // hi*hi + hi*lo + lo*hi  (relative error ~2^-21 per product, fp32 accumulation in TMEM).
 //
 // CTA = 8 warps, one 128x128 output tile, K in blocks of 32 floats (= one 128-byte swizzle atom):
-//   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B) of A and B into a 3-stage ring
+//   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B) of A and B into a TC_STAGES-deep ring
 //   warp 1      single-thread tcgen05.mma issuer (kind::tf32, M=128, N=128, K=8), tcgen05.commit
 //   warp 2      TMEM allocator (all 512 columns: two alternating main accumulators + one correction)
 //   warps 4-7   splitter: thread m moves row m of the landed A tile into TENSOR MEMORY as (hi, lo) with

@@ -47,6 +47,22 @@ def allreduce_mean_(bucket: torch.Tensor, group=None) -> float:
     return 1.0 / n
 
 
+def assert_replicas_identical(params: torch.Tensor, group=None, what: str = "parameters"):
+    """There is no parameter broadcast on this path (every rank applies the identical Adam step to identical weights), so
+    the replicas must START identical: raise if the ranks were built with different seeds / checkpoints.  Compares a 64-bit
+    checksum of the raw fp32 bits; a no-op for a single process."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2:
+        return
+    bits = params.detach().contiguous().view(torch.int32).to(torch.int64)
+    w = torch.arange(1, bits.numel() + 1, device=bits.device, dtype=torch.int64)
+    h = torch.stack([bits.sum(), (bits * (w % 65521)).sum()])
+    hs = [torch.empty_like(h) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(hs, h, group=group)
+    if any(not torch.equal(x, hs[0]) for x in hs):
+        raise RuntimeError(f"data-parallel replicas hold different {what}: construct every rank's network with the same "
+                           "`seed` (the per-rank sampling stream is derived from the rank automatically) or load the same checkpoint")
+
+
 class SyncReplicasAdam:
     """`SyncReplicasOptimizer(AdamOptimizer(lr), replicas_to_aggregate=N)` + clip_grads, for one
     network whose parameters / gradients are flat buffers (pfpn_b200.network)."""
@@ -70,6 +86,7 @@ class SyncReplicasAdam:
         if self.m is None:
             self.m = torch.zeros_like(net.params)
             self.v = torch.zeros_like(net.params)
+            assert_replicas_identical(net.params, self.group)
         if self.norm_scale is None:
             self.norm_scale = torch.zeros(2, dtype=torch.float32, device=net.params.device)
             self._scratch = torch.empty(296 * 8, dtype=torch.uint8, device=net.params.device)
@@ -105,6 +122,9 @@ class SyncReplicasAdam:
         self.pack_stats(net)
         if self.fused_peer and world()[1] > 1 and net.params.is_cuda:
             return self._apply_fused_peer(net, st)
+        return self._apply_nccl(net, st)
+
+    def _apply_nccl(self, net, st):
         # 2-4. one all-reduce of [clipped gradients | statistics], mean, assign statistics
         inv_n = allreduce_mean_(net.bucket, self.group)
         self.unpack_stats(net, inv_n)
@@ -121,7 +141,13 @@ class SyncReplicasAdam:
         """Steps 2-5 in one kernel over peer memory: sum in rank order, mean, Adam, averaged statistics."""
         from .peer import PeerBuckets
         if self._peers is None:
-            self._peers = PeerBuckets(net.bucket.numel(), net.params.device, self.group, with_reduced=True)
+            try:
+                self._peers = PeerBuckets(net.bucket.numel(), net.params.device, self.group, with_reduced=True)
+            except (RuntimeError, ValueError) as e:  # collective outcome (peer.py): every rank lands here together
+                import warnings
+                warnings.warn(f"fused peer-memory all-reduce unavailable ({e}); using NCCL all-reduce + Adam")
+                self.fused_peer = False
+                return self._apply_nccl(net, st)
         pb = self._peers
         self.step += 1
         # the exchange protocol counts ITS OWN calls (1, 2, 3, ... since the buffers were created); the Adam

@@ -95,7 +95,11 @@ class ParticleFilteringClipPPONetwork:
         self.entropy_beta, self.value_loss_coef = entropy_beta, value_loss_coef
         self.gamma, self.gae_gamma = gamma, None if lambd is None else gamma * lambd
         self.device = torch.device(device)
+        # `seed` is REPLICATED state: weight / particle initialisation and the resample tick's draws must be identical on
+        # every data-parallel rank (there is no parameter broadcast).  The rollout / SAC sampling draws instead come from a
+        # per-rank Philox stream (`sample_seed`, derived in init() from the rank) so shards do not share their noise.
         self.seed = int(seed)
+        self.sample_seed = int(seed)
         self.init_ops, self.train_ops, self.running_update_ops = [], [], []
         self.local_update_variables: List[torch.Tensor] = []
         self.global_step = self.GLOBAL_STEP0
@@ -107,8 +111,14 @@ class ParticleFilteringClipPPONetwork:
         self.use_tensor_cores = os.environ.get("PFPN_TRUNK", "tc") != "ffma"
 
     # ------------------------------------------------------------------------------ build ----
+    def _derive_sample_stream(self):
+        import torch.distributed as dist
+        rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+        self.sample_seed = (self.seed ^ (0x9E3779B97F4A7C15 * rank)) & 0xFFFFFFFFFFFFFFFF
+
     def init(self):
         S, A, P, dev = self.S, self.A, self.P, self.device
+        self._derive_sample_stream()
         self.Sp = _pad4(S)
         dims_a = [self.Sp] + self.actor_net_shape
         dims_c = [self.Sp] + self.critic_net_shape
@@ -235,11 +245,11 @@ class ParticleFilteringClipPPONetwork:
         logits, _, value, _ = self._forward(s)
         if self.random_action:
             if self.normalize_policy_output_:
-                smp, s_pre, _ = _sampling.rsample_fwd(logits, self.loc, self.logstd, seed=self.seed, offset=self._rng_offset,
+                smp, s_pre, _ = _sampling.rsample_fwd(logits, self.loc, self.logstd, seed=self.sample_seed, offset=self._rng_offset,
                                                       ext_uniform=ext_uniform, ext_normal=ext_normal)
                 action, val = smp, s_pre
             else:
-                action, _ = _sampling.sample_plain(logits, self.loc, self.logstd, seed=self.seed, offset=self._rng_offset,
+                action, _ = _sampling.sample_plain(logits, self.loc, self.logstd, seed=self.sample_seed, offset=self._rng_offset,
                                                    ext_uniform=ext_uniform, ext_normal=ext_normal)
                 val = action
             self._rng_offset += 2
@@ -315,7 +325,10 @@ class ParticleFilteringClipPPONetwork:
         logits, acts, v, cacts = self._forward(s)
         stats = _head.adv_stats(adv) if self.normalize_advantage else None
         ent_scale = -float(self.entropy_beta) * scale if self.entropy_beta else 0.0
-        out = _head.head_call(_cabi.HEAD_PPO, logits, self.loc, self.logstd, action, tanh=self.normalize_policy_output_,
+        # action_hist is the stored (tanh'd) action: MixtureGaussianDistribution.log_prob applies atanh to a non-tuple
+        # value when normalize_output (utils.py:120-126); K1 takes the pre-tanh value
+        head_value = torch.atanh(action) if self.normalize_policy_output_ else action
+        out = _head.head_call(_cabi.HEAD_PPO, logits, self.loc, self.logstd, head_value, tanh=self.normalize_policy_output_,
                               adv=adv, lp_old=lp_old, adv_stats_t=stats, eps_clip=self.epsilon, loss_scale=scale,
                               g_ent=ent_scale, dlogits_out=logits,
                               out=dict(dloc=self.dloc, dlogstd=self.dlogstd, lp=self._buf("lp", B), ent=self._buf("ent", B),
@@ -331,8 +344,9 @@ class ParticleFilteringClipPPONetwork:
         if self.entropy_beta:
             entropy = out["ent"].sum() * scale
             policy_loss = policy_loss - self.entropy_beta * entropy
-        loss = policy_loss + self.value_loss_coef * vloss[0]
-        return loss, entropy, policy_loss, vloss[0]
+        value_loss = self.value_loss_coef * vloss[0]  # actor_critic.py:131-133: the returned value_loss is the weighted one
+        loss = policy_loss + value_loss
+        return loss, entropy, policy_loss, value_loss
 
     def _backward_stack(self, layers: Sequence[_Linear], acts, dY):
         """acts[i] is the input of layers[i]; dY is dL/d(output of the last layer)."""

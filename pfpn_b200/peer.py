@@ -42,6 +42,7 @@ class PeerBuckets:
             gathered: List = [None] * self.world
             dist.all_gather_object(gathered, (h_stage, h_flag, h_red), group=group)
             stage_ptrs, flag_ptrs, red_ptrs = [], [], []
+            err = None
             for r, (hs, hf, hr) in enumerate(gathered):
                 if r == self.rank:
                     stage_ptrs.append(self._stage_ptr)
@@ -49,12 +50,22 @@ class PeerBuckets:
                     red_ptrs.append(self._red_ptr)
                     continue
                 ps, pf, pr = C.c_void_p(), C.c_void_p(), C.c_void_p()
-                _cabi.check(_cabi.pfpn_peer_open(hs, C.byref(ps)))
-                _cabi.check(_cabi.pfpn_peer_open(hf, C.byref(pf)))
-                _cabi.check(_cabi.pfpn_peer_open(hr, C.byref(pr)))
-                stage_ptrs.append(ps.value)
-                flag_ptrs.append(pf.value)
-                red_ptrs.append(pr.value)
+                try:  # (a peer on another host / without P2P: cudaIpcOpenMemHandle fails on THIS rank only)
+                    _cabi.check(_cabi.pfpn_peer_open(hs, C.byref(ps)))
+                    _cabi.check(_cabi.pfpn_peer_open(hf, C.byref(pf)))
+                    _cabi.check(_cabi.pfpn_peer_open(hr, C.byref(pr)))
+                except Exception as e:  # noqa: BLE001 -- reported collectively below
+                    err = e
+                stage_ptrs.append(ps.value or 0)
+                flag_ptrs.append(pf.value or 0)
+                red_ptrs.append(pr.value or 0)
+            # the outcome must be COLLECTIVE: either every rank maps every peer or every rank raises (and the caller
+            # falls back to the NCCL path on all ranks together)
+            ok = torch.tensor([0 if err is not None else 1], device=device, dtype=torch.int32)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                raise RuntimeError(f"peer-memory mapping failed on at least one rank ({err!r}): CUDA IPC + P2P need all "
+                                   "ranks on one NVLink/NVSwitch node")
         dist.barrier(group=group)
         self._flag_ptrs = (C.c_void_p * self.world)(*flag_ptrs)
         self.calls = 0  # exchange calls issued on these buffers (flag value / buffer parity / CTA-counter epoch)

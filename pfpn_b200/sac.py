@@ -29,7 +29,7 @@ import torch
 from . import _cabi
 from .distribution import MixtureGaussianDistribution
 from .head import _stream_ptr
-from .learner import SyncReplicasAdam
+from .learner import SyncReplicasAdam, assert_replicas_identical
 from .network import ParticleFilteringClipPPONetwork, _Linear, _pad4
 
 
@@ -43,6 +43,7 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
     # ------------------------------------------------------------------------------ build ----
     def init(self):
         S, A, P, dev = self.S, self.A, self.P, self.device
+        self._derive_sample_stream()
         self.Sp, self.QI = _pad4(S), _pad4(S + A)
         dims_a = [self.Sp] + self.actor_net_shape
         self.actor = [_Linear(f"actor/fc{i+1}", (S if i == 0 else dims_a[i]), dims_a[i + 1], dims_a[i])
@@ -186,7 +187,7 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
             lg = lg.detach().requires_grad_(True)
             loc, ls = loc.detach().requires_grad_(True), ls.detach().requires_grad_(True)
         dist = MixtureGaussianDistribution(lg, loc, torch.exp(ls.detach()), True, logstd=ls)
-        kw = dict(ext_uniform=ext[0], ext_normal=ext[1]) if ext is not None else dict(seed=self.seed, offset=seed_offset)
+        kw = dict(ext_uniform=ext[0], ext_normal=ext[1]) if ext is not None else dict(seed=self.sample_seed, offset=seed_offset)
         smp, s_ = dist.sample(1, **kw)
         logp = dist.log_prob((smp[0], s_[0]))
         return smp[0], logp, (lg, loc, ls)
@@ -322,6 +323,7 @@ class SACOptimizer:
             self.m, self.v = torch.zeros_like(net.params), torch.zeros_like(net.params)
             self.norm_scale = torch.zeros(2, dtype=torch.float32, device=net.params.device)
             self._scratch = torch.empty(296, dtype=torch.float64, device=net.params.device)
+            assert_replicas_identical(net.params, self.group)
         _cabi.check(_cabi.pfpn_clip_by_global_norm(net.grads.data_ptr(), net.n_params, self.norm_clip, self.norm_scale.data_ptr(),
                                                    self._scratch.data_ptr(), self._scratch.numel() * 8, st))
         # statistics pushed through the same accumulators as the gradients (normaliser moments of this minibatch and the

@@ -30,6 +30,13 @@ def _batch(B, S, A, g):
                 log_prob=r(B) * 0.1 + 4.0, advantage=r(B))
 
 
+def _free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -64,7 +71,7 @@ def test_two_rank_bucket_allreduce_equals_sync_replicas_emulation():
     assert [shard_bounds(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
+    port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     [p.start() for p in procs]
     keys, bucket, lo, hi = q.get(timeout=120)
@@ -106,3 +113,123 @@ def test_minibatch_indices_equal_the_reference_flat_train_loop():
         b = reference_loop(n, bs, ep, np.random.RandomState(28949))
         assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
         assert sum(len(x) for x in a) == n * ep
+
+
+# ---- SyncReplicasAdam.apply_gradients itself (pack_stats / exchange / unpack_stats / Adam / train_ops) under gloo -------------
+class _HostCabi:
+    """Stands in for the two CUDA entry points apply_gradients calls, on HOST pointers (numpy over ctypes), so the
+    collective host logic of the PRODUCT class runs under gloo without a GPU.  Same semantics as csrc/optim.cu."""
+
+    @staticmethod
+    def _arr(ptr, n):
+        import ctypes as C
+        import numpy as np
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(n,))
+
+    def check(self, status):
+        assert status == 0
+
+    def pfpn_clip_by_global_norm(self, grads, n, clip, norm_scale, scratch, scratch_bytes, st):
+        import numpy as np
+        g, ns = self._arr(grads, n), self._arr(norm_scale, 2)
+        norm = float(np.sqrt(np.sum(g.astype(np.float64) ** 2)))
+        scale = clip * min(1.0 / norm, 1.0 / clip)
+        g *= np.float32(scale)
+        ns[0], ns[1] = norm, scale
+        return 0
+
+    def pfpn_adam_step(self, params, grads, m, v, n, lr, b1, b2, eps, step, grad_scale, st):
+        import math
+        import numpy as np
+        p, g, mm, vv = (self._arr(x, n) for x in (params, grads, m, v))
+        gs = g.astype(np.float64) * grad_scale
+        lr_t = lr * math.sqrt(1 - b2 ** step) / (1 - b1 ** step)
+        m64 = b1 * mm.astype(np.float64) + (1 - b1) * gs
+        v64 = b2 * vv.astype(np.float64) + (1 - b2) * gs * gs
+        mm[:], vv[:] = m64, v64
+        p[:] = p.astype(np.float64) - lr_t * m64 / (np.sqrt(v64) + eps)
+        return 0
+
+
+class _HostNet:
+    """The attributes SyncReplicasAdam touches, with host tensors."""
+
+    def __init__(self, n_params, S, A, P, rank):
+        g = torch.Generator().manual_seed(3)
+        self.n_params, self.S, self.A, self.P, self.normalize_state = n_params, S, A, P, True
+        self.params = torch.randn(n_params, generator=g)
+        self.bucket = torch.zeros(n_params + 2 * S + 2 * A * P)
+        self.grads = self.bucket[:n_params]
+        gr = torch.Generator().manual_seed(100 + rank)
+        self.grads.copy_(torch.randn(n_params, generator=gr) * 3)
+        self._new_mean, self._new_std = torch.randn(S, generator=gr), torch.rand(S, generator=gr) + 0.5
+        self.state_mean, self.state_std = torch.zeros(S), torch.ones(S)
+        self.max_active, self.sum_active = torch.rand(A, P, generator=gr), torch.rand(A, P, generator=gr) * 9
+        self.global_step, self.ticks = 0, 0
+        self.train_ops = [self._tick]
+
+    def _tick(self):
+        self.ticks += 1
+
+
+def _adam_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pfpn_b200 import learner
+    learner._cabi = _HostCabi()
+    learner._stream_ptr = lambda: 0
+    net = _HostNet(64, 5, 2, 4, rank)
+    local = dict(g=net.grads.clone(), mean=net._new_mean.clone(), std=net._new_std.clone(), mx=net.max_active.clone(),
+                 sm=net.sum_active.clone(), p0=net.params.clone())
+    opt = learner.SyncReplicasAdam(lr=1e-3, norm_clip=1.0, fused_peer=False)
+    opt.apply_gradients(net)
+    q.put((rank, local, dict(params=net.params.clone(), mean=net.state_mean.clone(), std=net.state_std.clone(),
+                             mx=net.max_active.clone(), sm=net.sum_active.clone(), step=opt.step, gstep=net.global_step,
+                             ticks=net.ticks, norm=float(opt.norm_scale[0]))))
+    # replicas that start different must be refused (no parameter broadcast on this path)
+    bad = _HostNet(64, 5, 2, 4, rank)
+    bad.params[3] += float(rank)
+    try:
+        learner.SyncReplicasAdam(fused_peer=False).apply_gradients(bad)
+        q.put((rank, "no error", None))
+    except RuntimeError as e:
+        q.put((rank, "refused" if "replicas hold different" in str(e) else repr(e), None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sync_replicas_adam_apply_gradients_two_ranks_gloo():
+    """The product's SyncReplicasAdam (NCCL-path code, here over gloo): local clip BEFORE aggregation, mean of the clipped
+    gradients and of the four pushed statistics (max_active averaged, not max-reduced: sync_model.py:92-96), identical Adam on
+    both ranks, train_ops chained after the step."""
+    import math
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_adam_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = [q.get(timeout=120) for _ in range(4)]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    res = {r: (loc, out) for r, loc, out in got if isinstance(loc, dict)}
+    refusals = [loc for _, loc, out in got if not isinstance(loc, dict)]
+    assert refusals == ["refused", "refused"]
+    clipped = []
+    for r in range(2):
+        g = res[r][0]["g"].double()
+        norm = float(g.norm())
+        assert abs(res[r][1]["norm"] - norm) < 1e-4 * norm
+        clipped.append(g * min(1.0 / norm, 1.0))
+    gm = (clipped[0] + clipped[1]) / 2
+    lr_t = 1e-3 * math.sqrt(1 - 0.999) / (1 - 0.9)
+    m, v = 0.1 * gm, 0.001 * gm * gm
+    p_ref = res[0][0]["p0"].double() - lr_t * m / (v.sqrt() + 1e-8)
+    for r in range(2):
+        out = res[r][1]
+        assert torch.allclose(out["params"].double(), p_ref, rtol=1e-5, atol=1e-6)
+        for key, loc_key in (("mean", "mean"), ("std", "std"), ("mx", "mx"), ("sm", "sm")):
+            want = (res[0][0][loc_key] + res[1][0][loc_key]) / 2
+            assert torch.allclose(out[key], want, rtol=1e-6, atol=1e-7), key
+        assert out["step"] == 1 and out["gstep"] == 1 and out["ticks"] == 1
+    assert torch.equal(res[0][1]["params"], res[1][1]["params"])  # replicas bit-identical

@@ -210,3 +210,18 @@ def test_kernel_resampler_matches_reference_source(cuda_dev, name):
     for k in ("loc", "logstd", "bias", "weight"):
         assert np.allclose(g[k].cpu().numpy(), c["out_" + k], rtol=1e-5, atol=1e-6), k
     assert not g["max_active"].any() and not g["sum_active"].any()
+
+
+def test_product_particle_grid_matches_reference_source():
+    """a8: the PRODUCT's initialiser (pfpn_b200.network.initial_particles, what ParticleFilteringClipPPONetwork.init
+    writes into `samples` / `samples_std`) against ParticleFilteringA2CNetwork.build_policy executed from source
+    (a2c.py:476-535), both grids."""
+    from pfpn_b200.network import initial_particles
+    for tanh in (0, 1):
+        c = case(f"build_policy_tanh{tanh}")
+        A, P = c["loc"].shape
+        loc, logstd = initial_particles(A, P, bool(tanh))
+        assert loc.dtype == torch.float32 and tuple(loc.shape) == (A, P) and tuple(logstd.shape) == (A, P)
+        assert np.abs(loc.numpy().astype(np.float64) - c["loc"]).max() <= 2e-7 * max(1.0, np.abs(c["loc"]).max())
+        assert np.abs(logstd.numpy().astype(np.float64) - c["logstd"]).max() <= 2e-7 * np.abs(c["logstd"]).max()
+        assert np.abs(np.exp(logstd.numpy().astype(np.float64)) - c["scale"]).max() <= 1e-6 * np.abs(c["scale"]).max()

@@ -172,3 +172,90 @@ def test_flat_train_runs_the_reference_minibatch_schedule(cuda_dev):
         n2.compute_gradients(*(exp[k][ids] for k in ("state", "action", "value", "log_prob", "advantage")))
         opt.apply_gradients(n2)
     assert torch.equal(n1.params, n2.params) and torch.equal(n1.state_mean, n2.state_mean)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# f3: vectorised rollout inference `run_batch` (ppo.py:56-62 -> actor_critic.py:368-380 -> a2c.py:225-243, 346-365)
+# against the oracle with EXTERNAL draws: trunk + value vs oracle/network.forward, particle index bit-exact and
+# action / log_prob vs MixtureGaussianOracle.sample / log_prob, activity statistics vs softmax max / sum over the batch.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tanh", [False, True])
+def test_run_batch_matches_oracle_with_external_draws(cuda_dev, tanh):
+    from oracle import head as oh
+    B, S, A, P = 300, 197, 36, 35
+    net = build(cuda_dev, normalize_policy_output=tanh)
+    g = torch.Generator().manual_seed(11)
+    state = torch.randn(B, S, generator=g) * 1.5 + 0.3
+    normal = torch.randn(B, A, P, generator=g)
+    if tanh:
+        tiny = float(np.finfo(np.float32).tiny)
+        uniform = torch.rand(B, A, P, generator=g).clamp_min(tiny)
+    else:
+        uniform = torch.rand(B, A, generator=g, dtype=torch.float64)
+    p0 = oracle_params(net)
+    mean, std = net.state_mean.double().cpu(), net.state_std.double().cpu()
+    max0 = torch.rand(A, P, generator=g) * 0.05
+    sum0 = torch.rand(A, P, generator=g)
+    net.max_active.copy_(max0)
+    net.sum_active.copy_(sum0)
+    action, lp, value = net.run_batch(state, ext_uniform=uniform.to(cuda_dev), ext_normal=normal.to(cuda_dev))
+    # 1. trunk: logits and value against the fp64 forward
+    logits_ref, v_ref = on.forward(p0, state.double(), mean, std)
+    logits_gpu = net._act["logits"].detach().cpu().reshape(B, A, P)
+    assert rel(logits_gpu, logits_ref.reshape(B, A, P)) < TOL
+    assert rel(value, v_ref) < TOL
+    # 2. sampling + log_prob on the logits the kernels saw (the fp32 logits decide the particle index)
+    loc, scale = p0["global_net/actor/samples"], p0["global_net/actor/samples_std"].exp()
+    dist = oh.MixtureGaussianOracle(logits_gpu.double(), loc, scale, tanh)
+    if tanh:
+        smp, s_ = dist.sample(1, uniform=uniform.double(), normal=normal.double())
+        act_ref, lp_ref = smp[0], dist.log_prob((smp[0], s_[0]))
+    else:
+        act_ref = dist.sample(1, uniform=uniform.numpy(), normal=normal.double())[0]
+        lp_ref = dist.log_prob(act_ref)
+    assert rel(action, act_ref) < TOL
+    assert rel(lp, lp_ref) < TOL
+    # 3. running_update_ops (a2c.py:346-365): max_active = max(max_active, max_b probs), sum_active += sum_b probs
+    probs = oh.tf_softmax(logits_gpu.double())
+    assert rel(net.max_active, torch.maximum(max0.double(), probs.amax(0))) < TOL
+    assert rel(net.sum_active, sum0.double() + probs.sum(0)) < TOL
+
+
+def test_run_batch_particle_index_is_bit_exact(cuda_dev):
+    """dis_action of the plain branch: TF Multinomial CPU semantics on the network's own fp32 logits."""
+    from oracle import head as oh
+    from pfpn_b200 import sampling
+    B, S, A, P = 257, 197, 36, 35
+    net = build(cuda_dev)
+    g = torch.Generator().manual_seed(5)
+    state = torch.randn(B, S, generator=g)
+    u = torch.rand(B, A, generator=g, dtype=torch.float64)
+    nrm = torch.randn(B, A, P, generator=g)
+    net.run_batch(state, ext_uniform=u.to(cuda_dev), ext_normal=nrm.to(cuda_dev))
+    logits = net._act["logits"].view(B, A, P)
+    _, idx = sampling.sample_plain(logits, net.loc, net.logstd, ext_uniform=u.to(cuda_dev), ext_normal=nrm.to(cuda_dev))
+    ref = oh.tf_multinomial_cpu(logits.cpu().numpy().reshape(B * A, P), u.numpy().reshape(B * A, 1)).reshape(B, A)
+    assert np.array_equal(idx.cpu().numpy(), ref)
+
+
+def test_ppo_train_step_with_tanh_squashed_actions_matches_oracle(cuda_dev):
+    """normalize_policy_output=True under PPO: the stored action is tanh'd and log_prob applies atanh (utils.py:120-126)."""
+    B = 256
+    net = build(cuda_dev, normalize_policy_output=True)
+    batch = make_batch(B, 197, 36, seed=77)
+    batch["action"] = batch["action"] * 0.97  # strictly inside (-1, 1): atanh finite, as after a tanh squash
+    p0 = oracle_params(net)
+    mean, std = net.state_mean.double().cpu(), net.state_std.double().cpu()
+    b64 = {k: v.double() for k, v in batch.items()}
+    from oracle import head as oh
+    logits, _ = on.forward(p0, b64["state"], mean, std)
+    lp = oh.MixtureGaussianOracle(logits.reshape(B, 36, 35), p0["global_net/actor/samples"],
+                                  p0["global_net/actor/samples_std"].exp(), True).log_prob(b64["action"])
+    batch["log_prob"] = (lp + 0.1 * torch.randn(B, dtype=torch.float64)).float()
+    b64["log_prob"] = batch["log_prob"].double()
+    g_ref, l_ref = on.gradients(p0, b64["state"], b64["action"], b64["value"], b64["log_prob"], b64["advantage"],
+                                mean, std, 36, 35, tanh=True)
+    losses = net.compute_gradients(batch["state"], batch["action"], batch["value"], batch["log_prob"], batch["advantage"])
+    for k, (_, g) in net.named_parameters().items():
+        assert rel(g, g_ref[k]) < 2 * TOL, k  # (atanh of an fp32 action adds its own rounding on top of the head's)
+    assert abs(float(losses[3]) - float(l_ref[3])) < TOL * float(l_ref[3])

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_fused_peer_allreduce_adam_matches_nccl():
     port = 29600 + os.getpid() % 300
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-                        "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "test_peer_2gpu.py")],
+                        "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "run_peer_ngpu.py")],
                        capture_output=True, text=True, timeout=600)
     lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 2, r.stdout[-2000:] + r.stderr[-2000:]
@@ -30,7 +30,7 @@ def test_fused_peer_allreduce_adam_matches_nccl():
 def test_sac_learner_replicas_stay_identical_across_a_resample_tick():
     port = 29300 + os.getpid() % 300
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-                        "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "test_sac_2gpu.py")],
+                        "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "run_sac_ngpu.py")],
                        capture_output=True, text=True, timeout=600)
     lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 2, r.stdout[-2000:] + r.stderr[-2000:]

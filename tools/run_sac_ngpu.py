@@ -17,7 +17,6 @@ g = torch.Generator(device="cuda"); g.manual_seed(100 + rank)
 for it in range(4):  # crosses a resample tick (interval 3)
     batch = (torch.randn(B, S, device=dev, generator=g), torch.rand(B, A, device=dev, generator=g) * 2 - 1,
              torch.randn(B, device=dev, generator=g), torch.ones(B, device=dev), torch.randn(B, S, device=dev, generator=g))
-    net._rng_offset = 1000 * it + 10 * rank  # different draws per rank, as independent workers have
     net.compute_gradients(*batch)
     opt.apply_gradients(net)
     net.run_batch(batch[0])  # rollout-side statistics differ per rank; they are local state until pushed
