@@ -7,12 +7,22 @@
 One "step" = one pass of the fused head (log_prob + entropy + PPO surrogate, forward
 and backward) over one minibatch of B=65536 states
 per GPU, A=36, P=35 -- the configuration BASELINE.json's target is quoted on (c2's
-B=4096 working set, 42 MB, is L2-resident and therefore only a parity case).
+B=4096 working set, 42 MB, is L2-resident and therefore only a parity / latency case).
 Prints ONE JSON line on rank 0.
+
+Besides the headline the line carries (all measured in this run, outside the timed region):
+  roofline      the K1 call (head_kernel + its [A,P] finalize) against the measured HBM peak
+  e2e           the same metric through the host-buffer API, H2D / D2H inside the timed region
+  cpu_baseline  the oracle (torch-CPU restatement of the TF-1.14 graph) at 1 thread and on all cores
+  xcheck        N > 1: the peer-memory exchanges against NCCL, replicas bit-identical (asserted)
+  dppo_update   BASELINE c4: the DPPO minibatch update, B_total = 65536 sharded over the N GPUs
+  extra         BASELINE c2 / c3 / c5: the named secondary shapes at this run's N
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
+import importlib.util
 import json
 import os
 import subprocess
@@ -32,6 +42,22 @@ METRIC = "pfpn_head_action_samples_per_s_fwd_bwd"
 UNIT = "action-samples/s"
 ALG_BYTES_PER_STATE = 8 * A * P + 4 * A + 16  # logits in, dlogits out, action, adv+lp_old, lp+ent
 WORKLOAD = f"PFPN head fwd+bwd (log_prob+entropy+PPO surrogate), B={B_PER_GPU}/GPU, A={A}, P={P}, fp32"
+K1_SOURCE = os.path.join(ROOT, "pfpn_b200", "csrc", "head_logprob.cu")
+
+
+def static_config(world: int) -> dict:
+    """The workload description, identical in both arms."""
+    return {"workload": WORKLOAD, "B_per_gpu": B_PER_GPU, "A": A, "P": P, "n_gpus": world,
+            "l2": "inputs larger than L2: 330 MB logits in + 330 MB dlogits out per step vs 126 MB L2"}
+
+
+def load_synth():
+    """pfpn_b200/synth.py loaded BY PATH: importing the package would dlopen libpfpn_b200.so, which the reference arm
+    must not do (it times the CPU restatement only)."""
+    spec = importlib.util.spec_from_file_location("_pfpn_synth", os.path.join(ROOT, "pfpn_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def peaks():
@@ -42,15 +68,24 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def file_sha256(path: str) -> str:
+    with open(path, "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()
+
+
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the head kernel at this
-    exact shape (profiles/head_kernel_ncu.json, written by tools/make_profiles.py); None if absent."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the head kernel at this exact shape
+    (profiles/head_kernel_ncu.json, written by tools/make_profiles.py together with the sha256 of the kernel source it was
+    captured on).  A capture of a DIFFERENT kernel source is stale: traffic is then null and the reason is stated."""
     try:
         with open(os.path.join(ROOT, "profiles", "head_kernel_ncu.json")) as f:
             d = json.load(f)
-        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
-    except Exception:
-        return None
+        cur = file_sha256(K1_SOURCE)
+        if d.get("source_sha256") != cur:
+            return None, f"stale: captured on head_logprob.cu {str(d.get('source_sha256'))[:12]}, current {cur[:12]}"
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), f"ncu --set full, {d.get('round')}, head_logprob.cu {cur[:12]}"
+    except Exception as e:  # noqa: BLE001
+        return None, f"no capture ({e.__class__.__name__})"
 
 
 class ClockSampler:
@@ -100,46 +135,105 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_rate(b_sample: int, reps: int, threads: int):
-    """Times the oracle (op-order-faithful torch-CPU fp32 restatement of the reference
-    graph; TF 1.14 cannot be installed) on `b_sample` states.  Checker code, timed only
-    as the baseline."""
+# ------------------------------------------------------------------------------------------- CPU legs ----
+def cpu_reference_inputs(b: int):
+    synth = load_synth()
+    d = synth.head_inputs(b, A, P, seed=SEED, far_frac=0.0)
+    d["lp_old"] = torch.zeros(b)
+    return d
+
+
+def cpu_reference_pass(d):
+    """One pass of the oracle: the op-order-faithful torch-CPU fp32 restatement of the reference's TF graph for this path
+    (every [B,A,P] intermediate materialised as the graph does; TF 1.14 cannot be installed).  Checker code -- it is only
+    TIMED here, as the baseline."""
     from oracle import head as oracle_head
-    from pfpn_b200 import synth
+    return oracle_head.ppo_head_fwd_bwd(d["logits"], d["loc"], d["logstd"], d["value"], d["adv"], d["lp_old"],
+                                        dtype=torch.float32)
+
+
+def cpu_reference_rate(d, reps: int, threads: int):
     torch.set_num_threads(threads)
-    d = synth.head_inputs(b_sample, A, P, seed=SEED, far_frac=0.0)
-    lp_old = torch.zeros(b_sample)
-    oracle_head.ppo_head_fwd_bwd(d["logits"], d["loc"], d["logstd"], d["value"], d["adv"], lp_old,
-                                 dtype=torch.float32)  # warm-up
+    cpu_reference_pass(d)  # warm-up
     t0 = time.perf_counter()
     for _ in range(reps):
-        oracle_head.ppo_head_fwd_bwd(d["logits"], d["loc"], d["logstd"], d["value"], d["adv"], lp_old,
-                                     dtype=torch.float32)
+        cpu_reference_pass(d)
     dt = (time.perf_counter() - t0) / reps
-    return b_sample / dt, dt
+    return d["logits"].shape[0] / dt, dt
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def run_reference(args):
+    """The reference arm: the reference's CPU implementation of the path (TF 1.14 is not installable: the oracle port) on
+    all host threads, the FULL workload of the GPU arm per step (65536 states).  Imports neither pfpn_b200 nor its .so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    b_sample = 8192
-    # warm-up steps are real oracle passes too
-    for _ in range(max(0, args.warmup - 1)):
-        cpu_reference_rate(b_sample, 1, threads)
-    rate, dt = cpu_reference_rate(b_sample, max(1, args.steps), threads)
-    sample = f"oracle (torch-CPU fp32 op-order restatement of the TF-1.14 graph), {b_sample} of {B_PER_GPU} states per step, {threads} threads"
+    threads = host_cores()
+    torch.set_num_threads(threads)
+    d = cpu_reference_inputs(B_PER_GPU)
+    for _ in range(max(0, args.warmup)):
+        cpu_reference_pass(d)
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        cpu_reference_pass(d)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    rate = B_PER_GPU / dt
+    sample = (f"oracle (torch-CPU fp32 op-order restatement of the TF-1.14 graph; TF itself cannot be installed), the full "
+              f"{B_PER_GPU} states per step, {threads} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "B_per_gpu": B_PER_GPU, "A": A, "P": P},
+        "config": static_config(args.gpus),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "loaded_pfpn_so": any("libpfpn_b200" in l for l in open("/proc/self/maps")) if os.path.exists("/proc/self/maps") else None,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- helpers ----
+def timed(fn, n, stream, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+    ev[0].record(stream)
+    for i in range(n):
+        fn()
+        ev[i + 1].record(stream)
+    torch.cuda.synchronize()
+    ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(n))
+    return ts[n // 2], sum(ts) / n
+
+
+def tensor_hash(t: torch.Tensor) -> torch.Tensor:
+    bits = t.detach().contiguous().view(torch.int32).to(torch.int64)
+    w = torch.arange(1, bits.numel() + 1, device=bits.device, dtype=torch.int64) % 65521
+    return torch.stack([bits.sum(), (bits * w).sum()])
+
+
+def numa_note(local_rank: int) -> str:
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        rows = [l for l in out.splitlines() if l.startswith(f"GPU{local_rank}\t") or l.startswith(f"GPU{local_rank} ")]
+        hdr = [l for l in out.splitlines() if "NUMA Affinity" in l]
+        if rows and hdr:
+            cols = hdr[0].split("\t")
+            vals = rows[0].split("\t")
+            pick = {c.strip(): v.strip() for c, v in zip(cols, vals) if c.strip() in ("CPU Affinity", "NUMA Affinity")}
+            return ", ".join(f"{k} {v}" for k, v in pick.items())
+    except Exception:
+        pass
+    return "unknown"
 
 
 def main():
@@ -151,6 +245,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dppo", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--dppo-steps", type=int, default=10)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -171,6 +266,12 @@ def main():
     import ctypes as C
     from pfpn_b200 import _cabi, head, synth
     from pfpn_b200.host import HostHeadPipeline
+
+    def maxr(x: float) -> float:
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ---- synthetic minibatch shard, resident in HBM ---------------------------------
     B = B_PER_GPU
@@ -200,24 +301,27 @@ def main():
     a.dlogits, a.dloc, a.dlogstd, a.loss = dlogits.data_ptr(), dloc.data_ptr(), dlogstd.data_ptr(), loss.data_ptr()
     flat_small = torch.empty(2, A, P, device=dev)
     use_peer = world > 1 and os.environ.get("PFPN_FUSED_ALLREDUCE", "1") != "0"
+    gather = None
     if use_peer:
-        from pfpn_b200.peer import PeerSum
-        psum = PeerSum(2 * A * P, dev)
+        from pfpn_b200.peer import PeerGather
+        try:
+            gather = PeerGather(2 * A * P, dev)
+        except (RuntimeError, ValueError):  # collective outcome: every rank falls back together
+            use_peer = False
 
     def step():
         _cabi.check(_cabi.pfpn_adv_stats(adv.data_ptr(), B, stats.data_ptr(), stream.cuda_stream))
         if use_peer:
-            # the path's only exchange: [2, A, P] particle gradients.  K1's finalize kernel writes
-            # them straight into this rank's peer-visible staging slot; one kernel signals, waits and sums.
-            slot = psum.slot()
-            a.dloc, a.dlogstd = slot.data_ptr(), slot.data_ptr() + 4 * A * P
-        _cabi.check(_cabi.pfpn_head_logprob(a, ws.data_ptr(), ws.numel(), stream.cuda_stream))
-        if use_peer:
-            psum.reduce(flat_small.view(-1), 1.0, stream.cuda_stream)
-        elif world > 1:
-            flat_small[0].copy_(dloc)
-            flat_small[1].copy_(dlogstd)
-            dist.all_reduce(flat_small)
+            # the path's only exchange: [2, A, P] particle gradients.  K1's finalize kernel PUSHES them into
+            # every rank's gather buffer and raises the flags; the consumer sums its N local rows in rank order.
+            _cabi.check(_cabi.pfpn_head_logprob_push(a, ws.data_ptr(), ws.numel(), gather.push_args(), stream.cuda_stream))
+            gather.reduce(flat_small.view(-1), 1.0, stream.cuda_stream)
+        else:
+            _cabi.check(_cabi.pfpn_head_logprob(a, ws.data_ptr(), ws.numel(), stream.cuda_stream))
+            if world > 1:
+                flat_small[0].copy_(dloc)
+                flat_small[1].copy_(dlogstd)
+                dist.all_reduce(flat_small)
     launches_per_step = 3 + (1 if use_peer else 0)
 
     def barrier():
@@ -235,17 +339,37 @@ def main():
         step()
         evs[i + 1].record(stream)
     barrier()
-    total_ms = evs[0].elapsed_time(evs[-1])
     per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    total_ms = maxr(evs[0].elapsed_time(evs[-1]))
     value_rate = world * B * args.steps / (total_ms * 1e-3)
+
+    # ---- N > 1: the exchange against NCCL, in the driver's record (outside every timed region) -------------------
+    xcheck = None
+    if world > 1:
+        xcheck = {}
+        step()
+        torch.cuda.synchronize()
+        mine = torch.stack([dloc, dlogstd]).clone() if not use_peer else gather.gather[gather.calls & 1, rank].view(2, A, P).clone()
+        allc = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allc, mine)
+        ordered = allc[0].clone()
+        for r in range(1, world):
+            ordered += allc[r]  # rank-ordered fp32 sum: what the kernel promises, bit for bit
+        nccl = mine.clone()
+        dist.all_reduce(nccl)
+        xcheck["exchange"] = "push (K1 finalize -> peers' gather rows) + pfpn_peer_gather_sum" if use_peer else "NCCL all_reduce"
+        xcheck["peer_sum_bit_equal_rank_ordered"] = bool(torch.equal(flat_small, ordered)) if use_peer else None
+        xcheck["peer_sum_max_abs_vs_nccl"] = float((flat_small - nccl).abs().max())
+        xcheck["peer_sum_ref_max_abs"] = float(nccl.abs().max())
+        h = tensor_hash(flat_small)
+        hs = [torch.empty_like(h) for _ in range(world)]
+        dist.all_gather(hs, h)
+        xcheck["peer_sum_replicas_bit_identical"] = all(torch.equal(x, hs[0]) for x in hs)
 
     # ---- dominant kernel alone (head_kernel + its [A,P] finalize), for the roofline ---
     kev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
     _cabi.check(_cabi.pfpn_adv_stats(adv.data_ptr(), B, stats.data_ptr(), stream.cuda_stream))
+    a.dloc, a.dlogstd = dloc.data_ptr(), dlogstd.data_ptr()
     for i in range(args.steps):
         kev[2 * i].record(stream)
         _cabi.check(_cabi.pfpn_head_logprob(a, ws.data_ptr(), ws.numel(), stream.cuda_stream))
@@ -267,12 +391,12 @@ def main():
         out = pipe.run(**h)
     e1.record(stream)
     barrier()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_rate = world * B * args.e2e_steps / (float(e2e_ms.item()) * 1e-3)
+    e2e_ms_local = e0.elapsed_time(e1)
+    e2e_ms = maxr(e2e_ms_local)
+    e2e_rate = world * B * args.e2e_steps / (e2e_ms * 1e-3)
     # sanity: the host path and the resident path agree
     assert torch.allclose(out["lp"], lp.cpu(), rtol=0, atol=0), "host pipeline lp mismatch"
+    e2e_step_s = e2e_ms_local * 1e-3 / args.e2e_steps
 
     # ---- the DPPO minibatch update around the head (BASELINE c4): B_total = 65536 sharded ------
     dppo = None
@@ -302,44 +426,194 @@ def main():
             upd()
         u1.record(stream)
         barrier()
-        um = torch.tensor([u0.elapsed_time(u1) / args.dppo_steps], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(um, op=dist.ReduceOp.MAX)
+        um = maxr(u0.elapsed_time(u1) / args.dppo_steps)
         dppo = {"workload": f"DPPO minibatch update, B_total={B_PER_GPU} sharded over {world} GPU(s): 197-1024-512 actor+critic trunk (tcgen05 3xTF32 GEMMs), PFPN head, local clip, all-reduce of the 8.4 MB bucket fused into Adam over NVLink peer memory (N>1)",
-                "ms_per_update": float(um.item()), "samples_per_s": B_PER_GPU / (float(um.item()) * 1e-3), "scaling": "strong",
-                "trunk_tflops": 12.6e6 * B_PER_GPU / (float(um.item()) * 1e-3) / 1e12}
+                "ms_per_update": um, "samples_per_s": B_PER_GPU / (um * 1e-3), "scaling": "strong",
+                "trunk_tflops": 12.6e6 * B_PER_GPU / (um * 1e-3) / 1e12,
+                "launches_per_update": getattr(opt, "launches_last_step", None)}
+        if world > 1:
+            # one more update from IDENTICAL state through each exchange implementation: NCCL all-reduce + Adam,
+            # the one-phase peer kernel and the two-phase (reduce-scatter + all-gather) peer kernel
+            snap_n, snap_o = net.state_dict(), opt.state_dict()
+            results = {}
+            for name, fused, two_phase_min in (("nccl", False, "99"), ("peer_one_phase", True, "99"), ("peer_two_phase", True, "2")):
+                if fused and not opt.fused_peer:
+                    continue
+                net.load_state_dict(snap_n)
+                o2 = SyncReplicasAdam(lr=1e-4, norm_clip=1.0, fused_peer=fused)
+                o2._lazy(net)
+                o2.load_state_dict(snap_o)
+                if fused:
+                    o2._peers = opt._peers  # same peer-mapped buffers (their call counter carries on)
+                os.environ["PFPN_PEER_TWO_PHASE_MIN"] = two_phase_min
+                net.compute_gradients(st_, ac_, v_, lpo_, adv_)
+                o2.apply_gradients(net)
+                torch.cuda.synchronize()
+                results[name] = (net.params.clone(), o2.m.clone(), o2.v.clone())
+            os.environ.pop("PFPN_PEER_TWO_PHASE_MIN", None)
+            ref_p = results["nccl"][0]
+            for name, (p_, m_, v2_) in results.items():
+                hh = torch.cat([tensor_hash(p_), tensor_hash(m_), tensor_hash(v2_)])
+                hs = [torch.empty_like(hh) for _ in range(world)]
+                dist.all_gather(hs, hh)
+                xcheck[f"{name}_replica_hash_equal"] = all(torch.equal(x, hs[0]) for x in hs)
+                if name != "nccl":
+                    d_ = (p_ - ref_p).abs().max() / (ref_p - snap_n["params"]).abs().max().clamp_min(1e-30)
+                    xcheck[f"{name}_vs_nccl_rel_update_diff"] = float(d_)
     clocks = sampler.stop() if sampler else None
+
+    # ---- BASELINE c2 / c3 / c5 at this run's N ---------------------------------------------------------------------
+    extra = None
+    if not args.no_extra:
+        extra = run_extra(dev, rank, world, stream, maxr)
+
+    if xcheck is not None:
+        ok = xcheck["peer_sum_replicas_bit_identical"] and xcheck["peer_sum_max_abs_vs_nccl"] <= 1e-6 * max(1.0, xcheck["peer_sum_ref_max_abs"])
+        if xcheck.get("peer_sum_bit_equal_rank_ordered") is not None:
+            ok = ok and xcheck["peer_sum_bit_equal_rank_ordered"]
+        for k, v in xcheck.items():
+            if k.endswith("_replica_hash_equal"):
+                ok = ok and v
+            if k.endswith("_vs_nccl_rel_update_diff"):
+                ok = ok and v < 1e-3  # (Adam normalises by |g|: an ulp of the averaged gradient moves near-zero entries)
+        xcheck["ok"] = bool(ok)
 
     if rank == 0:
         peak, peak_src = peaks()
         achieved = ALG_BYTES_PER_STATE * B / (k_avg_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic()
+        cfg = static_config(world)
+        cfg["parallelism"] = f"dp{world} (states sharded, [2,A,P] particle-gradient exchange" + \
+            (" pushed by K1's finalize kernel over NVLink peer memory)" if use_peer else ", NCCL all-reduce)" if world > 1 else ")")
         line = {
             "metric": METRIC, "value": value_rate, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "B_per_gpu": B, "A": A, "P": P,
-                       "l2": "inputs larger than L2: 330 MB logits in + 330 MB dlogits out per step vs 126 MB L2",
-                       "step_ms_median": per[len(per) // 2], "parallelism": f"dp{world} (states sharded, [2,A,P] particle-gradient exchange" + (" over NVLink peer memory, one kernel)" if use_peer else ", NCCL all-reduce)" if world > 1 else ")")},
+            "config": cfg, "step_ms_median": per[len(per) // 2],
             "clocks": clocks,
             "e2e": {"value": e2e_rate, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
                     "d2h_bytes_per_step": pipe.d2h_bytes, "steps": args.e2e_steps,
-                    "api": "pfpn_b200.host.HostHeadPipeline.run (pinned host buffers, 3-stream chunked)"},
+                    "api": "pfpn_b200.host.HostHeadPipeline.run (pinned host buffers, 3-stream chunked)",
+                    "rank0_h2d_GBps": pipe.h2d_bytes / e2e_step_s / 1e9, "rank0_d2h_GBps": pipe.d2h_bytes / e2e_step_s / 1e9,
+                    "bound": "PCIe: both directions stream concurrently for the whole step; the 0.17 ms kernel is ~2 % of it",
+                    "rank0_host_affinity": numa_note(local_rank)},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "pfpn::head_kernel<.., KM=PPO> (+head_finalize)",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel": "pfpn::head_kernel<.., KM=PPO> (+head_finalize)",
                          "alg_bytes_per_state": ALG_BYTES_PER_STATE, "kernel_ms_avg": k_avg_ms,
                          "kernel_ms_median": kms[len(kms) // 2]},
         }
         if dppo is not None:
             line["dppo_update"] = dppo
+        if xcheck is not None:
+            line["xcheck"] = xcheck
+        if extra is not None:
+            line["extra"] = extra
         if not args.no_cpu_baseline and world == 1:
-            cores = os.cpu_count() or 1
-            rate, dt = cpu_reference_rate(4096, 3, cores)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"oracle torch-CPU fp32 op-order restatement, 4096 states x 3 reps ({dt*1e3:.0f} ms each), {cores} threads"}
+            cores = host_cores()
+            b_s = 8192
+            d = cpu_reference_inputs(b_s)
+            r1, dt1 = cpu_reference_rate(d, 2, 1)
+            rN, dtN = cpu_reference_rate(d, 4, cores)
+            line["cpu_baseline"] = {"value": rN, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"oracle torch-CPU fp32 op-order restatement, {b_s} of {B} states per pass, 4 passes "
+                                              f"({dtN*1e3:.0f} ms each) on {cores} threads; 2 passes ({dt1*1e3:.0f} ms each) on 1 thread",
+                                    "single_thread": {"value": r1, "unit": UNIT, "cores": 1,
+                                                      "note": "benchmark.sh:18 pins OPENBLAS_NUM_THREADS=1 per worker"}}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if xcheck is not None and not xcheck["ok"]:
+        raise SystemExit(f"xcheck failed: {xcheck}")
+
+
+def run_extra(dev, rank, world, stream, maxr):
+    """The secondary shapes BASELINE.json names, at this run's N (each rank its contiguous shard, no collective):
+    c2 head at B=4096 (L2-resident: a latency case), c3 resampler sweep P=10/35/100 (replicas only, rank 0's time),
+    c5 SAC head at B=1M total, A=36, P=100 against the HBM roofline of SURVEY 8(d)."""
+    import numpy as np
+    from pfpn_b200 import _cabi, head, resampling, sampling, synth
+    peak, _ = peaks()
+    out = {}
+    # ---- c2 ----
+    B2, A2, P2 = 4096, 36, 35
+    d = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in synth.head_inputs(B2, A2, P2).items()}
+    o = head.head_call(_cabi.HEAD_FWD, d["logits"], d["loc"], d["logstd"], d["value"])
+    lp_old = o["lp"] + d["lp_noise"]
+    st2 = head.adv_stats(d["adv"])
+    buf = {}
+    ms, _ = timed(lambda: head.head_call(_cabi.HEAD_PPO, d["logits"], d["loc"], d["logstd"], d["value"], adv=d["adv"],
+                                         lp_old=lp_old, adv_stats_t=st2, out=buf), 30, stream)
+    ms_f, _ = timed(lambda: head.head_call(_cabi.HEAD_FWD, d["logits"], d["loc"], d["logstd"], d["value"], out=buf), 30, stream)
+    ms_s, _ = timed(lambda: sampling.sample_plain(d["logits"], d["loc"], d["logstd"], seed=1, offset=2), 30, stream)
+    out["c2_head_B4096_per_gpu"] = {"ppo_fwd_bwd_us": maxr(ms) * 1e3, "fwd_only_us": maxr(ms_f) * 1e3, "plain_sample_us": maxr(ms_s) * 1e3,
+                                    "Mstates_s_all_gpus": world * B2 / maxr(ms) / 1e3,
+                                    "note": "41.9 MB working set is L2-resident: a latency case, not a roofline case"}
+    # ---- c3 ----
+    res = {}
+    for P3 in (10, 35, 100):
+        rng = np.random.default_rng(33406 + P3)
+        A3, H = 36, 512
+        lg = rng.normal(0, 3, (512, A3, P3))
+        pr = np.exp(lg - lg.max(-1, keepdims=True))
+        pr /= pr.sum(-1, keepdims=True)
+        mx, sm = pr.max(0).astype(np.float32), pr.sum(0).astype(np.float32)
+        dead = rng.random((A3, P3)) < 0.1
+        mx[dead] = 1e-6
+        t = lambda a_: torch.tensor(a_, dtype=torch.float32, device=dev)
+        base = dict(mx=t(mx), sm=t(sm), loc=t(np.linspace(-1, 1, P3)[None].repeat(A3, 0)), ls=t(np.full((A3, P3), np.log(2 / (P3 - 1)))),
+                    b=t(rng.normal(0, 1, A3 * P3)), W=t(rng.normal(0, .01, (H, A3 * P3))))
+        work = {k: v.clone() for k, v in base.items()}
+
+        def copies():
+            for k in work:
+                work[k].copy_(base[k])
+
+        def call():
+            copies()
+            resampling.resample_(work["mx"], work["sm"], work["loc"], work["ls"], work["b"], work["W"], seed=3, offset=5)
+        us = (timed(call, 20, stream)[0] - timed(copies, 20, stream)[0]) * 1e3
+        res[f"P{P3}"] = {"dead": int(dead.sum()), "us_per_resample": us}
+    out["c3_resample_A36_H512"] = dict(res, note="replicas only (every rank runs it identically); latency-bound, roofline fraction not meaningful")
+    # ---- c5 ----
+    A5, P5, BT = 36, 100, 1_000_000
+    B5 = BT // world
+    g5 = torch.Generator(device="cuda")
+    g5.manual_seed(12831 + rank)
+    logits5 = torch.randn(B5, A5, P5, device=dev, generator=g5) * 2.0
+    from pfpn_b200.network import initial_particles
+    loc5, ls5 = (x.to(dev) for x in initial_particles(A5, P5, True))
+    g_s = torch.randn(B5, A5, device=dev, generator=g5)
+    g_lp = torch.full((B5,), 1.0 / BT, device=dev)
+    smp, s_pre, _ = sampling.rsample_fwd(logits5, loc5, ls5, seed=7, offset=0)
+    buf5 = dict(dlogits=torch.empty_like(logits5))
+    t_f, _ = timed(lambda: sampling.rsample_fwd(logits5, loc5, ls5, seed=7, offset=0), 5, stream, warm=1)
+    t_l, _ = timed(lambda: head.head_call(_cabi.HEAD_GRAD, logits5, loc5, ls5, s_pre, tanh=True, g_lp=g_lp, want_dvalue=True, out=buf5), 5, stream, warm=1)
+    t_b, _ = timed(lambda: sampling.rsample_bwd(logits5, loc5, ls5, g_s, buf5["dvalue"], seed=7, offset=0), 3, stream, warm=1)
+    tot = maxr(t_f + t_l + t_b)
+    alg_state = 8 * A5 * P5 + 12 * A5 + 8
+    roof_states = peak * 1e9 / alg_state
+    c5 = {"B_total": BT, "B_per_gpu": B5, "A": A5, "P": P5,
+          "rsample_fwd_ms": maxr(t_f), "tanh_logprob_fwd_bwd_ms": maxr(t_l), "rsample_bwd_ms": maxr(t_b),
+          "variant": "split (boundary-faithful: rsample fwd, tanh log_prob fwd+bwd with dvalue, rsample bwd = 3 launches)",
+          "Mstates_s_all_gpus": BT / tot / 1e3,
+          "frac_of_8d_roofline": (BT / (tot * 1e-3)) / (world * roof_states),
+          "roofline_Mstates_s_per_gpu": roof_states / 1e6, "alg_bytes_per_state": alg_state}
+    try:
+        fz = {}
+        t_z, _ = timed(lambda: sampling.sac_head_fused(logits5, loc5, ls5, g_s, g_lp, seed=7, offset=0, out=fz), 3, stream, warm=1)
+        tz = maxr(t_z)
+        c5["fused_fwd_bwd_ms"] = tz
+        c5["fused_Mstates_s_all_gpus"] = BT / tz / 1e3
+        c5["fused_frac_of_8d_roofline"] = (BT / (tz * 1e-3)) / (world * roof_states)
+    except AttributeError:
+        pass
+    out["c5_sac_head"] = c5
+    del logits5, buf5
+    torch.cuda.empty_cache()
+    return out
 
 
 if __name__ == "__main__":

@@ -90,6 +90,25 @@ typedef struct pfpn_head_args {
 int pfpn_head_workspace_bytes(int32_t A, int32_t P, size_t* bytes);
 int pfpn_head_logprob(const pfpn_head_args* args, void* workspace, size_t workspace_bytes,
                       pfpn_stream_t stream);
+/* Data-parallel form: the [2, A, P] particle gradients are the sharded head's only exchange.  With a `push`
+ * the kernel that finishes dloc / dlogstd also writes them into row `rank` of EVERY rank's peer-mapped gather buffer
+ * (NVLink stores) and its last CTA publishes `value` (the call counter: 1, 2, 3, ...) in every rank's flag word with a
+ * system-scope release -- no separate exchange kernel sits behind K1.  The consumer calls pfpn_peer_gather_sum, which
+ * waits for the N flags and sums the N LOCAL rows in rank order (identical on every rank).  args->dloc / dlogstd may be
+ * NULL here.  Replaces (semantics) the accumulator sum of models/sync_model.py:92-96 for `samples` / `samples_std`. */
+typedef struct pfpn_head_push {
+  float* out[8];     /* out[p]: rank p's gather row for THIS rank and this call's parity, 2*A*P floats (peer-mapped)   */
+  int32_t* flags[8]; /* flags[p]: rank p's flag word for THIS rank (peer-mapped int32, zero-initialised, monotonic)    */
+  int32_t* ticket;   /* local device int32, zero-initialised (CTA-arrival counter, self-resetting)                     */
+  int32_t nranks;    /* 1..8                                                                                           */
+  int32_t value;     /* call counter, +1 per call                                                                      */
+} pfpn_head_push;
+int pfpn_head_logprob_push(const pfpn_head_args* args, void* workspace, size_t workspace_bytes,
+                           const pfpn_head_push* push, pfpn_stream_t stream);
+/* out[n] = scale * sum_{r < nranks} gather[r*n + i] once flags[r] >= value for every r (acquire loads, system scope);
+ * `gather` / `flags` are THIS rank's own buffers (the rows its peers pushed into).  n % 4 == 0. */
+int pfpn_peer_gather_sum(const float* gather, const int32_t* flags, int32_t nranks, int32_t value, size_t n, float* out,
+                         float scale, pfpn_stream_t stream);
 /* Minibatch advantage statistics: stats = {mean, 1/(sqrt(popvar)+1e-8)}
  * (actor_critic.py:151-155).  One CTA, deterministic. */
 int pfpn_adv_stats(const float* adv, int32_t B, float* stats, pfpn_stream_t stream);

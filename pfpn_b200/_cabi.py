@@ -47,6 +47,12 @@ class HeadArgs(C.Structure):
     ]
 
 
+class HeadPush(C.Structure):
+    """Mirror of ``pfpn_head_push``."""
+    _fields_ = [("out", C.c_void_p * 8), ("flags", C.c_void_p * 8), ("ticket", C.c_void_p),
+                ("nranks", C.c_int32), ("value", C.c_int32)]
+
+
 def _sig(name, restype, argtypes):
     fn = getattr(lib, name)
     fn.restype = restype
@@ -164,6 +170,9 @@ pfpn_peer_allreduce_adam_rs = _sig("pfpn_peer_allreduce_adam_rs", C.c_int,
                                    [_vp, _vp, _vp, _i32, _i32, _i32, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _vp, _f, _f, _f, _f,
                                     C.c_int64, _vp])
 pfpn_peer_allreduce_sum = _sig("pfpn_peer_allreduce_sum", C.c_int, [_vp, _vp, _i32, _i32, _i32, C.c_size_t, _vp, _f, _vp])
+pfpn_head_logprob_push = _sig("pfpn_head_logprob_push", C.c_int,
+                              [C.POINTER(HeadArgs), C.c_void_p, C.c_size_t, C.POINTER(HeadPush), C.c_void_p])
+pfpn_peer_gather_sum = _sig("pfpn_peer_gather_sum", C.c_int, [_vp, _vp, _i32, _i32, C.c_size_t, _vp, _f, _vp])
 pfpn_peer_alloc = _sig("pfpn_peer_alloc", C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p])
 pfpn_peer_open = _sig("pfpn_peer_open", C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)])
 pfpn_peer_close = _sig("pfpn_peer_close", C.c_int, [_vp])

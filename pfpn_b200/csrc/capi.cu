@@ -26,3 +26,4 @@ static_assert(sizeof(pfpn_sample_args) == 88, "pfpn_sample_args layout changed: 
 static_assert(sizeof(pfpn_rsample_args) == 136, "pfpn_rsample_args layout changed: update _cabi.RSampleArgs");
 static_assert(sizeof(pfpn_resample_args) == 200, "pfpn_resample_args layout changed: update _cabi.ResampleArgs");
 static_assert(offsetof(pfpn_resample_args, seed) == 160 && offsetof(pfpn_resample_args, threshold) == 176, "layout");
+static_assert(sizeof(pfpn_head_push) == 144 && offsetof(pfpn_head_push, ticket) == 128 && offsetof(pfpn_head_push, value) == 140, "pfpn_head_push layout changed: update _cabi.HeadPush");

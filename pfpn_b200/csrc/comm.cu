@@ -25,9 +25,20 @@ constexpr int kMaxPeers = 8;
 // A peer that never publishes (crashed rank, mismatched call counts) must not wedge the GPU: after ~10 s of polling
 // the kernel traps, which surfaces as a launch failure on the host instead of a hang.
 constexpr long long kSpinTimeoutCycles = 20000000000LL;
-__device__ __forceinline__ void spin_until_ge(const volatile int* f, int value) {
+// Flags are written with st.release.sys and polled with ld.acquire.sys: the data a peer published before raising its flag
+// (its bucket, written by earlier kernels on its stream or by the same kernel before a system-scope fence) is visible
+// to whoever observed the flag.
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void spin_until_ge(const int* f, int value) {
   const long long t0 = clock64();
-  while (*f < value) {
+  while (ld_acquire_sys(f) < value) {
     if (clock64() - t0 > kSpinTimeoutCycles) __trap();
   }
 }
@@ -40,7 +51,7 @@ __global__ void peer_signal_kernel(PeerPtrs pp, int rank, int nranks, int value)
   const int p = threadIdx.x;
   if (p < nranks) {
     __threadfence_system();  // this rank's bucket (written by earlier kernels on the stream) -> visible
-    *reinterpret_cast<volatile int*>(pp.flags[p] + rank) = value;
+    st_release_sys(pp.flags[p] + rank, value);
   }
 }
 
@@ -49,11 +60,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_adam_kernel(PeerPtrs pp, i
                                                                   float* __restrict__ m, float* __restrict__ v,
                                                                   float* __restrict__ avg_out, float lr_t, float b1, float b2,
                                                                   float eps) {
-  if (threadIdx.x < nranks) {
-    const volatile int* f = reinterpret_cast<const volatile int*>(pp.flags[rank]) + threadIdx.x;
-    spin_until_ge(f, value);
-    __threadfence_system();
-  }
+  if (threadIdx.x < nranks) spin_until_ge(pp.flags[rank] + threadIdx.x, value);
   __syncthreads();
   const float inv_n = 1.f / (float)nranks;
   const size_t n4 = n_total / 4;  // buckets are padded to a multiple of 4 floats
@@ -99,11 +106,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_adam_rs_kernel(PeerPtrs2 p
   const size_t n4 = n_total / 4;
   const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
   // ---- phase 0: every peer has published its clipped bucket of this step
-  if (threadIdx.x < nranks) {
-    const volatile int* f = reinterpret_cast<const volatile int*>(pp.flags[rank]) + threadIdx.x;
-    spin_until_ge(f, value);
-    __threadfence_system();
-  }
+  if (threadIdx.x < nranks) spin_until_ge(pp.flags[rank] + threadIdx.x, value);
   __syncthreads();
   // ---- phase 1: mean of my slice, in rank order
   const float inv_n = 1.f / (float)nranks;
@@ -122,19 +125,16 @@ __global__ void __launch_bounds__(256) peer_allreduce_adam_rs_kernel(PeerPtrs2 p
     __threadfence();
     int* ctr = pp.flags[rank] + 32;
     const int arrived = atomicAdd(ctr, 1) + 1;
-    if (arrived == (int)gridDim.x * value) {  // last CTA of this call (the counter is never reset; value = call index)
+    if (arrived == (int)gridDim.x) {  // last CTA of this call: every CTA has arrived, nobody touches the counter again
+      *ctr = 0;                       // self-resetting (the next call on this stream starts from zero)
       __threadfence_system();
-      for (int p = 0; p < nranks; ++p) *reinterpret_cast<volatile int*>(pp.flags[p] + 8 + rank) = value;
+      for (int p = 0; p < nranks; ++p) st_release_sys(pp.flags[p] + 8 + rank, value);
     }
   }
   // ---- phase 2: gather the averaged slices (own slice first, then the peers round-robin) + Adam on everything
   for (int k = 0; k < nranks; ++k) {
     const int q = (rank + k) % nranks;
-    if (threadIdx.x == 0) {
-      const volatile int* f = reinterpret_cast<const volatile int*>(pp.flags[rank]) + 8 + q;
-      spin_until_ge(f, value);
-      __threadfence_system();
-    }
+    if (threadIdx.x == 0) spin_until_ge(pp.flags[rank] + 8 + q, value);
     __syncthreads();
     const size_t qlo = (size_t)q * slice4, qhi = min(n4, qlo + slice4);
     for (size_t i = qlo + gtid; i < qhi; i += gsz) {
@@ -163,13 +163,9 @@ __global__ void __launch_bounds__(256) peer_sum_kernel(PeerPtrs pp, int rank, in
                                                        float* __restrict__ out, float scale) {
   if (blockIdx.x == 0 && threadIdx.x < nranks) {
     __threadfence_system();
-    *reinterpret_cast<volatile int*>(pp.flags[threadIdx.x] + rank) = value;  // publish to every peer (and self)
+    st_release_sys(pp.flags[threadIdx.x] + rank, value);  // publish to every peer (and self)
   }
-  if (threadIdx.x < nranks) {
-    const volatile int* f = reinterpret_cast<const volatile int*>(pp.flags[rank]) + threadIdx.x;
-    spin_until_ge(f, value);
-    __threadfence_system();
-  }
+  if (threadIdx.x < nranks) spin_until_ge(pp.flags[rank] + threadIdx.x, value);
   __syncthreads();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -182,9 +178,49 @@ __global__ void __launch_bounds__(256) peer_sum_kernel(PeerPtrs pp, int rank, in
   }
 }
 
+// Consumer side of the PUSH protocol (pfpn_head_logprob_push): the peers' kernels stored their rows into THIS rank's
+// gather buffer and raised this rank's flag words; wait for the N flags, then sum the N local rows in rank order.
+// Launched with programmatic stream serialization: it becomes resident behind K1's finalize and is already polling
+// when the flags arrive.  No CTA waits on another CTA of this grid, so there is no co-residency requirement.
+__global__ void __launch_bounds__(256) peer_gather_sum_kernel(const float* __restrict__ gather, const int* __restrict__ flags,
+                                                              int nranks, int value, size_t n4, float* __restrict__ out,
+                                                              float scale) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // (orders the previous consumer of `out` / this rank's own push)
+  if (threadIdx.x < nranks) spin_until_ge(flags + threadIdx.x, value);
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < nranks; ++p) {  // fixed order: identical result on every rank
+      const float4 g = __ldcg(reinterpret_cast<const float4*>(gather) + (size_t)p * n4 + i);
+      s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+    }
+    s.x *= scale; s.y *= scale; s.z *= scale; s.w *= scale;
+    reinterpret_cast<float4*>(out)[i] = s;
+  }
+}
+
 }  // namespace pfpn
 
 using namespace pfpn;
+
+extern "C" int pfpn_peer_gather_sum(const float* gather, const int32_t* flags, int32_t nranks, int32_t value, size_t n,
+                                    float* out, float scale, pfpn_stream_t stream_) {
+  if (!gather || !flags || !out || nranks < 1 || nranks > kMaxPeers || (n & 3) || n == 0 || value < 1) return PFPN_ERR_ARG;
+  const size_t n4 = n / 4;
+  size_t grid = (n4 + 255) / 256;
+  if (grid > 148) grid = 148;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(256);
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream_);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  PFPN_CUDA_OK(cudaLaunchKernelEx(&cfg, peer_gather_sum_kernel, gather, (const int*)flags, (int)nranks, (int)value, n4, out, scale));
+  return PFPN_OK;
+}
 
 extern "C" int pfpn_enable_peer_access(int32_t peer_device) {
   int dev = 0;
@@ -259,9 +295,26 @@ extern "C" int pfpn_peer_allreduce_adam_rs(const float* const* buckets, float* c
   const size_t n4 = n_total / 4;
   const size_t slice4 = (n4 + nranks - 1) / nranks;
   const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
-  peer_allreduce_adam_rs_kernel<<<296, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      pp, rank, nranks, value, n_params, n_total, slice4, params, m, v, avg_out, (float)lr_t, beta1, beta2, eps);
-  PFPN_CUDA_OK(cudaGetLastError());
+  // Phase 2 waits for the LOCAL phase 1 of every CTA of this grid: the grid must be co-resident.  A cooperative launch
+  // makes the driver guarantee that (or fail the launch) instead of assuming an idle GPU; the grid is sized from the
+  // occupancy of this device.
+  int dev = 0, sms = 0, per_sm = 0;
+  PFPN_CUDA_OK(cudaGetDevice(&dev));
+  PFPN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  PFPN_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peer_allreduce_adam_rs_kernel, 256, 0));
+  if (per_sm < 1) return PFPN_ERR_UNSUPPORTED;
+  const int grid = sms * (per_sm < 2 ? per_sm : 2);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(256);
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream_);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  PFPN_CUDA_OK(cudaLaunchKernelEx(&cfg, peer_allreduce_adam_rs_kernel, pp, (int)rank, (int)nranks, (int)value, n_params, n_total,
+                                  slice4, params, m, v, avg_out, (float)lr_t, beta1, beta2, eps));
   return PFPN_OK;
 }
 

@@ -23,6 +23,7 @@
 //    surrogate and publishes ONE dL/dlp per state through an mbarrier (SIP) -- there is no
 //    block-wide barrier in the steady state.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -70,6 +71,13 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
   constexpr bool BWD = KM != 0;
   constexpr bool CSM = (OPT & 1) != 0;
   constexpr bool RC = (OPT & 2) != 0 && BWD;
+  // OPT bit 2 (SPL): bank-conflict-free particle ownership for 2 lanes per row.  Rows are P floats apart (P odd), so the
+  // interleaved ownership k = c + 2 i makes lane pairs of different rows collide on a shared-memory bank (12.9 M
+  // conflicts per launch at P = 35 in the round-1 profile).  With k = 16 c + i for i < 16 the two lanes of a row are 16
+  // banks apart and the 32 lanes of a warp (16 consecutive rows, 3 banks apart each) hit 32 distinct banks; particles
+  // >= 32 stay interleaved.  Requires LPR == 2 and 32 <= P <= 2 * EPL.
+  constexpr bool SPL = (OPT & 4) != 0;
+  static_assert(!SPL || LPR == 2, "split ownership is defined for 2 lanes per row");
   constexpr bool LEAN = KM >= 2;
   constexpr int EP2 = (EPL + 1) / 2;  // packed pairs per lane
   // Software pipeline: iteration `it` runs pass A/B of tile it and pass C of tile it-1; the
@@ -93,6 +101,11 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
   // SIP (scalars in the producer): the otherwise idle producer warp sums a state's row partials, writes lp / ent, evaluates
   // the PPO surrogate and publishes ONE dL/dlp per state; the compute lanes (72..576 per state) no longer each re-derive it.
   constexpr bool SIP = SEG;
+  // OPT bit 3 (EARLY): the compute threads signal "row partials of tile it written" on a second barrier right after pass A/B
+  // instead of only at the end of the step, and the producer publishes dL/dlp of tile it while they are still in pass C of
+  // tile it-1.  A warp then needs the slowest warp to be at most TWO passes behind (one before) when it reaches its g_bar
+  // wait -- the round-1 profile had 7.5 % of all stall samples in that spin.
+  constexpr bool EARLY = (OPT & 8) != 0 && SIP && BWD;
   const int TS = slots * RPT;
   const int tile_floats = TS * AP;
   const uint32_t mode = KM == 2 ? (uint32_t)PFPN_HEAD_PPO : (KM == 3 ? (uint32_t)PFPN_HEAD_GRAD : kp.a.mode);
@@ -118,8 +131,9 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
   unsigned char* tail = smem_raw + (size_t)NSTAGE * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* cta_bar = full_bar + NSTAGE;                            // split-phase CTA barrier
-  uint64_t* g_bar = cta_bar + 1;                                    // SIP: producer -> compute, per-state dL/dlp ready
-  float2* rowbuf = reinterpret_cast<float2*>(tail + 8 * (NSTAGE + 2));  // [NSTAGE][TS*A] per-row (log p, H) partials
+  uint64_t* g_bar = cta_bar + 1;                                    // [2] SIP: producer -> compute, per-state dL/dlp ready (tile parity)
+  uint64_t* ab_bar = cta_bar + 3;                                   // EARLY: compute -> producer, row partials of a tile written
+  float2* rowbuf = reinterpret_cast<float2*>(tail + 8 * (NSTAGE + 4));  // [NSTAGE][TS*A] per-row (log p, H) partials
   float* lossbuf = reinterpret_cast<float*>(rowbuf + NSTAGE * TS * A);  // [kHeadMaxWarps]
   float* gbuf = lossbuf + kHeadMaxWarps;                            // [NSTAGE][TS] per-state dL/dlp (SIP), 256 floats
   float* dummy = gbuf + 256;                                        // [LPR*EPL] sink for masked rows
@@ -129,7 +143,9 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
 #pragma unroll
     for (int s = 0; s < NSTAGE; ++s) mbar_init(smem_u32(&full_bar[s]), 1);
     mbar_init(smem_u32(cta_bar), (uint32_t)nthr);
-    mbar_init(smem_u32(g_bar), 1);
+    mbar_init(smem_u32(&g_bar[0]), 1);
+    mbar_init(smem_u32(&g_bar[1]), 1);
+    mbar_init(smem_u32(ab_bar), (uint32_t)nthr);
     mbar_fence_init();
   }
   // programmatic dependent launch: everything above overlaps the tail of the previous kernel on the stream
@@ -173,6 +189,9 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
   const int nfull = P / LPR;
   const bool part_ok = c < P - nfull * LPR;
   auto k_ok = [&](int i) -> bool { return (i < nfull) || (i == nfull && part_ok); };
+  // element offset (within the row) of this lane's i-th particle, MINUS c: rows are addressed as row_base + c + kofs(i)
+  const int spl_c = SPL ? 15 * c : 0;
+  auto kofs = [&](int i) -> int { return (SPL && i < 16) ? (spl_c + i) : LPR * i; };
 
   constexpr int NCR = CSM ? 1 : EP2;
   float2 isig_r[NCR], nmisig_r[NCR], cst_r[NCR];
@@ -186,7 +205,7 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
     for (int h = 0; h < 2; ++h) {
       const int i = 2 * i2 + h;
       const bool ok = active && (i < EPL) && k_ok(i);
-      const int k = c + LPR * i;
+      const int k = c + kofs(i);
       const float ls = ok ? __ldg(&kp.a.logstd[a * P + k]) : 0.f;
       const float mu = ok ? __ldg(&kp.a.loc[a * P + k]) : 0.f;
       const float is = ok ? expf(-ls) : 0.f;
@@ -232,26 +251,46 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
     // compute thread has fenced its gradient STS of tile it-2, so that tile can leave; the
     // stage that load(it+DIST) refills held tile it+DIST-NSTAGE, whose store is older than the
     // NSTAGE-DIST-2 most recent bulk groups.  Only this warp ever blocks on TMA traffic.
-    for (int it = 1; it <= my_tiles; ++it) {
-      mbar_wait(cta_bar_a, (uint32_t)((it - 1) & 1));
-      if (lane == 0) {
-        if (BWD && it >= 2) {
-          const int ptile = first_tile + (it - 2) * tile_step;
-          bulk_s2g(g_dlogits + (size_t)ptile * tile_floats,
-                   smem_u32(stage_base) + ((it - 2) % NSTAGE) * stage_bytes, (uint32_t)(tile_floats * 4));
-          bulk_commit();
-          bulk_wait_read<NSTAGE - DIST - 2>();
+    // Iteration `it`: (1) TMA duties that became possible when step it-1 completed, (2) the per-state scalars of tile
+    // `sit` -- tile it-1 (its partials are complete once step it-1 is) or, with EARLY, tile it (as soon as its pass A/B is).
+    for (int it = EARLY ? 0 : 1; it <= my_tiles; ++it) {
+      const int sit = EARLY ? it : it - 1;
+      const bool do_sip = SIP && sit < my_tiles;
+      // the per-state scalars (PPO: adv, lp_old; GRAD: dL/dlp) do not depend on the compute warps: fetch them before
+      // blocking on a barrier so the DRAM latency is off the g_bar critical path
+      float pf0 = 0.f, pf1 = 0.f;
+      if (do_sip && BWD && lane < TS) {
+        const int b = (first_tile + sit * tile_step) * TS + lane;
+        if (b < B) {
+          if (mode == PFPN_HEAD_PPO) {
+            pf0 = __ldg(&kp.a.adv[b]);
+            pf1 = __ldg(&kp.a.lp_old[b]);
+          } else {
+            pf0 = __ldg(&kp.a.g_lp[b]);
+          }
         }
-        issue_load(it + DIST);
       }
-      __syncwarp();
-      if (SIP) {
-        // ---- per-state scalars of tile it-1 (its row partials are complete: that is what the barrier phase says) ----
-        const int pit = it - 1;
-        const int pb0 = (first_tile + pit * tile_step) * TS;
+      if (it >= 1) {
+        mbar_wait(cta_bar_a, (uint32_t)((it - 1) & 1));
+        if (lane == 0) {
+          if (BWD && it >= 2) {
+            const int ptile = first_tile + (it - 2) * tile_step;
+            bulk_s2g(g_dlogits + (size_t)ptile * tile_floats,
+                     smem_u32(stage_base) + ((it - 2) % NSTAGE) * stage_bytes, (uint32_t)(tile_floats * 4));
+            bulk_commit();
+            bulk_wait_read<NSTAGE - DIST - 2>();
+          }
+          issue_load(it + DIST);
+        }
+        __syncwarp();
+      }
+      if (do_sip) {
+        if (EARLY) mbar_wait(smem_u32(ab_bar), (uint32_t)(sit & 1));  // every compute thread wrote its partials of tile sit
+        // ---- per-state scalars of tile sit ----
+        const int pb0 = (first_tile + sit * tile_step) * TS;
         if (lane < TS) {
           const int jj = lane / slots, sl = lane - jj * slots;
-          const float2* hb = rowbuf + (pit % NSTAGE) * TS * A + jj * (MAXT / GL + 1) + sl * HPS;
+          const float2* hb = rowbuf + (sit % NSTAGE) * TS * A + jj * (MAXT / GL + 1) + sl * HPS;
           float lp = 0.f, en = 0.f;
 #pragma unroll
           for (int h = 0; h < HPS; ++h) {
@@ -266,22 +305,23 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
             if (kp.a.ent != nullptr) kp.a.ent[b] = en;
             if (BWD) {
               if (mode == PFPN_HEAD_PPO) {
-                const float an = (__ldg(&kp.a.adv[b]) - adv_mean) * adv_rstd;
-                const float ratio = ex2f((lp - __ldg(&kp.a.lp_old[b])) * kLog2e);
+                const float an = (pf0 - adv_mean) * adv_rstd;
+                const float ratio = ex2f((lp - pf1) * kLog2e);
                 const float surr = ratio * an;
                 const float clipped = fminf(fmaxf(ratio, 1.f - eps_clip), 1.f + eps_clip) * an;
                 loss_acc -= fminf(surr, clipped) * loss_scale;
                 g = (surr <= clipped) ? -loss_scale * ratio * an : 0.f;  // TF Minimum: ties -> x
               } else {
-                g = __ldg(&kp.a.g_lp[b]);
+                g = pf0;
               }
             }
           }
-          if (BWD) gbuf[(pit % NSTAGE) * TS + lane] = g;
+          if (BWD) gbuf[(sit % NSTAGE) * TS + lane] = g;
         }
         if (BWD) {
           __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(g_bar)) : "memory");
+          if (lane == 0)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&g_bar[sit & 1])) : "memory");
         }
       }
     }
@@ -377,9 +417,9 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
 #pragma unroll
         for (int i2 = 0; i2 < EP2; ++i2) {
           const int i0 = 2 * i2, i1 = 2 * i2 + 1;
-          l[i2].x = (i0 < nfull) ? ld[LPR * i0] : ((i0 == nfull && part_ok) ? ld[LPR * i0] : kNegBig);
+          l[i2].x = (i0 < nfull) ? ld[kofs(i0)] : ((i0 == nfull && part_ok) ? ld[kofs(i0)] : kNegBig);
           l[i2].y = (i1 >= EPL) ? kNegBig
-                                : ((i1 < nfull) ? ld[LPR * i1] : ((i1 == nfull && part_ok) ? ld[LPR * i1] : kNegBig));
+                                : ((i1 < nfull) ? ld[kofs(i1)] : ((i1 == nfull && part_ok) ? ld[kofs(i1)] : kNegBig));
           m = max3f(m, l[i2].x, l[i2].y);
         }
         m = row_max<LPR>(m);
@@ -436,6 +476,7 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
           rb[row_off[j]] = make_float2(lnp, Hval);
         }
       }
+      if (EARLY) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(ab_bar)) : "memory");
     }
     // ======================= pass C of tile it-1 (state in registers) ==================
     // Placed first in program order so that the carried registers die before pass A/B
@@ -449,7 +490,7 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
       const float2* rb = rowbuf + (pit % NSTAGE) * TS * A;
 
       if (SIP && BWD) {
-        mbar_wait(smem_u32(g_bar), (uint32_t)(pit & 1));  // the producer published dL/dlp of tile it-1
+        mbar_wait(smem_u32(&g_bar[pit & 1]), (uint32_t)((pit >> 1) & 1));  // the producer published dL/dlp of tile it-1
       } else {  // (forward: keeps the compute warps within one step of each other and of the producer)
         mbar_wait(cta_bar_a, (uint32_t)(pit & 1));  // every compute thread finished iteration it-1
       }
@@ -519,9 +560,9 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
           }
           const int i0 = 2 * i2, i1 = 2 * i2 + 1;
           float2 l;
-          l.x = (i0 < nfull) ? ldp[LPR * i0] : ((i0 == nfull && part_ok) ? ldp[LPR * i0] : kNegBig);
+          l.x = (i0 < nfull) ? ldp[kofs(i0)] : ((i0 == nfull && part_ok) ? ldp[kofs(i0)] : kNegBig);
           l.y = (i1 >= EPL) ? kNegBig
-                            : ((i1 < nfull) ? ldp[LPR * i1] : ((i1 == nfull && part_ok) ? ldp[LPR * i1] : kNegBig));
+                            : ((i1 < nfull) ? ldp[kofs(i1)] : ((i1 == nfull && part_ok) ? ldp[kofs(i1)] : kNegBig));
           const float2 t = fma2(l, L2, nmLc);
           x1.x = ex2f(t.x);
           x1.y = ex2f(t.y);
@@ -556,11 +597,11 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
               dv_rc += w.x + w.y;
             }
             const int i0 = 2 * i2, i1 = 2 * i2 + 1;
-            if (i0 < nfull) stp[LPR * i0] = d.x;
-            else if (i0 == nfull && part_ok) stp[LPR * i0] = d.x;
+            if (i0 < nfull) stp[kofs(i0)] = d.x;
+            else if (i0 == nfull && part_ok) stp[kofs(i0)] = d.x;
             if (i1 < EPL) {
-              if (i1 < nfull) stp[LPR * i1] = d.y;
-              else if (i1 == nfull && part_ok) stp[LPR * i1] = d.y;
+              if (i1 < nfull) stp[kofs(i1)] = d.y;
+              else if (i1 == nfull && part_ok) stp[kofs(i1)] = d.y;
             }
           }
         } else {
@@ -589,11 +630,11 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
               dv_rc += w.x + w.y;
             }
             const int i0 = 2 * i2, i1 = 2 * i2 + 1;
-            if (i0 < nfull) stp[LPR * i0] = d.x;
-            else if (i0 == nfull && part_ok) stp[LPR * i0] = d.x;
+            if (i0 < nfull) stp[kofs(i0)] = d.x;
+            else if (i0 == nfull && part_ok) stp[kofs(i0)] = d.x;
             if (i1 < EPL) {
-              if (i1 < nfull) stp[LPR * i1] = d.y;
-              else if (i1 == nfull && part_ok) stp[LPR * i1] = d.y;
+              if (i1 < nfull) stp[kofs(i1)] = d.y;
+              else if (i1 == nfull && part_ok) stp[kofs(i1)] = d.y;
             }
           }
         }
@@ -664,7 +705,7 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
         for (int h = 0; h < 2; ++h) {
           const int i = 2 * i2 + h;
           if (i < EPL && k_ok(i)) {
-            const int k = c + LPR * i;
+            const int k = c + kofs(i);
             red[(slot * 2 + 0) * AP + a * P + k] = h ? acc1[i2].y : acc1[i2].x;
             red[(slot * 2 + 1) * AP + a * P + k] = h ? acc2[i2].y : acc2[i2].x;
           }
@@ -687,34 +728,93 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
 }
 
 // Deterministic second stage over the per-CTA partials.
-// 32 columns x 8 partial groups per CTA: coalesced 128-byte reads, fixed summation order
-// (group g sums parts g, g+8, ...; groups are combined in order), ~80 CTAs instead of 5.
-__global__ void __launch_bounds__(256) head_finalize_kernel(const float* __restrict__ part,
-                                                            const float* __restrict__ loss_part,
-                                                            const float* __restrict__ logstd, float* __restrict__ dloc,
-                                                            float* __restrict__ dlogstd, float* __restrict__ loss, int AP,
-                                                            int nparts) {
-  __shared__ float sh[8][33];
+// 32 columns x kFinGroups partial groups per CTA: coalesced 128-byte reads; group g sums parts g, g+G, ... in that
+// order and the groups are combined in order, so the result is bit-reproducible.  Every thread issues ALL its loads
+// (<= kFinBatch per trip, one trip for <= G*kFinBatch partials) before the first add: one L2 round trip instead of the
+// dependent chain the round-1 kernel spent 12 us in.
+//
+// Optional peer push (N > 1, the sharded head's only exchange): the thread that owns a finished column writes
+// it into row `rank` of EVERY rank's gather buffer (remote stores over NVLink), and the last CTA of the grid -- ticket
+// counter -- publishes the call number with a system-scope release store into every rank's flag word.  The consumer
+// (pfpn_peer_gather_sum) then only reads LOCAL memory.
+constexpr int kFinGroups = 32;
+constexpr int kFinBatch = 10;
+struct HeadPushK {
+  float* out[8];   // peer p's gather row for THIS rank ([n] floats), p < nranks
+  int* flags[8];   // peer p's flag word for THIS rank
+  int* ticket;     // local CTA-arrival counter (self-resetting)
+  int nranks;      // 0 = no push
+  int value;
+};
+__global__ void __launch_bounds__(32 * kFinGroups) head_finalize_kernel(const float* __restrict__ part,
+                                                                        const float* __restrict__ loss_part,
+                                                                        const float* __restrict__ logstd, float* __restrict__ dloc,
+                                                                        float* __restrict__ dlogstd, float* __restrict__ loss, int AP,
+                                                                        int nparts, const HeadPushK push) {
+  __shared__ float sh[kFinGroups][33];
+  __shared__ int last_cta;
   const int col = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int idx = blockIdx.x * 32 + col;  // column in the [2*AP] partial row
+  const bool col_ok = idx < 2 * AP;
+  asm volatile("griddepcontrol.launch_dependents;");  // (push mode: lets pfpn_peer_gather_sum get resident and poll early)
+  const float ils = (col_ok && idx < AP && grp == 0) ? expf(-logstd[idx]) : 1.f;  // (parameter, not written by the head kernel)
   asm volatile("griddepcontrol.wait;" ::: "memory");  // the head kernel's partials are complete and visible
   float s = 0.f;
-  if (idx < 2 * AP)
-    for (int p = grp; p < nparts; p += 8) s += part[(size_t)p * 2 * AP + idx];
+  if (col_ok) {
+    for (int p0 = grp; p0 < nparts; p0 += kFinGroups * kFinBatch) {
+      float x[kFinBatch];
+#pragma unroll
+      for (int u = 0; u < kFinBatch; ++u) {
+        const int p = p0 + u * kFinGroups;
+        x[u] = p < nparts ? __ldcg(&part[(size_t)p * 2 * AP + idx]) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kFinBatch; ++u) s += x[u];
+    }
+  }
   sh[grp][col] = s;
+  float l = 0.f;
+  const bool loss_warp = loss != nullptr && blockIdx.x == 0 && grp == 1;
+  if (loss_warp) {  // one warp sums the per-CTA loss terms (fixed order)
+    for (int p0 = col; p0 < nparts; p0 += 32 * kFinBatch) {
+      float x[kFinBatch];
+#pragma unroll
+      for (int u = 0; u < kFinBatch; ++u) {
+        const int p = p0 + u * 32;
+        x[u] = p < nparts ? __ldcg(&loss_part[p]) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kFinBatch; ++u) l += x[u];
+    }
+  }
   __syncthreads();
-  if (grp == 0 && idx < 2 * AP) {
+  if (grp == 0 && col_ok) {
     float t = 0.f;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) t += sh[g][col];
-    if (idx < AP) dloc[idx] = t * expf(-logstd[idx]);
-    else dlogstd[idx - AP] = t;
+    for (int g = 0; g < kFinGroups; ++g) t += sh[g][col];
+    t *= ils;
+    if (idx < AP) {
+      if (dloc != nullptr) dloc[idx] = t;
+    } else if (dlogstd != nullptr) {
+      dlogstd[idx - AP] = t;
+    }
+    for (int p = 0; p < push.nranks; ++p) push.out[p][idx] = t;
   }
-  if (loss != nullptr && blockIdx.x == 0 && grp == 1) {  // one warp sums the per-CTA loss terms
-    float l = 0.f;
-    for (int p = col; p < nparts; p += 32) l += loss_part[p];
+  if (loss_warp) {
     for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
     if (col == 0) *loss = l;
+  }
+  if (push.nranks > 0) {
+    // every CTA: my remote stores are ordered before my ticket; the last CTA of the grid raises the flags
+    if (grp == 0) __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last_cta = (atomicAdd(push.ticket, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (last_cta && threadIdx.x < push.nranks) {
+      if (threadIdx.x == 0) *push.ticket = 0;  // next call starts from zero again (stream-ordered after this grid)
+      __threadfence_system();
+      asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(push.flags[threadIdx.x]), "r"(push.value) : "memory");
+    }
   }
 }
 
@@ -797,6 +897,9 @@ static const HeadVariant kHeadVariants[] = {
     // PPO .183 vs .185); the lean GRAD mode stays on 4 lanes per row with carried terms (.179 vs .183).
     PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 4, 288, 96, 35, 36, 3, 1 | 2 | 4),
     PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, 1, 8),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 4, 288, 96, 35, 36, 7, 0),   // [2] split ownership (bank-conflict-free)
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 4, 288, 96, 35, 36, 11, 0),  // [3] early dL/dlp
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 4, 288, 96, 35, 36, 15, 0),  // [4] both
     PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 6, 288, 96, 35, 36, 1, 0),
     PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, 0, 0),
     PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 5, 144, 128, 35, 36, 1, 0),
@@ -860,7 +963,7 @@ static int plan_head(int A, int P, int km, HeadLaunch* L) {
   L->ts = slots * v.rpt;
   L->threads = ((slots * per_slot + 31) & ~31) + 32;  // + the TMA producer warp
   const int stage_bytes = (L->ts * A * P * 4 + L->ts * A * 4 + 127) & ~127;  // logits tile + its action values
-  L->smem_bytes = v.nstage * stage_bytes + 8 * (v.nstage + 2) + v.nstage * L->ts * A * 8 + (kHeadMaxWarps + 256) * 4 +
+  L->smem_bytes = v.nstage * stage_bytes + 8 * (v.nstage + 4) + v.nstage * L->ts * A * 8 + (kHeadMaxWarps + 256) * 4 +
                   (v.lpr * v.epl + 1) * 4 + 16 + ((v.csm & 1) ? ((v.epl + 1) / 2) * 3 * per_slot * 8 : 0);
   L->fn = v.fn[km];
   int dev = 0;
@@ -919,8 +1022,8 @@ extern "C" int pfpn_head_launch_info(int32_t A, int32_t P, uint32_t mode, int32_
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-extern "C" int pfpn_head_logprob(const pfpn_head_args* args, void* workspace, size_t workspace_bytes,
-                                 pfpn_stream_t stream_) {
+static int head_logprob_impl(const pfpn_head_args* args, void* workspace, size_t workspace_bytes, const pfpn_head_push* push,
+                             pfpn_stream_t stream_) {
   if (args == nullptr) return PFPN_ERR_ARG;
   const pfpn_head_args& a = *args;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -929,7 +1032,21 @@ extern "C" int pfpn_head_logprob(const pfpn_head_args* args, void* workspace, si
   if (a.B == 0) return PFPN_OK;
   if (!a.logits || !a.loc || !a.logstd || !a.value || !a.lp) return PFPN_ERR_ARG;
   const bool bwd = a.mode != PFPN_HEAD_FWD;
-  if (bwd && (!a.dlogits || !a.dloc || !a.dlogstd)) return PFPN_ERR_ARG;
+  if (bwd && !a.dlogits) return PFPN_ERR_ARG;
+  if (bwd && push == nullptr && (!a.dloc || !a.dlogstd)) return PFPN_ERR_ARG;  // (with a push the local copies are optional)
+  HeadPushK pk;
+  memset(&pk, 0, sizeof(pk));
+  if (push != nullptr) {
+    if (!bwd || push->nranks < 1 || push->nranks > 8 || !push->ticket || push->value < 1) return PFPN_ERR_ARG;
+    for (int p = 0; p < push->nranks; ++p) {
+      if (!push->out[p] || !push->flags[p]) return PFPN_ERR_ARG;
+      pk.out[p] = push->out[p];
+      pk.flags[p] = push->flags[p];
+    }
+    pk.ticket = push->ticket;
+    pk.nranks = push->nranks;
+    pk.value = push->value;
+  }
   if (a.mode == PFPN_HEAD_GRAD && !a.g_lp) return PFPN_ERR_ARG;
   if (a.mode == PFPN_HEAD_PPO && (!a.adv || !a.lp_old || !a.loss)) return PFPN_ERR_ARG;
   if (!aligned16(a.logits) || !aligned16(a.value) || (bwd && !aligned16(a.dlogits))) return PFPN_ERR_ALIGN;
@@ -962,12 +1079,22 @@ extern "C" int pfpn_head_logprob(const pfpn_head_args* args, void* workspace, si
   PFPN_CUDA_OK(launch_pdl(L.fn, dim3(grid), dim3(L.threads), (size_t)L.smem_bytes, stream, kp));
   if (bwd) {
     const int blocks = (int)((2 * AP + 31) / 32);
-    PFPN_CUDA_OK(launch_pdl(head_finalize_kernel, dim3(blocks), dim3(256), (size_t)0, stream, (const float*)kp.part,
-                            (const float*)kp.loss_part, (const float*)a.logstd, a.dloc, a.dlogstd,
-                            a.mode == PFPN_HEAD_PPO ? a.loss : (float*)nullptr, (int)AP, grid));
-    
+    PFPN_CUDA_OK(launch_pdl(head_finalize_kernel, dim3(blocks), dim3(32 * kFinGroups), (size_t)0, stream,
+                            (const float*)kp.part, (const float*)kp.loss_part, (const float*)a.logstd, a.dloc, a.dlogstd,
+                            a.mode == PFPN_HEAD_PPO ? a.loss : (float*)nullptr, (int)AP, grid, pk));
   }
   return PFPN_OK;
+}
+
+extern "C" int pfpn_head_logprob(const pfpn_head_args* args, void* workspace, size_t workspace_bytes,
+                                 pfpn_stream_t stream_) {
+  return head_logprob_impl(args, workspace, workspace_bytes, nullptr, stream_);
+}
+
+extern "C" int pfpn_head_logprob_push(const pfpn_head_args* args, void* workspace, size_t workspace_bytes,
+                                      const pfpn_head_push* push, pfpn_stream_t stream_) {
+  if (push == nullptr) return PFPN_ERR_ARG;
+  return head_logprob_impl(args, workspace, workspace_bytes, push, stream_);
 }
 
 extern "C" int pfpn_adv_stats(const float* adv, int32_t B, float* stats, pfpn_stream_t stream_) {

@@ -67,11 +67,13 @@ def adv_stats(adv: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
 def head_call(mode: int, logits, loc, logstd, value, *, tanh=False, g_lp=None, g_ent_ba=None,
               g_ent: float = 0.0, adv=None, lp_old=None, adv_stats_t=None, eps_clip: float = 0.2,
               loss_scale: float = 0.0, want_ent_ba=False, want_dvalue=False, dlogits_out=None,
-              out: Optional[dict] = None) -> dict:
+              out: Optional[dict] = None, push=None) -> dict:
     """One launch of K1.  Returns a dict of freshly written tensors.
 
     ``out`` may carry preallocated ``lp, ent, dlogits, dloc, dlogstd, loss``
     tensors (bench / CUDA-graph use) -- then nothing is allocated here.
+    ``push`` (a ``pfpn_b200.peer.PeerGather``): data-parallel form -- the finalize kernel also stores dloc / dlogstd
+    into every rank's gather buffer; follow with ``push.reduce(...)``.
     """
     logits = _f32c(logits, "logits")
     B, A, P = logits.shape
@@ -137,5 +139,9 @@ def head_call(mode: int, logits, loc, logstd, value, *, tanh=False, g_lp=None, g
     nbytes = head_workspace_bytes(A, P)
     ws = _ws(dev, nbytes)
     with torch.cuda.device(dev):
-        _cabi.check(_cabi.pfpn_head_logprob(C.byref(a), ws.data_ptr(), ws.numel(), _stream_ptr()))
+        if push is not None and mode != _cabi.HEAD_FWD:
+            _cabi.check(_cabi.pfpn_head_logprob_push(C.byref(a), ws.data_ptr(), ws.numel(), C.byref(push.push_args()),
+                                                     _stream_ptr()))
+        else:
+            _cabi.check(_cabi.pfpn_head_logprob(C.byref(a), ws.data_ptr(), ws.numel(), _stream_ptr()))
     return out

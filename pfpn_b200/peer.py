@@ -1,14 +1,14 @@
-"""Peer-memory plumbing for the fused all-reduce + Adam kernel (csrc/comm.cu).
+"""Peer-memory plumbing for the kernels that exchange over NVLink (csrc/comm.cu, K1's finalize).
 
-Every rank owns a double-buffered staging area for its [gradient | statistics] bucket and an int32
-flag array, allocated by the library (cudaMalloc) and exported through CUDA IPC; the 64-byte handles
-travel over torch.distributed and every rank maps its peers' buffers into its own device context
-(cudaIpcOpenMemHandle with lazy peer access).  torch only wraps the local buffer as a tensor.
+Every rank owns staging / gather buffers and an int32 flag array, allocated by the library (cudaMalloc) and exported
+through CUDA IPC; the 64-byte handles travel over torch.distributed and every rank maps its peers' buffers into its own
+device context (cudaIpcOpenMemHandle with lazy peer access).  torch only wraps the local buffer as a tensor.
+The mapping outcome is COLLECTIVE: either every rank maps every peer, or every rank raises (callers fall back to NCCL).
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import List
+from typing import List, Sequence
 
 import torch
 import torch.distributed as dist
@@ -27,48 +27,52 @@ def _alloc(nbytes: int):
     return ptr.value, handle.raw
 
 
+def _share(local: Sequence, device: torch.device, group) -> List[List[int]]:
+    """local = [(ptr, handle), ...] of this rank; returns ptrs[k][r] = rank r's k-th buffer mapped into this process."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world > 8:
+        raise ValueError("the peer-memory kernels cover one NVSwitch node (<= 8 ranks)")
+    gathered: List = [None] * world
+    dist.all_gather_object(gathered, tuple(h for _, h in local), group=group)
+    ptrs = [[0] * world for _ in local]
+    err = None
+    for r, handles in enumerate(gathered):
+        for k, h in enumerate(handles):
+            if r == rank:
+                ptrs[k][r] = local[k][0]
+                continue
+            p = C.c_void_p()
+            try:  # (a peer on another host / without P2P: cudaIpcOpenMemHandle fails on THIS rank only)
+                _cabi.check(_cabi.pfpn_peer_open(h, C.byref(p)))
+            except Exception as e:  # noqa: BLE001 -- reported collectively below
+                err = e
+            ptrs[k][r] = p.value or 0
+    ok = torch.tensor([0 if err is not None else 1], device=device, dtype=torch.int32)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 0:
+        raise RuntimeError(f"peer-memory mapping failed on at least one rank ({err!r}): CUDA IPC + P2P need all ranks on "
+                           "one NVLink/NVSwitch node")
+    dist.barrier(group=group)
+    return ptrs
+
+
 class PeerBuckets:
+    """PULL protocol of the fused all-reduce + Adam (pfpn_peer_allreduce_adam[_rs]): every rank publishes its bucket in
+    its own double-buffered staging area; the kernels read the peers' staging areas."""
+
     def __init__(self, n_total: int, device: torch.device, group=None, with_reduced: bool = False):
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        if self.world > 8:
-            raise ValueError("peer all-reduce covers one NVSwitch node (<= 8 ranks)")
         self.n_total, self.dev, self.group = n_total, device, group
         with torch.cuda.device(device):
-            self._stage_ptr, h_stage = _alloc(2 * n_total * 4)
-            self._flag_ptr, h_flag = _alloc(64 * 4)
+            stage = _alloc(2 * n_total * 4)
+            flag = _alloc(64 * 4)
             # averaged-slice buffer of the two-phase all-reduce (pfpn_peer_allreduce_adam_rs); tiny dummy otherwise
-            self._red_ptr, h_red = _alloc((n_total if with_reduced else 4) * 4)
+            red = _alloc((n_total if with_reduced else 4) * 4)
+            self._stage_ptr, self._flag_ptr, self._red_ptr = stage[0], flag[0], red[0]
             self.stage = torch.as_tensor(_CudaArray(self._stage_ptr, 2 * n_total, "<f4"), device=device).view(2, n_total)
-            gathered: List = [None] * self.world
-            dist.all_gather_object(gathered, (h_stage, h_flag, h_red), group=group)
-            stage_ptrs, flag_ptrs, red_ptrs = [], [], []
-            err = None
-            for r, (hs, hf, hr) in enumerate(gathered):
-                if r == self.rank:
-                    stage_ptrs.append(self._stage_ptr)
-                    flag_ptrs.append(self._flag_ptr)
-                    red_ptrs.append(self._red_ptr)
-                    continue
-                ps, pf, pr = C.c_void_p(), C.c_void_p(), C.c_void_p()
-                try:  # (a peer on another host / without P2P: cudaIpcOpenMemHandle fails on THIS rank only)
-                    _cabi.check(_cabi.pfpn_peer_open(hs, C.byref(ps)))
-                    _cabi.check(_cabi.pfpn_peer_open(hf, C.byref(pf)))
-                    _cabi.check(_cabi.pfpn_peer_open(hr, C.byref(pr)))
-                except Exception as e:  # noqa: BLE001 -- reported collectively below
-                    err = e
-                stage_ptrs.append(ps.value or 0)
-                flag_ptrs.append(pf.value or 0)
-                red_ptrs.append(pr.value or 0)
-            # the outcome must be COLLECTIVE: either every rank maps every peer or every rank raises (and the caller
-            # falls back to the NCCL path on all ranks together)
-            ok = torch.tensor([0 if err is not None else 1], device=device, dtype=torch.int32)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-            if int(ok.item()) == 0:
-                raise RuntimeError(f"peer-memory mapping failed on at least one rank ({err!r}): CUDA IPC + P2P need all "
-                                   "ranks on one NVLink/NVSwitch node")
-        dist.barrier(group=group)
+            stage_ptrs, flag_ptrs, red_ptrs = _share([stage, flag, red], device, group)
         self._flag_ptrs = (C.c_void_p * self.world)(*flag_ptrs)
-        self.calls = 0  # exchange calls issued on these buffers (flag value / buffer parity / CTA-counter epoch)
+        self.calls = 0  # exchange calls issued on these buffers (flag value / buffer parity)
         self.reduced_ptrs = (C.c_void_p * self.world)(*red_ptrs)
         self._bucket_ptrs = [(C.c_void_p * self.world)(*[p + par * n_total * 4 for p in stage_ptrs]) for par in (0, 1)]
 
@@ -77,8 +81,8 @@ class PeerBuckets:
 
 
 class PeerSum:
-    """The sharded head's [2, A, P] exchange over peer memory (`pfpn_peer_allreduce_sum`): the caller lets
-    K1's finalize kernel write dloc / dlogstd straight into ``slot(parity)`` and then calls ``reduce``."""
+    """The sharded head's [2, A, P] exchange, pull form (`pfpn_peer_allreduce_sum`): the caller writes dloc / dlogstd into
+    ``slot()`` and then calls ``reduce``.  Kept as the comparison point of ``PeerGather``."""
 
     def __init__(self, n: int, device: torch.device, group=None):
         if n % 4:
@@ -95,4 +99,48 @@ class PeerSum:
         buckets, flags = self.pb.ptrs(self.calls & 1)
         _cabi.check(_cabi.pfpn_peer_allreduce_sum(buckets, flags, self.pb.rank, self.pb.world, self.calls, self.n,
                                                   out.data_ptr(), scale, stream_ptr))
+        return out
+
+
+class PeerGather:
+    """PUSH protocol for the sharded head's [2, A, P] exchange (`pfpn_head_logprob_push` + `pfpn_peer_gather_sum`): K1's
+    finalize kernel stores this rank's dloc / dlogstd into row `rank` of EVERY rank's gather buffer and raises the flags;
+    ``reduce`` waits for the N flags and sums the N local rows in rank order.  No exchange kernel sits behind K1.
+
+    Per rank: gather [2 parities][world][n] floats, flags int32[64] (word r = last call rank r pushed), one local ticket."""
+
+    def __init__(self, n: int, device: torch.device, group=None):
+        if n % 4:
+            raise ValueError("n must be a multiple of 4 floats")
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.n, self.calls, self.dev = n, 0, device
+        with torch.cuda.device(device):
+            gather = _alloc(2 * self.world * n * 4)
+            flag = _alloc(64 * 4)
+            self._gather_ptr, self._flag_ptr = gather[0], flag[0]
+            self._gather_ptrs, self._flag_ptrs = _share([gather, flag], device, group)
+        self.gather = torch.as_tensor(_CudaArray(self._gather_ptr, 2 * self.world * n, "<f4"), device=device).view(2, self.world, n)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
+        self._push = [self._make_push(par) for par in (0, 1)]
+
+    def _make_push(self, parity: int):
+        p = _cabi.HeadPush()
+        for r in range(self.world):
+            p.out[r] = self._gather_ptrs[r] + ((parity * self.world + self.rank) * self.n) * 4
+            p.flags[r] = self._flag_ptrs[r] + 4 * self.rank
+        p.ticket = self.ticket.data_ptr()
+        p.nranks = self.world
+        return p
+
+    def push_args(self):
+        """The `pfpn_head_push` of the NEXT exchange (pass to pfpn_head_logprob_push, then call ``reduce``)."""
+        p = self._push[(self.calls + 1) & 1]
+        p.value = self.calls + 1
+        return p
+
+    def reduce(self, out: torch.Tensor, scale: float = 1.0, stream_ptr: int = 0):
+        self.calls += 1
+        par = self.calls & 1
+        _cabi.check(_cabi.pfpn_peer_gather_sum(self._gather_ptr + par * self.world * self.n * 4, self._flag_ptr, self.world,
+                                               self.calls, self.n, out.data_ptr(), scale, stream_ptr))
         return out

@@ -183,3 +183,37 @@ def test_full_size_shard_linearity(cuda_dev):
     shifted = head.head_call(_cabi.HEAD_FWD, logits + 3.0, loc, logstd, value)
     assert rel(shifted["lp"], full["lp"]) < 1e-5
     assert math.isfinite(float(full["dloc"].abs().sum()))
+
+
+def test_push_form_single_rank_equals_plain_call(cuda_dev):
+    """pfpn_head_logprob_push + pfpn_peer_gather_sum (the data-parallel form of K1's [2,A,P] output) on a world of one
+    rank: the finalize kernel's push / ticket / flag protocol and the gather-sum consumer, over several calls (both
+    buffer parities), must reproduce the plain call's dloc / dlogstd bit for bit."""
+    import socket
+    import torch.distributed as dist
+    from pfpn_b200.head import _stream_ptr
+    from pfpn_b200.peer import PeerGather
+    created = False
+    if not dist.is_initialized():
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1, device_id=cuda_dev)
+        created = True
+    try:
+        B, A, P = 1000, 36, 35
+        d = {k: (v.to(cuda_dev) if torch.is_tensor(v) else v) for k, v in synth.head_inputs(B, A, P, seed=9).items()}
+        pg = PeerGather(2 * A * P, cuda_dev)
+        out = torch.empty(2 * A * P, device=cuda_dev)
+        for it in range(5):
+            g_lp = torch.randn(B, device=cuda_dev) / B
+            ref = head.head_call(_cabi.HEAD_GRAD, d["logits"], d["loc"], d["logstd"], d["value"], g_lp=g_lp)
+            o = head.head_call(_cabi.HEAD_GRAD, d["logits"], d["loc"], d["logstd"], d["value"], g_lp=g_lp, push=pg)
+            pg.reduce(out, 1.0, _stream_ptr())
+            torch.cuda.synchronize()
+            assert torch.equal(o["dloc"], ref["dloc"]) and torch.equal(o["dlogstd"], ref["dlogstd"])
+            assert torch.equal(out[:A * P].view(A, P), ref["dloc"]) and torch.equal(out[A * P:].view(A, P), ref["dlogstd"])
+            assert int(pg.ticket.item()) == 0  # self-resetting CTA counter
+    finally:
+        if created:
+            dist.destroy_process_group()

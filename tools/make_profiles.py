@@ -55,6 +55,8 @@ if os.path.exists(rep):
         return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
     js = {"kernel": get("Kernel Name"), "dram_bytes_read": tobytes("dram__bytes_read.sum"), "dram_bytes_write": tobytes("dram__bytes_write.sum"),
           "gpu_time_us_under_ncu": float(get("gpu__time_duration.sum").replace(",", "")), "round": rnd,
+          # bench.py nulls roofline.traffic when the kernel source no longer matches the one this capture was taken on
+          "source_sha256": __import__("hashlib").sha256(open(os.path.join(ROOT, "pfpn_b200", "csrc", "head_logprob.cu"), "rb").read()).hexdigest(),
           "command": "ncu --set full --clock-control none --import-source on -k regex:head_kernel -s 6 -c 1 python tools/time_head.py  (B=65536, A=36, P=35, PPO fwd+bwd)"}
     json.dump(js, open(os.path.join(out, "head_kernel_ncu.json"), "w"), indent=1)
     with open(os.path.join(out, f"{rnd}_head_kernel.md"), "w") as f:

@@ -69,5 +69,37 @@ dist.barrier(); e0.record()
 for _ in range(50): dist.all_reduce(buf)
 e1.record(); torch.cuda.synchronize(); t_nccl = e0.elapsed_time(e1) / 50
 out.update(small_sum_ok=ok_sum, ms_small_sum_peer=round(t_peer, 4), ms_small_sum_nccl=round(t_nccl, 4))
+# ---- the PUSH form: K1's finalize kernel stores dloc / dlogstd into every rank's gather row (pfpn_head_logprob_push),
+#      pfpn_peer_gather_sum sums the local rows in rank order; vs NCCL on the same per-rank contributions ----------------
+from pfpn_b200 import _cabi, head
+from pfpn_b200.peer import PeerGather
+Bh = 4096 + 64 * rank  # ragged shards
+lg = torch.randn(Bh, A, P, device=dev, generator=g) * 2
+locp, lsp = make().loc.clone(), make().logstd.clone()
+val = torch.rand(Bh, A, device=dev, generator=g) * 2 - 1
+glp = torch.randn(Bh, device=dev, generator=g) / Bh
+pg = PeerGather(n, dev)
+ok_push, outg = True, torch.empty(n, device=dev)
+for it in range(5):
+    glp = glp * (1.0 + 0.1 * it)
+    o = head.head_call(_cabi.HEAD_GRAD, lg, locp, lsp, val, g_lp=glp, push=pg)
+    pg.reduce(outg, 1.0, _stream_ptr())
+    mine = torch.cat([o["dloc"].reshape(-1), o["dlogstd"].reshape(-1)])
+    allc = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allc, mine)
+    ordered = allc[0].clone()
+    for r in range(1, world):
+        ordered += allc[r]
+    ok_push = ok_push and bool(torch.equal(outg, ordered))  # bit-equal to the rank-ordered sum, on every rank
+torch.cuda.synchronize(); dist.barrier()
+e0.record()
+for _ in range(30):
+    head.head_call(_cabi.HEAD_GRAD, lg, locp, lsp, val, g_lp=glp, push=pg, out=o); pg.reduce(outg, 1.0, _stream_ptr())
+e1.record(); torch.cuda.synchronize(); t_push = e0.elapsed_time(e1) / 30
+e0.record()
+for _ in range(30):
+    head.head_call(_cabi.HEAD_GRAD, lg, locp, lsp, val, g_lp=glp, out=o)
+e1.record(); torch.cuda.synchronize(); t_nopush = e0.elapsed_time(e1) / 30
+out.update(push_sum_ok=ok_push, ms_head_with_push_exchange=round(t_push, 4), ms_head_alone=round(t_nopush, 4))
 print(json.dumps(out), flush=True)
 dist.barrier(); dist.destroy_process_group()
