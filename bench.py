@@ -414,29 +414,43 @@ def main():
         lpo_ = lp_ + 0.05 * torch.randn(Bs, device=dev, generator=g)
         adv_ = torch.randn(Bs, device=dev, generator=g)
 
-        def upd():
+        from pfpn_b200.learner import GraphedUpdate
+
+        def time_updates(fn, n):
+            barrier()
+            u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            u0.record(stream)
+            for _ in range(n):
+                fn()
+            u1.record(stream)
+            barrier()
+            return maxr(u0.elapsed_time(u1) / n)
+
+        def upd_eager():
             net.compute_gradients(st_, ac_, v_, lpo_, adv_)
             opt.apply_gradients(net)
         for _ in range(3):
-            upd()
-        barrier()
-        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        u0.record(stream)
-        for _ in range(args.dppo_steps):
-            upd()
-        u1.record(stream)
-        barrier()
-        um = maxr(u0.elapsed_time(u1) / args.dppo_steps)
-        dppo = {"workload": f"DPPO minibatch update, B_total={B_PER_GPU} sharded over {world} GPU(s): 197-1024-512 actor+critic trunk (tcgen05 3xTF32 GEMMs), PFPN head, local clip, all-reduce of the 8.4 MB bucket fused into Adam over NVLink peer memory (N>1)",
+            upd_eager()
+        um_eager = time_updates(upd_eager, args.dppo_steps)
+        # the same update captured once in a CUDA graph (device-resident step counters) and replayed
+        gu = GraphedUpdate(net, opt, Bs, warmup=0)
+        gu._set(st_, ac_, v_, lpo_, adv_)
+        gu.run()  # capture + first replay
+        for _ in range(2):
+            gu.run()
+        um = time_updates(gu.run, args.dppo_steps)
+        dppo = {"workload": f"DPPO minibatch update, B_total={B_PER_GPU} sharded over {world} GPU(s): 197-1024-512 actor+critic trunk (tcgen05 3xTF32 GEMMs, critic on a parallel graph branch), PFPN head, local clip -> staged bucket -> rank-ordered mean over NVLink peer memory -> Adam: 3 launches; whole update replayed as ONE CUDA graph",
                 "ms_per_update": um, "samples_per_s": B_PER_GPU / (um * 1e-3), "scaling": "strong",
                 "trunk_tflops": 12.6e6 * B_PER_GPU / (um * 1e-3) / 1e12,
-                "launches_per_update": getattr(opt, "launches_last_step", None)}
+                "ms_per_update_eager": um_eager, "optimizer_chain_launches": getattr(opt, "launches_last_step", None),
+                "exchange": opt._mode + (f", {'two' if world >= int(os.environ.get('PFPN_PEER_TWO_PHASE_MIN', '6')) else 'one'}-phase peer kernel" if world > 1 else "")}
         if world > 1:
-            # one more update from IDENTICAL state through each exchange implementation: NCCL all-reduce + Adam,
-            # the one-phase peer kernel and the two-phase (reduce-scatter + all-gather) peer kernel
+            # one more update from IDENTICAL state through each exchange implementation: the round-1 chain with an NCCL
+            # all-reduce, and the 3-launch step with the one-phase and the two-phase (reduce-scatter + all-gather) kernel
             snap_n, snap_o = net.state_dict(), opt.state_dict()
             results = {}
-            for name, fused, two_phase_min in (("nccl", False, "99"), ("peer_one_phase", True, "99"), ("peer_two_phase", True, "2")):
+            for name, fused, sync_step, two_phase_min in (("nccl", False, "0", "99"), ("peer_one_phase", True, "1", "99"),
+                                                          ("peer_two_phase", True, "1", "2")):
                 if fused and not opt.fused_peer:
                     continue
                 net.load_state_dict(snap_n)
@@ -446,20 +460,23 @@ def main():
                 if fused:
                     o2._peers = opt._peers  # same peer-mapped buffers (their call counter carries on)
                 os.environ["PFPN_PEER_TWO_PHASE_MIN"] = two_phase_min
+                os.environ["PFPN_SYNC_STEP"] = sync_step
                 net.compute_gradients(st_, ac_, v_, lpo_, adv_)
                 o2.apply_gradients(net)
                 torch.cuda.synchronize()
-                results[name] = (net.params.clone(), o2.m.clone(), o2.v.clone())
+                results[name] = (net.params.clone(), o2.m.clone(), o2.v.clone(), net.state_mean.clone())
             os.environ.pop("PFPN_PEER_TWO_PHASE_MIN", None)
+            os.environ.pop("PFPN_SYNC_STEP", None)
             ref_p = results["nccl"][0]
-            for name, (p_, m_, v2_) in results.items():
-                hh = torch.cat([tensor_hash(p_), tensor_hash(m_), tensor_hash(v2_)])
+            for name, (p_, m_, v2_, sm_) in results.items():
+                hh = torch.cat([tensor_hash(p_), tensor_hash(m_), tensor_hash(v2_), tensor_hash(sm_)])
                 hs = [torch.empty_like(hh) for _ in range(world)]
                 dist.all_gather(hs, hh)
                 xcheck[f"{name}_replica_hash_equal"] = all(torch.equal(x, hs[0]) for x in hs)
                 if name != "nccl":
                     d_ = (p_ - ref_p).abs().max() / (ref_p - snap_n["params"]).abs().max().clamp_min(1e-30)
                     xcheck[f"{name}_vs_nccl_rel_update_diff"] = float(d_)
+                    xcheck[f"{name}_vs_nccl_state_mean_max_abs"] = float((sm_ - results["nccl"][3]).abs().max())
     clocks = sampler.stop() if sampler else None
 
     # ---- BASELINE c2 / c3 / c5 at this run's N ---------------------------------------------------------------------

@@ -284,6 +284,13 @@ int pfpn_state_normalize(const float* state, const float* mean, const float* std
  * Replaces: online_normalizer(moving_average=True)   networks/utils.py:60-68 */
 int pfpn_normalizer_update(const float* state, float* mean, float* std, int32_t B, int32_t S, float step,
                            float* scratch, pfpn_stream_t stream);
+/* Graph-capturable form: the step (the network's global_step) is read from DEVICE memory, inputs and outputs are
+ * separate buffers (the pushed statistics are computed from the pre-update values and applied after aggregation:
+ * LocalUpdateHookPre, models/sync_model.py:123-138).  Coalesced fp64 partial sums, fixed order. */
+int pfpn_normalizer_scratch_bytes(int32_t S, size_t* bytes);
+int pfpn_normalizer_update_dev(const float* state, const float* mean_in, const float* std_in, float* mean_out,
+                               float* std_out, int32_t B, int32_t S, const int32_t* global_step, void* scratch,
+                               size_t scratch_bytes, pfpn_stream_t stream);
 /* loss[0] = scale * sum((v - (adv + v_old))^2); dv = coef * 2 (v - target) * scale  (scale = 1/B).
  * Replaces: ClipPPONetwork.build_value_loss / setup_value_target_tensor   ppo.py:31-42 */
 int pfpn_value_loss(const float* v, const float* adv, const float* v_old, float* dv, float* loss, int32_t B,
@@ -357,6 +364,45 @@ int pfpn_peer_allreduce_adam_rs(const float* const* buckets, float* const* reduc
  * protocol as above; `value` = call counter, +1 per call, buffers alternate by its parity). */
 int pfpn_peer_allreduce_sum(const float* const* buckets, int32_t* const* flags, int32_t rank, int32_t nranks,
                             int32_t value, size_t n, float* out, float scale, pfpn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * The whole data-parallel optimizer step, graph-capturable: local clip_by_global_norm -> this rank's scaled gradients and
+ * the four pushed statistics staged in peer-visible memory -> flags -> rank-ordered sum over the N ranks out of NVLink
+ * peer memory -> mean -> Adam -> averaged statistics assigned.  THREE launches; nothing in the arguments changes from
+ * step to step: the exchange call number (flag value / staging parity), the Adam step and the network's global_step live
+ * in DEVICE memory (`counters`, int32[4] = {calls, adam_step, global_step, ticket}; the first kernel increments the
+ * first three), so one CUDA graph of the update can be replayed.
+ * Replaces: clip_grads (models/workers/base_worker.py:97-102) + SyncReplicasOptimizer accumulators
+ *           (models/sync_model.py:37-45,92-96) + ApplyAdam (base_worker.py:64-70).
+ * Statistics tail of the bucket: [new_mean S][new_std S][max_active AP][sum_active AP]; S == 0 / AP == 0 drop a part.
+ * nranks == 1: no peers, gradients scaled in place.  two_phase != 0: reduce-scatter + all-gather form (N >= 3).
+ * ---------------------------------------------------------------------- */
+typedef struct pfpn_sync_args {
+  float* grads;            /* [n_total] this rank's bucket: gradients in [0, n_params)                           */
+  size_t n_params, n_total;
+  float clip;              /* <= 0: norm only                                                                    */
+  const float* new_mean;   /* [S] this minibatch's moving-average state statistics (pushed)                      */
+  const float* new_std;    /* [S]                                                                                */
+  float* state_mean;       /* [S] receives the accumulator mean                                                  */
+  float* state_std;        /* [S]                                                                                */
+  float* max_active;       /* [AP] pushed AND assigned (averaged, not max-reduced: a reference quirk)            */
+  float* sum_active;       /* [AP]                                                                               */
+  int32_t S, AP;
+  float* params;           /* [n_params]                                                                         */
+  float* m;                /* [n_params] Adam slots                                                              */
+  float* v;
+  float lr, beta1, beta2, eps;
+  int32_t* counters;       /* device int32[4], see above                                                         */
+  float* norm_scale;       /* [2] out: {global norm, applied scale}                                              */
+  void* scratch;           /* pfpn_sync_step_scratch_bytes, 8-byte aligned                                       */
+  size_t scratch_bytes;
+  float* const* stage;     /* HOST array [nranks]: rank r's staging base, 2 * n_total floats (peer-mapped)       */
+  float* const* reduced;   /* HOST array [nranks]: rank r's averaged-slice buffer, n_total floats (two_phase)    */
+  int32_t* const* flags;   /* HOST array [nranks]: rank r's flag words, int32[64], zero-initialised              */
+  int32_t rank, nranks, two_phase;
+} pfpn_sync_args;
+int pfpn_sync_step_scratch_bytes(size_t* bytes);
+int pfpn_sync_step(const pfpn_sync_args* args, pfpn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -53,6 +53,20 @@ class HeadPush(C.Structure):
                 ("nranks", C.c_int32), ("value", C.c_int32)]
 
 
+class SyncArgs(C.Structure):
+    """Mirror of ``pfpn_sync_args``."""
+    _fields_ = [
+        ("grads", C.c_void_p), ("n_params", C.c_size_t), ("n_total", C.c_size_t), ("clip", C.c_float),
+        ("new_mean", C.c_void_p), ("new_std", C.c_void_p), ("state_mean", C.c_void_p), ("state_std", C.c_void_p),
+        ("max_active", C.c_void_p), ("sum_active", C.c_void_p), ("S", C.c_int32), ("AP", C.c_int32),
+        ("params", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("counters", C.c_void_p), ("norm_scale", C.c_void_p), ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t),
+        ("stage", C.c_void_p), ("reduced", C.c_void_p), ("flags", C.c_void_p),
+        ("rank", C.c_int32), ("nranks", C.c_int32), ("two_phase", C.c_int32),
+    ]
+
+
 def _sig(name, restype, argtypes):
     fn = getattr(lib, name)
     fn.restype = restype
@@ -149,6 +163,8 @@ pfpn_mlp_linear_bwd_weight = _sig("pfpn_mlp_linear_bwd_weight", C.c_int,
                                   [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, C.c_size_t, _vp])
 pfpn_state_normalize = _sig("pfpn_state_normalize", C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _f, _i32, _vp])
 pfpn_normalizer_update = _sig("pfpn_normalizer_update", C.c_int, [_vp, _vp, _vp, _i32, _i32, _f, _vp, _vp])
+pfpn_normalizer_scratch_bytes = _sig("pfpn_normalizer_scratch_bytes", C.c_int, [_i32, C.POINTER(C.c_size_t)])
+pfpn_normalizer_update_dev = _sig("pfpn_normalizer_update_dev", C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, C.c_size_t, _vp])
 pfpn_value_loss = _sig("pfpn_value_loss", C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _f, _f, _vp])
 pfpn_gae = _sig("pfpn_gae", C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _vp])
 pfpn_sac_losses = _sig("pfpn_sac_losses", C.c_int, [_vp] * 11 + [_f, _f, _f, _i32] + [_vp] * 6 + [_vp])
@@ -173,6 +189,8 @@ pfpn_peer_allreduce_sum = _sig("pfpn_peer_allreduce_sum", C.c_int, [_vp, _vp, _i
 pfpn_head_logprob_push = _sig("pfpn_head_logprob_push", C.c_int,
                               [C.POINTER(HeadArgs), C.c_void_p, C.c_size_t, C.POINTER(HeadPush), C.c_void_p])
 pfpn_peer_gather_sum = _sig("pfpn_peer_gather_sum", C.c_int, [_vp, _vp, _i32, _i32, C.c_size_t, _vp, _f, _vp])
+pfpn_sync_step_scratch_bytes = _sig("pfpn_sync_step_scratch_bytes", C.c_int, [C.POINTER(C.c_size_t)])
+pfpn_sync_step = _sig("pfpn_sync_step", C.c_int, [C.POINTER(SyncArgs), C.c_void_p])
 pfpn_peer_alloc = _sig("pfpn_peer_alloc", C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p])
 pfpn_peer_open = _sig("pfpn_peer_open", C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)])
 pfpn_peer_close = _sig("pfpn_peer_close", C.c_int, [_vp])

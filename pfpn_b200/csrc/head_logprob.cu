@@ -75,9 +75,11 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
   // interleaved ownership k = c + 2 i makes lane pairs of different rows collide on a shared-memory bank (12.9 M
   // conflicts per launch at P = 35 in the round-1 profile).  With k = 16 c + i for i < 16 the two lanes of a row are 16
   // banks apart and the 32 lanes of a warp (16 consecutive rows, 3 banks apart each) hit 32 distinct banks; particles
-  // >= 32 stay interleaved.  Requires LPR == 2 and 32 <= P <= 2 * EPL.
+  // >= 32 stay interleaved (P = 35).  8 lanes per row, rows 100 floats (4 banks) apart: k = 32 (i / 4) + 4 (i % 4) +
+  // 16 (c / 4) + c % 4 -- the four rows of a warp land on banks 4r + {0..3, 16..19}, all 32 distinct in every round
+  // (P = 100).  Both maps keep the validity rule "slot i < P / LPR for every lane, slot P / LPR for c < P % LPR".
   constexpr bool SPL = (OPT & 4) != 0;
-  static_assert(!SPL || LPR == 2, "split ownership is defined for 2 lanes per row");
+  static_assert(!SPL || (LPR == 2 && PT == 35) || (LPR == 8 && PT == 100), "split ownership: P=35 / 2 lanes or P=100 / 8 lanes");
   constexpr bool LEAN = KM >= 2;
   constexpr int EP2 = (EPL + 1) / 2;  // packed pairs per lane
   // Software pipeline: iteration `it` runs pass A/B of tile it and pass C of tile it-1; the
@@ -101,11 +103,6 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
   // SIP (scalars in the producer): the otherwise idle producer warp sums a state's row partials, writes lp / ent, evaluates
   // the PPO surrogate and publishes ONE dL/dlp per state; the compute lanes (72..576 per state) no longer each re-derive it.
   constexpr bool SIP = SEG;
-  // OPT bit 3 (EARLY): the compute threads signal "row partials of tile it written" on a second barrier right after pass A/B
-  // instead of only at the end of the step, and the producer publishes dL/dlp of tile it while they are still in pass C of
-  // tile it-1.  A warp then needs the slowest warp to be at most TWO passes behind (one before) when it reaches its g_bar
-  // wait -- the round-1 profile had 7.5 % of all stall samples in that spin.
-  constexpr bool EARLY = (OPT & 8) != 0 && SIP && BWD;
   const int TS = slots * RPT;
   const int tile_floats = TS * AP;
   const uint32_t mode = KM == 2 ? (uint32_t)PFPN_HEAD_PPO : (KM == 3 ? (uint32_t)PFPN_HEAD_GRAD : kp.a.mode);
@@ -132,7 +129,6 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* cta_bar = full_bar + NSTAGE;                            // split-phase CTA barrier
   uint64_t* g_bar = cta_bar + 1;                                    // [2] SIP: producer -> compute, per-state dL/dlp ready (tile parity)
-  uint64_t* ab_bar = cta_bar + 3;                                   // EARLY: compute -> producer, row partials of a tile written
   float2* rowbuf = reinterpret_cast<float2*>(tail + 8 * (NSTAGE + 4));  // [NSTAGE][TS*A] per-row (log p, H) partials
   float* lossbuf = reinterpret_cast<float*>(rowbuf + NSTAGE * TS * A);  // [kHeadMaxWarps]
   float* gbuf = lossbuf + kHeadMaxWarps;                            // [NSTAGE][TS] per-state dL/dlp (SIP), 256 floats
@@ -145,7 +141,6 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
     mbar_init(smem_u32(cta_bar), (uint32_t)nthr);
     mbar_init(smem_u32(&g_bar[0]), 1);
     mbar_init(smem_u32(&g_bar[1]), 1);
-    mbar_init(smem_u32(ab_bar), (uint32_t)nthr);
     mbar_fence_init();
   }
   // programmatic dependent launch: everything above overlaps the tail of the previous kernel on the stream
@@ -190,8 +185,12 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
   const bool part_ok = c < P - nfull * LPR;
   auto k_ok = [&](int i) -> bool { return (i < nfull) || (i == nfull && part_ok); };
   // element offset (within the row) of this lane's i-th particle, MINUS c: rows are addressed as row_base + c + kofs(i)
-  const int spl_c = SPL ? 15 * c : 0;
-  auto kofs = [&](int i) -> int { return (SPL && i < 16) ? (spl_c + i) : LPR * i; };
+  const int spl_c = SPL ? (LPR == 2 ? 15 * c : 12 * (c >> 2)) : 0;
+  auto kofs = [&](int i) -> int {
+    if (SPL && LPR == 2) return i < 16 ? (spl_c + i) : LPR * i;
+    if (SPL && LPR == 8) return 32 * (i >> 2) + 4 * (i & 3) + spl_c;
+    return LPR * i;
+  };
 
   constexpr int NCR = CSM ? 1 : EP2;
   float2 isig_r[NCR], nmisig_r[NCR], cst_r[NCR];
@@ -252,10 +251,10 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
     // stage that load(it+DIST) refills held tile it+DIST-NSTAGE, whose store is older than the
     // NSTAGE-DIST-2 most recent bulk groups.  Only this warp ever blocks on TMA traffic.
     // Iteration `it`: (1) TMA duties that became possible when step it-1 completed, (2) the per-state scalars of tile
-    // `sit` -- tile it-1 (its partials are complete once step it-1 is) or, with EARLY, tile it (as soon as its pass A/B is).
-    for (int it = EARLY ? 0 : 1; it <= my_tiles; ++it) {
-      const int sit = EARLY ? it : it - 1;
-      const bool do_sip = SIP && sit < my_tiles;
+    // sit = it-1 (its row partials are complete once step it-1 is).
+    for (int it = 1; it <= my_tiles; ++it) {
+      const int sit = it - 1;
+      const bool do_sip = SIP;
       // the per-state scalars (PPO: adv, lp_old; GRAD: dL/dlp) do not depend on the compute warps: fetch them before
       // blocking on a barrier so the DRAM latency is off the g_bar critical path
       float pf0 = 0.f, pf1 = 0.f;
@@ -285,7 +284,6 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
         __syncwarp();
       }
       if (do_sip) {
-        if (EARLY) mbar_wait(smem_u32(ab_bar), (uint32_t)(sit & 1));  // every compute thread wrote its partials of tile sit
         // ---- per-state scalars of tile sit ----
         const int pb0 = (first_tile + sit * tile_step) * TS;
         if (lane < TS) {
@@ -476,7 +474,6 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
           rb[row_off[j]] = make_float2(lnp, Hval);
         }
       }
-      if (EARLY) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(ab_bar)) : "memory");
     }
     // ======================= pass C of tile it-1 (state in registers) ==================
     // Placed first in program order so that the carried registers die before pass A/B
@@ -892,27 +889,21 @@ struct HeadVariant {
 // exactly (P, A) == (PT, AT) -- the shapes BASELINE.json names (A = 36 DeepMimic action
 // dims, P in {10, 35, 100}); PT == AT == 0 entries take both at run time.
 static const HeadVariant kHeadVariants[] = {
-    // P = 35 (DPPO): 2 lanes per row / 18 particles per lane with recompute (OPT 3) halves the per-row fixed work;
-    // it wins wherever pass C is absent or heavy (B = 65536, ms: FWD .090 vs .117, tanh+dvalue .198 vs .247,
-    // PPO .183 vs .185); the lean GRAD mode stays on 4 lanes per row with carried terms (.179 vs .183).
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 4, 288, 96, 35, 36, 3, 1 | 2 | 4),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, 1, 8),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 4, 288, 96, 35, 36, 7, 0),   // [2] split ownership (bank-conflict-free)
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 4, 288, 96, 35, 36, 11, 0),  // [3] early dL/dlp
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 4, 288, 96, 35, 36, 15, 0),  // [4] both
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 6, 288, 96, 35, 36, 1, 0),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, 0, 0),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 5, 144, 128, 35, 36, 1, 0),
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 2, 5, 288, 96, 35, 36, 1, 0),
+    // P = 35 (DPPO): 2 lanes per row / 18 particles per lane, recompute (OPT bit 1) and bank-conflict-free split
+    // ownership (OPT bit 2).  Round-2 measurements at B = 65536 (ms; interleaved ownership in parentheses): PPO .1546
+    // (.165), GRAD .1537 (.165; 4 lanes per row with carried terms .179), FWD .0799 (.084), tanh + dvalue .169 (.177).
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 4, 288, 96, 35, 36, 7, 1 | 2 | 4 | 8),
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 4, 288, 96, 35, 36, 3, 0),  // [1] interleaved ownership (round 1 default)
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, 1, 0),   // [2] 4 lanes per row, carried terms
     // P = 100 (SAC sweep): 13 particles per lane spill in the backward modes when the particle terms are carried,
-    // so the backward runs 8 lanes per row WITH recompute (OPT 3: no carried terms, no spills, two CTAs per SM);
+    // so the backward runs 8 lanes per row WITH recompute (no carried terms, no spills, two CTAs per SM);
     // 16 lanes per row / 7 per lane (one 19-warp CTA per SM) is the carried-terms alternative.  Forward: 8 lanes,
-    // constants in registers.  Measured at B = 65536 (ms): PPO .52 (16 lanes .63), GRAD .54 (.56), tanh+dvalue .61
-    // (.86), FWD .25.
-    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 4, 288, 96, 100, 36, 3, 2 | 4 | 8),
-    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 5, 288, 96, 100, 36, 0, 1),
+    // constants in registers.  Entries [0] / [1]: the same with split ownership (conflict-free at a 100-float row pitch).
+    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 4, 288, 96, 100, 36, 7, 2 | 4 | 8),
+    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 5, 288, 96, 100, 36, 4, 1),
+    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 4, 288, 96, 100, 36, 3, 0),  // [2] interleaved (round 1 default, backward)
+    PFPN_HEAD_VARIANT_ENTRY(100, 100, 8, 13, 1, 5, 288, 96, 100, 36, 0, 0),  // [3] interleaved (round 1 default, forward)
     PFPN_HEAD_VARIANT_ENTRY(100, 100, 16, 7, 1, 6, 576, 96, 100, 36, 1, 0),
-    PFPN_HEAD_VARIANT_ENTRY(100, 100, 16, 7, 1, 5, 576, 96, 100, 36, 0, 0),
     PFPN_HEAD_VARIANT_ENTRY(10, 10, 4, 3, 2, 5, 288, 72, 10, 36, 0, 15),
     PFPN_HEAD_VARIANT_ENTRY(1, 12, 4, 3, 2, 5, 320, 96, 0, 0, 0, 15),
     PFPN_HEAD_VARIANT_ENTRY(13, 36, 4, 9, 1, 5, 288, 96, 0, 0, 0, 15),

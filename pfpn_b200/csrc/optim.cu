@@ -67,6 +67,51 @@ __global__ void normalizer_update_kernel(float* __restrict__ mean, float* __rest
   std[k] = fmaxf(1e-6f, decay * std[k] + (1.f - decay) * sqrtf(v[k]));
 }
 
+// Graph-capturable form of the statistics update (the step comes from DEVICE memory, inputs and outputs are separate
+// buffers): coalesced partial column sums (thread = column, CTA = a block of rows; fp64), then one fixed-order finalize
+// that also applies the moving average.  var = E[x^2] - mean^2 in fp64 (tf.nn.moments computes mean((x - mean)^2)).
+constexpr int kMomentBlocks = 148;
+__global__ void __launch_bounds__(256) moments_partial_kernel(const float* __restrict__ X, int B, int S, int rows_per,
+                                                              double* __restrict__ part) {
+  const int r0 = blockIdx.x * rows_per, r1 = min(B, r0 + rows_per);
+  for (int k = threadIdx.x; k < S; k += 256) {
+    double s = 0.0, q = 0.0;
+    int b = r0;
+    for (; b + 3 < r1; b += 4) {  // four independent loads in flight
+      const float x0 = X[(size_t)b * S + k], x1 = X[(size_t)(b + 1) * S + k], x2 = X[(size_t)(b + 2) * S + k],
+                  x3 = X[(size_t)(b + 3) * S + k];
+      s += (double)x0 + (double)x1 + (double)x2 + (double)x3;
+      q += (double)x0 * x0 + (double)x1 * x1 + (double)x2 * x2 + (double)x3 * x3;
+    }
+    for (; b < r1; ++b) {
+      const float x = X[(size_t)b * S + k];
+      s += x;
+      q += (double)x * x;
+    }
+    part[((size_t)blockIdx.x * 2 + 0) * S + k] = s;
+    part[((size_t)blockIdx.x * 2 + 1) * S + k] = q;
+  }
+}
+__global__ void normalizer_finalize_kernel(const double* __restrict__ part, int nblk, int B, int S,
+                                           const float* __restrict__ mean_in, const float* __restrict__ std_in,
+                                           float* __restrict__ mean_out, float* __restrict__ std_out,
+                                           const int* __restrict__ global_step) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= S) return;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < nblk; ++i) {
+    s += part[((size_t)i * 2 + 0) * S + k];
+    q += part[((size_t)i * 2 + 1) * S + k];
+  }
+  const double mean = s / B;
+  double var = q / B - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float step = (float)*global_step;
+  const float decay = fminf(0.9999f, (1.f + step) / (10.f + step));
+  mean_out[k] = decay * mean_in[k] + (1.f - decay) * (float)mean;
+  std_out[k] = fmaxf(1e-6f, decay * std_in[k] + (1.f - decay) * sqrtf((float)var));
+}
+
 // value loss: mean((v - sg(adv + v_old))^2); dv = coef * 2 (v - target) * scale; one CTA
 __global__ void __launch_bounds__(1024) value_loss_kernel(const float* __restrict__ v, const float* __restrict__ adv,
                                                           const float* __restrict__ v_old, float* __restrict__ dv,
@@ -247,6 +292,28 @@ extern "C" int pfpn_normalizer_update(const float* state, float* mean, float* st
   col_moments_kernel<<<S, 256, 0, st>>>(state, B, S, scratch, scratch + S);
   PFPN_CUDA_OK(cudaGetLastError());
   normalizer_update_kernel<<<(S + 255) / 256, 256, 0, st>>>(mean, std, scratch, scratch + S, S, step);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}
+
+extern "C" int pfpn_normalizer_scratch_bytes(int32_t S, size_t* bytes) {
+  if (!bytes || S <= 0) return PFPN_ERR_ARG;
+  *bytes = (size_t)kMomentBlocks * 2 * S * sizeof(double);
+  return PFPN_OK;
+}
+extern "C" int pfpn_normalizer_update_dev(const float* state, const float* mean_in, const float* std_in, float* mean_out,
+                                          float* std_out, int32_t B, int32_t S, const int32_t* global_step, void* scratch,
+                                          size_t scratch_bytes, pfpn_stream_t stream_) {
+  if (!state || !mean_in || !std_in || !mean_out || !std_out || !global_step || !scratch || B <= 0 || S <= 0) return PFPN_ERR_ARG;
+  if (scratch_bytes < (size_t)kMomentBlocks * 2 * S * sizeof(double)) return PFPN_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(scratch) & 7u) return PFPN_ERR_ALIGN;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  const int rows_per = (B + kMomentBlocks - 1) / kMomentBlocks;
+  const int nblk = (B + rows_per - 1) / rows_per;
+  double* part = reinterpret_cast<double*>(scratch);
+  moments_partial_kernel<<<nblk, 256, 0, st>>>(state, B, S, rows_per, part);
+  PFPN_CUDA_OK(cudaGetLastError());
+  normalizer_finalize_kernel<<<(S + 127) / 128, 128, 0, st>>>(part, nblk, B, S, mean_in, std_in, mean_out, std_out, global_step);
   PFPN_CUDA_OK(cudaGetLastError());
   return PFPN_OK;
 }

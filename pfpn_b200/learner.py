@@ -90,6 +90,7 @@ class SyncReplicasAdam:
         if self.norm_scale is None:
             self.norm_scale = torch.zeros(2, dtype=torch.float32, device=net.params.device)
             self._scratch = torch.empty(296 * 8, dtype=torch.uint8, device=net.params.device)
+            self.launches_last_step = None
 
     def pack_stats(self, net):
         """Statistics pushed through the same accumulators as the gradients (sync_model.py:37-45)."""
@@ -113,8 +114,81 @@ class SyncReplicasAdam:
         net.sum_active.copy_(tail[2 * S + AP:2 * S + 2 * AP].view_as(net.sum_active))
 
     def apply_gradients(self, net):
+        """One optimizer step on the gradients `net.compute_gradients` left in the bucket, then the network's train_ops."""
+        self._launch_step(net)
+        self._after_step(net)
+
+    # The step is split in two so that the device work can be captured in a CUDA graph (GraphedUpdate below):
+    # `_launch_step` only enqueues kernels whose arguments never change; `_after_step` is the host bookkeeping.
+    def _launch_step(self, net):
         self._lazy(net)
         st = _stream_ptr()
+        n_world = world()[1] if net.params.is_cuda else 1
+        self._mode = "sync_step"
+        if os.environ.get("PFPN_SYNC_STEP", "1") == "0" or not hasattr(net, "dev_counters"):
+            self._mode = "legacy"
+        elif n_world > 1:
+            if not self.fused_peer:
+                self._mode = "legacy"
+            elif self._peers is None:
+                from .peer import PeerBuckets
+                try:
+                    self._peers = PeerBuckets(net.bucket.numel(), net.params.device, self.group, with_reduced=True)
+                except (RuntimeError, ValueError) as e:  # collective outcome (peer.py): every rank lands here together
+                    import warnings
+                    warnings.warn(f"fused peer-memory all-reduce unavailable ({e}); using NCCL all-reduce + Adam")
+                    self.fused_peer = False
+                    self._mode = "legacy"
+        if self._mode == "legacy":
+            return self._launch_legacy(net, st)
+        # ---- three launches: sum of squares (+ counters), clip -> stage -> flags, rank-ordered mean -> Adam -> statistics
+        a = self._sync_args(net, n_world)
+        net._ensure_counters(self._peers.calls if self._peers is not None else None, self.step)
+        _cabi.check(_cabi.pfpn_sync_step(a, st))
+        self.launches_last_step = 3
+
+    def _sync_args(self, net, n_world):
+        key = (id(net), n_world, int(os.environ.get("PFPN_PEER_TWO_PHASE_MIN", "6")))
+        if getattr(self, "_sync_key", None) == key:
+            return self._sync_a
+        import ctypes as C
+        a = _cabi.SyncArgs()
+        a.grads, a.n_params, a.n_total, a.clip = net.bucket.data_ptr(), net.n_params, net.bucket.numel(), self.norm_clip
+        if net.normalize_state:
+            a.new_mean, a.new_std = net._new_mean.data_ptr(), net._new_std.data_ptr()
+            a.state_mean, a.state_std, a.S = net.state_mean.data_ptr(), net.state_std.data_ptr(), net.S
+        a.max_active, a.sum_active, a.AP = net.max_active.data_ptr(), net.sum_active.data_ptr(), net.A * net.P
+        a.params, a.m, a.v = net.params.data_ptr(), self.m.data_ptr(), self.v.data_ptr()
+        a.lr, a.beta1, a.beta2, a.eps = self.lr, self.beta1, self.beta2, self.eps
+        a.counters, a.norm_scale = net.dev_counters.data_ptr(), self.norm_scale.data_ptr()
+        a.scratch, a.scratch_bytes = self._scratch.data_ptr(), self._scratch.numel()
+        a.rank, a.nranks, a.two_phase = 0, 1, 0
+        if n_world > 1:
+            pb = self._peers
+            stage, flags = pb.ptrs(0)
+            self._keep = (stage, flags, pb.reduced_ptrs)
+            a.stage = C.cast(stage, C.c_void_p)
+            a.flags = C.cast(flags, C.c_void_p)
+            a.reduced = C.cast(pb.reduced_ptrs, C.c_void_p)
+            a.rank, a.nranks = pb.rank, pb.world
+            a.two_phase = 1 if pb.world >= key[2] else 0
+        self._sync_key, self._sync_a = key, a
+        return a
+
+    def _after_step(self, net):
+        if self._mode == "sync_step":
+            self.step += 1
+            if self._peers is not None:
+                self._peers.calls += 1
+            net.global_step += 1
+            net._dev_shadow = [net._dev_shadow[0] + 1, net._dev_shadow[1] + 1, net._dev_shadow[2] + 1]
+        # train_ops chained after the optimizer step (sync_model.py:79-81): resample tick
+        for op in net.train_ops:
+            op()
+
+    def _launch_legacy(self, net, st):
+        """Round-1 chain, kept as the comparison point (PFPN_SYNC_STEP=0) and as the NCCL fallback: clip, pack, exchange
+        (peer kernel or NCCL all-reduce), Adam, unpack -- host-side step numbers in the arguments."""
         # 1. local clip (before aggregation: optimizer/clip_by_global_norm/mul_* feed the accumulators)
         _cabi.check(_cabi.pfpn_clip_by_global_norm(net.grads.data_ptr(), net.n_params, self.norm_clip,
                                                    self.norm_scale.data_ptr(), self._scratch.data_ptr(),
@@ -133,9 +207,6 @@ class SyncReplicasAdam:
         _cabi.check(_cabi.pfpn_adam_step(net.params.data_ptr(), net.grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                          net.n_params, self.lr, self.beta1, self.beta2, self.eps, self.step, inv_n, st))
         net.global_step += 1
-        # 6. train_ops chained after the optimizer step (sync_model.py:79-81): resample tick
-        for op in net.train_ops:
-            op()
 
     def _apply_fused_peer(self, net, st):
         """Steps 2-5 in one kernel over peer memory: sum in rank order, mean, Adam, averaged statistics."""
@@ -170,8 +241,6 @@ class SyncReplicasAdam:
                                                        self.eps, self.step, st))
         self.unpack_stats(net, 1.0)  # the kernel wrote the averaged bucket back
         net.global_step += 1
-        for op in net.train_ops:
-            op()
 
     def state_dict(self):
         return dict(step=self.step, m=None if self.m is None else self.m.clone(), v=None if self.v is None else self.v.clone())
@@ -179,7 +248,62 @@ class SyncReplicasAdam:
     def load_state_dict(self, sd):
         self.step = int(sd["step"])
         if sd["m"] is not None:
-            self.m, self.v = sd["m"].clone(), sd["v"].clone()
+            if self.m is not None and self.m.shape == sd["m"].shape:
+                self.m.copy_(sd["m"])  # in place: kernels / captured graphs hold these pointers
+                self.v.copy_(sd["v"])
+            else:
+                self.m, self.v = sd["m"].clone(), sd["v"].clone()
+                self._sync_key = None
+
+
+class GraphedUpdate:
+    """One DPPO minibatch update -- `net.compute_gradients(...)` + `optimizer.apply_gradients(net)` -- captured ONCE in a
+    CUDA graph and replayed (at 8192 states per GPU the update is a chain of ~45 launch-latency-sized kernels).
+    Possible because nothing in the captured kernels' arguments changes between steps: the Adam step, the exchange call
+    number / staging parity and the normaliser's step are read from device memory (csrc/syncstep.cu).  The minibatch is
+    copied into fixed input buffers; the resample tick (host-side interval logic, a2c.py:370-383) runs eagerly after
+    the replay.  Every rank must call `run` the same number of times (the replayed step contains the exchange)."""
+
+    KEYS = ("state", "action", "value", "log_prob", "advantage")
+
+    def __init__(self, net, optimizer, batch: int, warmup: int = 2):
+        dev = net.device
+        self.net, self.opt, self.B = net, optimizer, int(batch)
+        f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        self.inputs = dict(state=f(batch, net.S), action=f(batch, net.A), value=f(batch), log_prob=f(batch), advantage=f(batch))
+        self.graph = None
+        self.losses = None
+        self._warm = int(warmup)
+        self.replays = 0
+
+    def _set(self, state, action, value, log_prob, advantage):
+        for k, v in zip(self.KEYS, (state, action, value, log_prob, advantage)):
+            if v is not None and v is not self.inputs[k]:
+                self.inputs[k].copy_(torch.as_tensor(v, dtype=torch.float32).reshape(self.inputs[k].shape), non_blocking=True)
+
+    def run(self, state=None, action=None, value=None, log_prob=None, advantage=None):
+        """Arguments left None keep what is already in ``self.inputs`` (zero-copy use: write the minibatch there)."""
+        self._set(state, action, value, log_prob, advantage)
+        net, opt = self.net, self.opt
+        args = tuple(self.inputs[k] for k in self.KEYS)
+        if self._warm > 0 or os.environ.get("PFPN_GRAPH", "1") == "0":  # eager steps: allocate every buffer, map the peers
+            self._warm -= 1
+            self.losses = net.compute_gradients(*args)
+            opt.apply_gradients(net)
+            return self.losses
+        if self.graph is None:
+            net._ensure_counters(opt._peers.calls if opt._peers is not None else None, opt.step)
+            torch.cuda.synchronize(net.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.losses = net.compute_gradients(*args)
+                opt._launch_step(net)
+            if opt._mode != "sync_step":
+                raise RuntimeError("the graph-captured update needs the device-counter step (PFPN_SYNC_STEP=1, peer memory available)")
+        self.graph.replay()
+        self.replays += 1
+        opt._after_step(net)
+        return self.losses
 
 
 # ---- a20: the on-policy training loop over one rollout (models/distributed_model.py:320-345) ---------------------------

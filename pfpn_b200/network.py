@@ -170,7 +170,35 @@ class ParticleFilteringClipPPONetwork:
             self.local_update_variables += [self.max_active, self.sum_active]  # a2c.py:362-363
             self.train_ops.append(self.update)                                 # a2c.py:383
         self._scratch = torch.empty(max(2 * S, 8), dtype=torch.float32, device=dev)
+        self._init_step_state()
         return self
+
+    def _init_step_state(self):
+        """Device-resident step counters {exchange calls, Adam step, global_step, ticket} (read by the kernels of the
+        graph-capturable update, csrc/syncstep.cu) + their host shadow, buffers of the pushed statistics, side stream."""
+        dev, S = self.device, self.S
+        self.dev_counters = torch.zeros(4, dtype=torch.int32, device=dev)
+        self._dev_shadow = [0, 0, 0]
+        self._new_mean = torch.zeros(S, dtype=torch.float32, device=dev)
+        self._new_std = torch.ones(S, dtype=torch.float32, device=dev)
+        n = C.c_size_t(0)
+        _cabi.check(_cabi.pfpn_normalizer_scratch_bytes(S, C.byref(n)))
+        self._norm_scratch = torch.empty(n.value // 8, dtype=torch.float64, device=dev)
+        self._adv_stats = torch.empty(2, dtype=torch.float32, device=dev)
+        self._side = torch.cuda.Stream(dev) if dev.type == "cuda" else None
+        import os
+        # the critic trunk is independent of the actor trunk + head: run it on a second stream (a parallel branch of the
+        # captured graph); pays off when a rank's minibatch shard no longer fills the GPU with one GEMM
+        self.overlap_critic = os.environ.get("PFPN_CRITIC_STREAM", "1") != "0"
+
+    def _ensure_counters(self, calls=None, adam_step=None):
+        """Upload the host-side step numbers when the device copy is stale (first use, checkpoint resume, a switch between
+        exchange implementations).  Steady state: no-op -- the kernels increment the device copy themselves."""
+        want = [self._dev_shadow[0] if calls is None else int(calls),
+                self._dev_shadow[1] if adam_step is None else int(adam_step), int(self.global_step)]
+        if want != self._dev_shadow:
+            self.dev_counters.copy_(torch.tensor(want + [0], dtype=torch.int32), non_blocking=False)
+            self._dev_shadow = want
 
     def _init_values(self):
         """a2c.py:476-535 particle grid (bounds forced to +-1) + truncated_normal(0, .01) weights."""
@@ -205,14 +233,16 @@ class ParticleFilteringClipPPONetwork:
                                               Y.stride(0) if Y.dim() > 1 else 1, X.shape[0], l.k, l.n_out,
                                               1 if relu6 else 0, _stream_ptr()))
 
-    def _forward(self, state: torch.Tensor, want_value=True):
+    def _normalized(self, state: torch.Tensor):
         B = state.shape[0]
         x = self._buf("x", B, self.Sp)
         _cabi.check(_cabi.pfpn_state_normalize(state.data_ptr(), self.state_mean.data_ptr(), self.state_std.data_ptr(),
                                                x.data_ptr(), B, self.S, self.Sp, self.clip_state,
                                                1 if self.normalize_state else 0, _stream_ptr()))
-        h = x
-        acts = [x]
+        return x
+
+    def _forward_actor(self, x):
+        B, h, acts = x.shape[0], x, [x]
         for i, l in enumerate(self.actor):
             y = self._buf(f"h{i}", B, l.n_out)
             self._linear(l, h, y, True)
@@ -220,17 +250,24 @@ class ParticleFilteringClipPPONetwork:
             acts.append(y)
         logits = self._buf("logits", B, self.A * self.P)
         self._linear(self.fc_policy, h, logits, False)
-        value, cacts = None, [x]
-        if want_value:
-            h = x
-            for i, l in enumerate(self.critic[:-1]):
-                y = self._buf(f"c{i}", B, l.n_out)
-                self._linear(l, h, y, True)
-                h = y
-                cacts.append(y)
-            value = self._buf("value", B)
-            self._linear(self.critic[-1], h, value, False)
-        return logits.view(B, self.A, self.P), acts, value, cacts
+        return logits.view(B, self.A, self.P), acts
+
+    def _forward_critic(self, x):
+        B, h, cacts = x.shape[0], x, [x]
+        for i, l in enumerate(self.critic[:-1]):
+            y = self._buf(f"c{i}", B, l.n_out)
+            self._linear(l, h, y, True)
+            h = y
+            cacts.append(y)
+        value = self._buf("value", B)
+        self._linear(self.critic[-1], h, value, False)
+        return value, cacts
+
+    def _forward(self, state: torch.Tensor, want_value=True):
+        x = self._normalized(state)
+        logits, acts = self._forward_actor(x)
+        value, cacts = self._forward_critic(x) if want_value else (None, [x])
+        return logits, acts, value, cacts
 
     def _dev_state(self, state):
         t = torch.as_tensor(np.asarray(state, dtype=np.float32) if not torch.is_tensor(state) else state)
@@ -319,11 +356,29 @@ class ParticleFilteringClipPPONetwork:
         # statistics pushed with this step (LocalUpdateHookPre, sync_model.py:123-138): computed from
         # the pre-update values, applied by the optimizer after aggregation
         if self.normalize_state:
-            self._new_mean, self._new_std = self.state_mean.clone(), self.state_std.clone()
-            _cabi.check(_cabi.pfpn_normalizer_update(s.data_ptr(), self._new_mean.data_ptr(), self._new_std.data_ptr(), B,
-                                                     self.S, float(self.global_step), self._scratch.data_ptr(), _stream_ptr()))
-        logits, acts, v, cacts = self._forward(s)
-        stats = _head.adv_stats(adv) if self.normalize_advantage else None
+            self._ensure_counters()
+            _cabi.check(_cabi.pfpn_normalizer_update_dev(s.data_ptr(), self.state_mean.data_ptr(), self.state_std.data_ptr(),
+                                                         self._new_mean.data_ptr(), self._new_std.data_ptr(), B, self.S,
+                                                         self.dev_counters[2:].data_ptr(), self._norm_scratch.data_ptr(),
+                                                         self._norm_scratch.numel() * 8, _stream_ptr()))
+        x = self._normalized(s)
+        vloss = self._buf("vloss", 1)
+
+        def critic_branch():
+            v, cacts = self._forward_critic(x)
+            dval = self._buf("dval", B)
+            _cabi.check(_cabi.pfpn_value_loss(v.data_ptr(), adv.data_ptr(), value_old.data_ptr(), dval.data_ptr(),
+                                              vloss.data_ptr(), B, float(self.value_loss_coef), scale, _stream_ptr()))
+            self._backward_stack(self.critic, cacts, dval, tag="c")
+
+        main = torch.cuda.current_stream(self.device)
+        fork = self.overlap_critic and self._side is not None
+        if fork:  # parallel branch: critic trunk forward, value loss, critic backward
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                critic_branch()
+        logits, acts = self._forward_actor(x)
+        stats = _head.adv_stats(adv, out=self._adv_stats) if self.normalize_advantage else None
         ent_scale = -float(self.entropy_beta) * scale if self.entropy_beta else 0.0
         # action_hist is the stored (tanh'd) action: MixtureGaussianDistribution.log_prob applies atanh to a non-tuple
         # value when normalize_output (utils.py:120-126); K1 takes the pre-tanh value
@@ -334,11 +389,11 @@ class ParticleFilteringClipPPONetwork:
                               out=dict(dloc=self.dloc, dlogstd=self.dlogstd, lp=self._buf("lp", B), ent=self._buf("ent", B),
                                        loss=self._buf("ploss", 1)))
         dlogits = logits.view(B, self.A * self.P)
-        dval, vloss = self._buf("dval", B), self._buf("vloss", 1)
-        _cabi.check(_cabi.pfpn_value_loss(v.data_ptr(), adv.data_ptr(), value_old.data_ptr(), dval.data_ptr(),
-                                          vloss.data_ptr(), B, float(self.value_loss_coef), scale, _stream_ptr()))
-        self._backward_stack(self.actor + [self.fc_policy], acts, dlogits)
-        self._backward_stack(self.critic, cacts, dval)
+        self._backward_stack(self.actor + [self.fc_policy], acts, dlogits, tag="a")
+        if fork:
+            main.wait_stream(self._side)
+        else:
+            critic_branch()
         policy_loss = out["loss"][0]
         entropy = None
         if self.entropy_beta:
@@ -348,14 +403,15 @@ class ParticleFilteringClipPPONetwork:
         loss = policy_loss + value_loss
         return loss, entropy, policy_loss, value_loss
 
-    def _backward_stack(self, layers: Sequence[_Linear], acts, dY):
-        """acts[i] is the input of layers[i]; dY is dL/d(output of the last layer)."""
+    def _backward_stack(self, layers: Sequence[_Linear], acts, dY, tag=""):
+        """acts[i] is the input of layers[i]; dY is dL/d(output of the last layer).  `tag` names the scratch buffer (the
+        actor and critic stacks may run concurrently on two streams)."""
         st = _stream_ptr()
         for i in range(len(layers) - 1, -1, -1):
             l, X = layers[i], acts[i]
             M = X.shape[0]
             if self.use_tensor_cores and l.n_out > 1 and M >= 512:
-                self._tc_wgrad(l, X, dY, M)
+                self._tc_wgrad(l, X, dY, M, tag)
                 if i > 0:
                     dX = self._buf(f"d_{l.name}", M, l.k)
                     _cabi.check(_cabi.pfpn_tc_gemm_nt(dY.data_ptr(), dY.stride(0), l.W.data_ptr(), l.n_out, dX.data_ptr(),
@@ -364,7 +420,7 @@ class ParticleFilteringClipPPONetwork:
                 continue
             n = C.c_size_t(0)
             _cabi.check(_cabi.pfpn_mlp_wgrad_workspace_bytes(M, l.k, l.n_out, C.byref(n)))
-            ws = self._ws(n.value)
+            ws = self._ws(n.value, tag)
             ldy = dY.stride(0) if dY.dim() > 1 else 1
             _cabi.check(_cabi.pfpn_mlp_linear_bwd_weight(X.data_ptr(), X.stride(0), dY.data_ptr(), ldy, l.dW.data_ptr(),
                                                          l.db.data_ptr(), M, l.k, l.n_out, ws.data_ptr(), ws.numel(), st))
@@ -380,21 +436,21 @@ class ParticleFilteringClipPPONetwork:
                                                             dX.stride(0), M, l.k, l.n_out, st))
                 dY = dX
 
-    def _tc_wgrad(self, l, X, dY, M):
+    def _tc_wgrad(self, l, X, dY, M, tag=""):
         """dW and db on the tensor cores: X and dY as stored (MN-major operands), split-K GEMM; the bias
         gradient is accumulated from the dY tiles the GEMM stages anyway."""
         st = _stream_ptr()
         n = C.c_size_t(0)
         _cabi.check(_cabi.pfpn_tc_wgrad_workspace_bytes(M, l.k, l.n_out, C.byref(n)))
-        ws = self._ws(n.value)
+        ws = self._ws(n.value, tag)
         _cabi.check(_cabi.pfpn_tc_linear_bwd_weight(X.data_ptr(), X.stride(0), dY.data_ptr(), dY.stride(0), l.dW.data_ptr(),
                                                     l.db.data_ptr(), M, l.k, l.n_out, ws.data_ptr(), ws.numel(), st))
 
-    def _ws(self, nbytes):
-        t = self._act.get("_ws")
+    def _ws(self, nbytes, tag=""):
+        t = self._act.get("_ws" + tag)
         if t is None or t.numel() < nbytes:
             t = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            self._act["_ws"] = t
+            self._act["_ws" + tag] = t
         return t
 
     def train(self, sess, optimizer, ops, state, action, value, log_prob, advantage):

@@ -259,3 +259,62 @@ def test_ppo_train_step_with_tanh_squashed_actions_matches_oracle(cuda_dev):
     for k, (_, g) in net.named_parameters().items():
         assert rel(g, g_ref[k]) < 2 * TOL, k  # (atanh of an fp32 action adds its own rounding on top of the head's)
     assert abs(float(losses[3]) - float(l_ref[3])) < TOL * float(l_ref[3])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# a17-a19: the 3-launch optimizer step with device-resident counters (csrc/syncstep.cu) and its CUDA-graph replay
+# ---------------------------------------------------------------------------------------------------------------------
+def _run_steps(cuda_dev, n_steps, mode, B=192):
+    import os
+    from pfpn_b200.learner import GraphedUpdate
+    net = build(cuda_dev)
+    opt = SyncReplicasAdam(lr=1e-4, norm_clip=1.0)
+    old = os.environ.get("PFPN_SYNC_STEP")
+    os.environ["PFPN_SYNC_STEP"] = "0" if mode == "legacy" else "1"
+    try:
+        gu = GraphedUpdate(net, opt, B, warmup=2) if mode == "graph" else None
+        for i in range(n_steps):
+            b = make_batch(B, 197, 36, seed=100 + i)
+            b["log_prob"] = b["log_prob"] - 60.0 - 30.0  # near the mixture's log-density so the ratio stays finite
+            args = (b["state"].to(cuda_dev), b["action"].to(cuda_dev), b["value"].to(cuda_dev), b["log_prob"].to(cuda_dev),
+                    b["advantage"].to(cuda_dev))
+            if gu is not None:
+                gu.run(*args)
+            else:
+                net.compute_gradients(*args)
+                opt.apply_gradients(net)
+        torch.cuda.synchronize()
+    finally:
+        if old is None:
+            os.environ.pop("PFPN_SYNC_STEP", None)
+        else:
+            os.environ["PFPN_SYNC_STEP"] = old
+    return net, opt, gu
+
+
+def test_sync_step_matches_the_legacy_optimizer_chain(cuda_dev):
+    """clip -> stage -> mean -> Adam -> statistics in 3 launches vs the round-1 chain (clip, pack, Adam, unpack) over 4
+    steps: same parameters / slots / statistics up to the rounding of the norm (different but fixed summation orders)."""
+    n1, o1, _ = _run_steps(cuda_dev, 4, "legacy")
+    n2, o2, _ = _run_steps(cuda_dev, 4, "sync")
+    assert o1._mode == "legacy" and o2._mode == "sync_step" and o2.launches_last_step == 3
+    assert o1.step == o2.step == 4 and n1.global_step == n2.global_step == 4 and n1.train_flag == n2.train_flag == 4
+    assert rel(o2.norm_scale, o1.norm_scale) < 1e-6
+    assert rel(n2.params, n1.params) < 1e-6 and rel(o2.m, o1.m) < 1e-5 and rel(o2.v, o1.v) < 1e-5
+    upd1, upd2 = n1.params - build(cuda_dev).params, n2.params - build(cuda_dev).params
+    assert rel(upd2, upd1) < 1e-3  # the update itself (|dp| ~ 4e-4), not just the parameters it is added to
+    assert rel(n2.state_mean, n1.state_mean) < 1e-6 and rel(n2.state_std, n1.state_std) < 1e-6
+    assert torch.equal(n2.max_active, n1.max_active) and torch.equal(n2.sum_active, n1.sum_active)
+    assert n2.dev_counters[:3].tolist() == [4, 4, 4]
+
+
+def test_graphed_update_is_bit_identical_to_eager_steps(cuda_dev):
+    """The whole update captured once and replayed (2 eager warm-up steps + 4 replays, a different minibatch each) equals
+    6 eager steps bit for bit: the step number, the normaliser's decay and the exchange parity come from device memory."""
+    n1, o1, _ = _run_steps(cuda_dev, 6, "sync")
+    n2, o2, gu = _run_steps(cuda_dev, 6, "graph")
+    assert gu.graph is not None and gu.replays == 4
+    assert torch.equal(n1.params, n2.params) and torch.equal(o1.m, o2.m) and torch.equal(o1.v, o2.v)
+    assert torch.equal(n1.state_mean, n2.state_mean) and torch.equal(n1.state_std, n2.state_std)
+    assert o2.step == 6 and n2.global_step == 6 and n2.dev_counters[:3].tolist() == [6, 6, 6]
+    assert np.isfinite(float(gu.losses[0]))

@@ -44,6 +44,20 @@ d = (res["fused"]["params"] - res["nccl"]["params"]).abs().max().item()
 out = dict(rank=rank, world=world, max_abs_param_diff_fused_vs_nccl=d, replica_equal=(res["nccl"]["replica_equal"], res["fused"]["replica_equal"]),
            stats_equal=bool(torch.allclose(res["fused"]["mean"], res["nccl"]["mean"], rtol=1e-6, atol=1e-7)),
            ms_apply_nccl=round(res["nccl"]["ms"], 4), ms_apply_fused=round(res["fused"]["ms"], 4))
+# ---- the whole update replayed as a CUDA graph on every rank (device-resident counters, exchange inside the graph) ----
+from pfpn_b200.learner import GraphedUpdate
+snaps = {}
+for name, graphed in (("eager", False), ("graph", True)):
+    net, opt = make(), SyncReplicasAdam(lr=1e-4, norm_clip=1.0, fused_peer=True)
+    _, lp, _ = net.run_batch(state); lp_old = lp.clone()
+    gu = GraphedUpdate(net, opt, B, warmup=2 if graphed else 10 ** 9)
+    for it in range(6):  # crosses resample ticks (interval 3), both staging parities
+        gu.run(state, action, value, lp_old, adv * (1.0 + 0.1 * it))
+    torch.cuda.synchronize()
+    snaps[name] = (net.params.clone(), net.state_mean.clone(), gu.replays)
+refp = snaps["graph"][0].clone(); dist.broadcast(refp, 0)
+out.update(graph_replays=snaps["graph"][2], graph_equals_eager=bool(torch.equal(snaps["graph"][0], snaps["eager"][0]) and torch.equal(snaps["graph"][1], snaps["eager"][1])),
+           graph_replicas_equal=bool(torch.equal(refp, snaps["graph"][0])))
 # ---- the sharded head's [2, A, P] exchange in one kernel (pfpn_peer_allreduce_sum) vs NCCL ----------------
 from pfpn_b200.peer import PeerSum
 from pfpn_b200.head import _stream_ptr
