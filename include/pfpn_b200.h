@@ -170,6 +170,38 @@ int pfpn_head_rsample_fwd(const pfpn_rsample_args* args, pfpn_stream_t stream);
 int pfpn_rsample_bwd_workspace_bytes(int32_t B, int32_t A, int32_t P, size_t* bytes);
 int pfpn_head_rsample_bwd(const pfpn_rsample_args* args, void* workspace, size_t workspace_bytes, pfpn_stream_t stream);
 
+/* K3f  the SAC-PFPN head in ONE pass (the fused fwd_bwd of the c5 sweep): reparameterised sample, the
+ * tanh-squashed log_prob of that sample, and the backward of both given dL/dsample (from the critics) and dL/dlog_prob
+ * -- 8AP + 12A + 8 bytes per state instead of the five [B,A,P] passes of the three-launch form, every draw generated
+ * once.  With the same (seed, offset) it draws the same Gumbel / normal variates as pfpn_head_rsample_fwd / _bwd; with
+ * ext_uniform / ext_normal (verification) the argmax particle is bit-exact against the oracle.
+ * Replaces: MixtureGaussianDistribution.sample (rsample branch) + .log_prob((sample, s_pre)) + tf.gradients through both,
+ *           networks/utils.py:108-144,156-186; AbstractSACNetwork.build_policy_loss's head-facing part, sac.py:166-173.
+ * Compiled for the BASELINE c5 shape A = 36, P = 100 (PFPN_ERR_UNSUPPORTED otherwise: use the three-launch form). */
+typedef struct pfpn_sac_head_args {
+  const float* logits;      /* [B, A, P]                                              */
+  const float* loc;         /* [A, P]                                                 */
+  const float* logstd;      /* [A, P]                                                 */
+  const float* ext_uniform; /* [B, A, P] in [tiny, 1) or NULL = Philox                 */
+  const float* ext_normal;  /* [B, A, P] or NULL (both or neither)                     */
+  const float* g_sample;    /* [B, A]  dL/dsample                                      */
+  const float* g_lp;        /* [B]     dL/dlog_prob                                    */
+  float* sample;            /* [B, A]  out: tanh(s_pre)                                */
+  float* s_pre;             /* [B, A]  out                                             */
+  int32_t* idx;             /* [B, A]  out: argmax particle                            */
+  float* logp;              /* [B]     out: log_prob((sample, s_pre))                  */
+  float* dlogits;           /* [B, A, P] out (may alias logits)                        */
+  float* dloc;              /* [A, P]  out, overwritten                                */
+  float* dlogstd;           /* [A, P]  out, overwritten                                */
+  uint64_t seed, offset;
+  int32_t B, A, P;
+} pfpn_sac_head_args;
+int pfpn_sac_head_workspace_bytes(int32_t A, int32_t P, size_t* bytes);
+int pfpn_sac_head_fwd_bwd(const pfpn_sac_head_args* args, void* workspace, size_t workspace_bytes, pfpn_stream_t stream);
+/* Deterministic second stage over per-CTA [nparts][2*AP] partials in K1's convention: dloc = sum / exp(logstd), dlogstd = sum. */
+int pfpn_head_finalize_partials(const float* part, int32_t nparts, const float* logstd, float* dloc, float* dlogstd,
+                                int32_t AP, pfpn_stream_t stream);
+
 /* Deterministic action (evaluator): MixtureGaussianDistribution.mean  networks/utils.py:202-236.
  * action[b,a] = loc[a, argmax_k logits[b,a,k]]  (tanh of it with PFPN_HEAD_FLAG_TANH). idx may be NULL. */
 int pfpn_head_mean(const float* logits, const float* loc, float* action, int32_t* idx, int32_t B, int32_t A,
@@ -258,6 +290,18 @@ int pfpn_tc_gemm_nt(const float* A, int32_t lda, const float* Bt, int32_t ldb, f
 int pfpn_tc_gemm_nn(const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
                     const float* bias, const float* Hm, int32_t ldh, int32_t M, int32_t N, int32_t K,
                     int32_t epi, pfpn_stream_t stream);
+/* The same two GEMMs with the low part of the B operand precomputed: B_lo = B - tf32(B) (pfpn_split_lo), same layout
+ * and ldb.  The weights are constant within an optimizer step, so they are split ONCE per step (the optimizer kernel of
+ * pfpn_sync_step writes the low parts next to the parameters) instead of once per tile per GEMM by the splitter warps;
+ * B_lo then arrives by TMA.  Bit-identical results. */
+int pfpn_tc_gemm_nt_lo(const float* A, int32_t lda, const float* Bt, const float* Bt_lo, int32_t ldb, float* C, int32_t ldc,
+                       const float* bias, const float* Hm, int32_t ldh, int32_t M, int32_t N, int32_t K, int32_t epi,
+                       pfpn_stream_t stream);
+int pfpn_tc_gemm_nn_lo(const float* A, int32_t lda, const float* B, const float* B_lo, int32_t ldb, float* C, int32_t ldc,
+                       const float* bias, const float* Hm, int32_t ldh, int32_t M, int32_t N, int32_t K, int32_t epi,
+                       pfpn_stream_t stream);
+/* lo[i] = x[i] - tf32(x[i]), n % 4 == 0, 16-byte aligned. */
+int pfpn_split_lo(const float* x, float* lo, size_t n, pfpn_stream_t stream);
 /* out[cols, ldo] = in[rows, ldi]^T (utility; the GEMMs above no longer need transposed copies). */
 int pfpn_transpose(const float* in, int32_t ldi, float* out, int32_t ldo, int32_t rows, int32_t cols,
                    pfpn_stream_t stream);
@@ -400,6 +444,7 @@ typedef struct pfpn_sync_args {
   float* const* reduced;   /* HOST array [nranks]: rank r's averaged-slice buffer, n_total floats (two_phase)    */
   int32_t* const* flags;   /* HOST array [nranks]: rank r's flag words, int32[64], zero-initialised              */
   int32_t rank, nranks, two_phase;
+  float* params_lo;        /* [n_params] or NULL: receives params - tf32(params) for the tensor-core GEMMs         */
 } pfpn_sync_args;
 int pfpn_sync_step_scratch_bytes(size_t* bytes);
 int pfpn_sync_step(const pfpn_sync_args* args, pfpn_stream_t stream);

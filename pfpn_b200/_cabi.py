@@ -53,6 +53,18 @@ class HeadPush(C.Structure):
                 ("nranks", C.c_int32), ("value", C.c_int32)]
 
 
+class SacHeadArgs(C.Structure):
+    """Mirror of ``pfpn_sac_head_args``."""
+    _fields_ = [
+        ("logits", _f32p), ("loc", _f32p), ("logstd", _f32p), ("ext_uniform", _f32p), ("ext_normal", _f32p),
+        ("g_sample", _f32p), ("g_lp", _f32p),
+        ("sample", _f32p), ("s_pre", _f32p), ("idx", C.c_void_p), ("logp", _f32p),
+        ("dlogits", _f32p), ("dloc", _f32p), ("dlogstd", _f32p),
+        ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("B", C.c_int32), ("A", C.c_int32), ("P", C.c_int32),
+    ]
+
+
 class SyncArgs(C.Structure):
     """Mirror of ``pfpn_sync_args``."""
     _fields_ = [
@@ -64,6 +76,7 @@ class SyncArgs(C.Structure):
         ("counters", C.c_void_p), ("norm_scale", C.c_void_p), ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t),
         ("stage", C.c_void_p), ("reduced", C.c_void_p), ("flags", C.c_void_p),
         ("rank", C.c_int32), ("nranks", C.c_int32), ("two_phase", C.c_int32),
+        ("params_lo", C.c_void_p),
     ]
 
 
@@ -142,6 +155,10 @@ pfpn_head_sample = _sig("pfpn_head_sample", C.c_int, [C.POINTER(SampleArgs), C.c
 pfpn_head_rsample_fwd = _sig("pfpn_head_rsample_fwd", C.c_int, [C.POINTER(RSampleArgs), C.c_void_p])
 pfpn_rsample_bwd_workspace_bytes = _sig("pfpn_rsample_bwd_workspace_bytes", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)])
 pfpn_head_rsample_bwd = _sig("pfpn_head_rsample_bwd", C.c_int, [C.POINTER(RSampleArgs), C.c_void_p, C.c_size_t, C.c_void_p])
+pfpn_sac_head_workspace_bytes = _sig("pfpn_sac_head_workspace_bytes", C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)])
+pfpn_sac_head_fwd_bwd = _sig("pfpn_sac_head_fwd_bwd", C.c_int, [C.POINTER(SacHeadArgs), C.c_void_p, C.c_size_t, C.c_void_p])
+pfpn_head_finalize_partials = _sig("pfpn_head_finalize_partials", C.c_int,
+                                   [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p])
 pfpn_head_mean = _sig("pfpn_head_mean", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                                   C.c_int32, C.c_int32, C.c_uint32, C.c_void_p])
 pfpn_stats_workspace_bytes = _sig("pfpn_stats_workspace_bytes", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)])
@@ -173,6 +190,9 @@ pfpn_clip_by_global_norm = _sig("pfpn_clip_by_global_norm", C.c_int, [_vp, C.c_s
 pfpn_adam_step = _sig("pfpn_adam_step", C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _f, _f, _f, _f, C.c_int64, _f, _vp])
 pfpn_tc_gemm_nt = _sig("pfpn_tc_gemm_nt", C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp])
 pfpn_tc_gemm_nn = _sig("pfpn_tc_gemm_nn", C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp])
+pfpn_tc_gemm_nt_lo = _sig("pfpn_tc_gemm_nt_lo", C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp])
+pfpn_tc_gemm_nn_lo = _sig("pfpn_tc_gemm_nn_lo", C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp])
+pfpn_split_lo = _sig("pfpn_split_lo", C.c_int, [_vp, _vp, C.c_size_t, _vp])
 pfpn_transpose = _sig("pfpn_transpose", C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _vp])
 pfpn_tc_wgrad_workspace_bytes = _sig("pfpn_tc_wgrad_workspace_bytes", C.c_int, [_i32, _i32, _i32, C.POINTER(C.c_size_t)])
 pfpn_tc_linear_bwd_weight = _sig("pfpn_tc_linear_bwd_weight", C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, C.c_size_t, _vp])

@@ -1088,6 +1088,19 @@ extern "C" int pfpn_head_logprob_push(const pfpn_head_args* args, void* workspac
   return head_logprob_impl(args, workspace, workspace_bytes, push, stream_);
 }
 
+// Second stage alone, for kernels that produce per-CTA [2*AP] partials in K1's convention (dloc partial = sum g r z,
+// divided by sigma here; dlogstd partial as is): csrc/sac_head.cu.
+extern "C" int pfpn_head_finalize_partials(const float* part, int32_t nparts, const float* logstd, float* dloc, float* dlogstd,
+                                           int32_t AP, pfpn_stream_t stream_) {
+  if (!part || !logstd || !dloc || !dlogstd || nparts <= 0 || AP <= 0) return PFPN_ERR_ARG;
+  HeadPushK pk;
+  memset(&pk, 0, sizeof(pk));
+  head_finalize_kernel<<<(2 * AP + 31) / 32, 32 * kFinGroups, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      part, nullptr, logstd, dloc, dlogstd, nullptr, AP, nparts, pk);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}
+
 extern "C" int pfpn_adv_stats(const float* adv, int32_t B, float* stats, pfpn_stream_t stream_) {
   if (!adv || !stats || B <= 0) return PFPN_ERR_ARG;
   adv_stats_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(adv, B, stats);

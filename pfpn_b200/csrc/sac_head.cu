@@ -1,0 +1,426 @@
+// K3f -- the SAC-PFPN head in ONE pass over logits[B, A, P]: reparameterised sample (Gumbel-softmax straight-through,
+// forward), the tanh-squashed mixture log_prob of that sample (forward) and the backward of both, given dL/dsample
+// (from the critics) and dL/dlog_prob.
+//
+// Reference: /root/reference/networks/utils.py:156-186 (sample: RelaxedOneHotCategorical, mask2 :164-171, mask :176-183)
+// and :108-144 (log_prob on the tuple (sample, s_pre)); closed forms in SURVEY.md Appendix A1 / A2.  The boundary-faithful
+// form is three launches (pfpn_head_rsample_fwd, pfpn_head_logprob with TANH + dvalue, pfpn_head_rsample_bwd) that read
+// or write [B,A,P] five times and generate every Gumbel / normal draw twice; this kernel reads the logits once, writes the
+// gradient once (8AP + 12A + 8 bytes per state) and draws once.  It is issue / MUFU bound, not HBM bound:
+// per particle ~24 integer instructions of Philox, 8 MUFU operations (2 lg2 Gumbel, 2 Box-Muller, 2 tanh, 2 ex2).
+//
+// Structure (same skeleton as K1, csrc/head_logprob.cu, minus the cross-row dependency: everything here is row-local):
+//  * persistent CTAs, one tile = SLOTS consecutive states fetched by ONE bulk async copy (TMA, UBLKCP) into a ring of
+//    NSTAGE shared-memory stages; the gradient overwrites the logits in place and leaves with one bulk store issued
+//    by the producer warp once every compute thread has arrived on the stage's `done` barrier.  No block-wide barrier in
+//    the steady state; compute warps may drift NSTAGE-1 tiles apart.
+//  * a mixture row (b, a) is owned by 8 adjacent lanes; lane c owns the particles k = 32 j + 4 u + 16 (c / 4) + c % 4
+//    (u, j < 4): conflict-free at a 100-float row pitch (see K1) AND exactly the four particles one Philox4x32 block of
+//    the split kernels serves (k0, k0+32, k0+64, k0+96 with k0 = 4 u + 16 (c/4) + c%4), so with the same (seed, offset)
+//    this kernel draws the same Gumbel / normal variates as pfpn_head_rsample_fwd / _bwd.
+//  * per-row reductions are 3-step xor butterflies over the 8 lanes: one (max, argmax, winner's p) and one of five sums.
+//  * dloc / dlogstd: the mixture terms accumulate in registers (a thread's particle set never changes), the winner's
+//    straight-through terms in a per-slot shared-memory table written by the row's own lanes only; per-CTA partials
+//    are combined in CTA order by K1's finalize kernel -- no float atomics, bit-reproducible.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace pfpn {
+
+constexpr uint64_t kSacNormalStream = 1ull << 63;  // same stream split as csrc/rsample.cu
+constexpr int kSacMaxCtas = 148 * 2;
+
+__device__ __forceinline__ float sac_sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sac_bits_to_unit(uint32_t w) {  // 23 random bits -> (i + 0.5) 2^-23, strictly in (0, 1)
+  return __uint_as_float(0x3f800000u | (w >> 9)) - 0.99999994f;
+}
+__device__ __forceinline__ void sac_normal4(const uint4 q, float (&n)[4]) {  // two Box-Muller pairs, MUFU pipe
+  const float r0 = sac_sqrt_approx(-2.f * kLn2 * lg2f(sac_bits_to_unit(q.x)));
+  const float r1 = sac_sqrt_approx(-2.f * kLn2 * lg2f(sac_bits_to_unit(q.z)));
+  float s0, c0, s1, c1;
+  __sincosf(6.283185307179586f * sac_bits_to_unit(q.y), &s0, &c0);
+  __sincosf(6.283185307179586f * sac_bits_to_unit(q.w), &s1, &c1);
+  n[0] = r0 * c0;
+  n[1] = r0 * s0;
+  n[2] = r1 * c1;
+  n[3] = r1 * s1;
+}
+__device__ __forceinline__ float sac_fast_tanh(float x) {  // 1 - 2 / (1 + e^{2x}); |err| ~ 1e-7
+  const float e = ex2f(x * (2.f * kLog2e));
+  return 1.f - 2.f * rcpf(1.f + e);
+}
+
+struct SacHeadK {
+  pfpn_sac_head_args a;
+  float* part;  // [grid][2 * A * P]
+  int num_tiles;
+};
+
+// P = PT particles (32 < PT <= 128, so that every lane's four Philox blocks exist), A = AT action dims, 8 lanes per row.
+template <int PT, int AT, int SLOTS, int NSTAGE, bool FAST>
+__global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const SacHeadK kp) {
+  constexpr int P = PT, A = AT, AP = A * P, LPR = 8;
+  constexpr int NE = 13;                       // particle slots per lane: (u, j<3) -> 3u + j, (u = 0, j = 3) -> 12
+  constexpr int NTHR = SLOTS * A * LPR;        // compute threads
+  constexpr int TILE_F = SLOTS * AP;           // logits floats per tile
+  constexpr int STAGE_BYTES = ((TILE_F + SLOTS * A) * 4 + 127) & ~127;
+  static_assert(PT > 96 && PT <= 100 + 0 * AT, "instantiated for P = 100 (slot (0,3) valid for c < P - 96 <= 4)");
+  static_assert((A * LPR) % 32 == 0, "rows must not straddle warps");
+  const int B = kp.a.B;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_producer = warp == NTHR / 32;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* tail = smem_raw + (size_t)NSTAGE * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* done_bar = full_bar + NSTAGE;
+  float* rowbuf = reinterpret_cast<float*>(tail + 16 * NSTAGE);  // [NSTAGE][SLOTS * A] per-row log p
+  float* mu_s = rowbuf + NSTAGE * SLOTS * A;                     // [AP] each
+  float* sd_s = mu_s + AP;
+  float* isig_s = sd_s + AP;
+  float* cst_s = isig_s + AP;
+  float* acc_s = cst_s + AP;  // [SLOTS][2][AP] straight-through terms of the winning particles
+
+  if (is_producer && lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&done_bar[s]), (uint32_t)NTHR);
+    }
+    mbar_fence_init();
+  }
+  for (int i = tid; i < AP; i += NTHR + 32) {
+    const float ls = __ldg(&kp.a.logstd[i]), mu = __ldg(&kp.a.loc[i]);
+    mu_s[i] = mu;
+    sd_s[i] = FAST ? ex2f(ls * kLog2e) : expf(ls);  // (FAST: the same scale the split kernels use -> the same locations)
+    isig_s[i] = expf(-ls);
+    cst_s[i] = -(ls + kHalfLog2Pi) * kLog2e;
+  }
+  for (int i = tid; i < SLOTS * 2 * AP; i += NTHR + 32) acc_s[i] = 0.f;
+  __syncthreads();
+
+  const int first_tile = blockIdx.x, tile_step = gridDim.x;
+  int my_tiles = 0;
+  if (first_tile < kp.num_tiles) my_tiles = (kp.num_tiles - 1 - first_tile) / tile_step + 1;
+  const bool tail_exists = (B % SLOTS) != 0;
+  const int tail_tile = kp.num_tiles - 1;
+  const float* __restrict__ g_logits = kp.a.logits;
+  float* __restrict__ g_dlogits = kp.a.dlogits;
+  unsigned char* stage0 = smem_raw;
+
+  if (is_producer) {
+    // ===================== TMA producer warp =====================================================================
+    auto issue_load = [&](int it) {
+      const int tile = first_tile + it * tile_step;
+      if (it >= my_tiles || (tail_exists && tile == tail_tile)) return;  // the ragged last tile is copied cooperatively
+      const int st = it % NSTAGE;
+      const uint32_t bar = smem_u32(&full_bar[st]);
+      mbar_expect_tx(bar, (uint32_t)((TILE_F + SLOTS * A) * 4));
+      bulk_g2s(smem_u32(stage0) + st * STAGE_BYTES, g_logits + (size_t)tile * TILE_F, (uint32_t)(TILE_F * 4), bar);
+      bulk_g2s(smem_u32(stage0) + st * STAGE_BYTES + TILE_F * 4, kp.a.g_sample + (size_t)tile * SLOTS * A,
+               (uint32_t)(SLOTS * A * 4), bar);
+    };
+    if (lane == 0) {
+#pragma unroll
+      for (int d = 0; d < NSTAGE; ++d) issue_load(d);
+    }
+    for (int it = 0; it < my_tiles; ++it) {
+      const int st = it % NSTAGE;
+      const int tile = first_tile + it * tile_step;
+      mbar_wait(smem_u32(&done_bar[st]), (uint32_t)((it / NSTAGE) & 1));  // every compute thread finished (and fenced) this tile
+      if (lane < SLOTS) {  // log_prob of the state = sum over a of the per-row log p, fixed order
+        const int b = tile * SLOTS + lane;
+        if (b < B) {
+          const float* rb = rowbuf + st * SLOTS * A + lane * A;
+          float lp = 0.f;
+#pragma unroll 4
+          for (int aa = 0; aa < A; ++aa) lp += rb[aa];
+          kp.a.logp[b] = lp;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        if (!(tail_exists && tile == tail_tile)) {
+          bulk_s2g(g_dlogits + (size_t)tile * TILE_F, smem_u32(stage0) + st * STAGE_BYTES, (uint32_t)(TILE_F * 4));
+          bulk_commit();
+          bulk_wait_read<0>();  // the stage may be refilled once the store has READ it
+        }
+        issue_load(it + NSTAGE);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== compute threads ========================================================================
+    const int slot = tid / (A * LPR);
+    const int rem = tid - slot * (A * LPR);
+    const int a = rem >> 3, c = rem & 7;
+    const int kb0 = 16 * (c >> 2) + (c & 3);
+    const bool tail_ok = c < P - 96;  // slot (u = 0, j = 3): particle 96 + kb0
+    const float* mu_r = mu_s + a * P;
+    const float* sd_r = sd_s + a * P;
+    const float* isig_r = isig_s + a * P;
+    const float* cst_r = cst_s + a * P;
+    float* acc_r = acc_s + (size_t)slot * 2 * AP + a * P;
+    const Philox rng(kp.a.seed);
+    float acc1[NE], acc2[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) acc1[e] = acc2[e] = 0.f;
+
+    for (int it = 0; it < my_tiles; ++it) {
+      const int st = it % NSTAGE;
+      const int tile = first_tile + it * tile_step;
+      float* sbuf = reinterpret_cast<float*>(stage0 + (size_t)st * STAGE_BYTES);
+      const bool is_tail = tail_exists && tile == tail_tile;
+      const int b0 = tile * SLOTS;
+      if (!is_tail) {
+        mbar_wait(smem_u32(&full_bar[st]), (uint32_t)((it / NSTAGE) & 1));
+      } else {
+        const int nvalid = (B - b0) * AP;
+        for (int i = tid; i < nvalid; i += NTHR) sbuf[i] = __ldg(&g_logits[(size_t)b0 * AP + i]);
+        for (int i = tid; i < (B - b0) * A; i += NTHR) sbuf[TILE_F + i] = __ldg(&kp.a.g_sample[(size_t)b0 * A + i]);
+        asm volatile("bar.sync 1, %0;" ::"r"(NTHR) : "memory");  // compute threads only; the last tile only
+      }
+      const int b = b0 + slot;
+      const bool row_ok = b < B;
+      const long long r = (long long)(row_ok ? b : b0) * A + a;  // (masked rows recompute state b0, results discarded)
+      float* lg = sbuf + (row_ok ? slot : 0) * AP + a * P;
+
+      // ---- step 1: draws, noisy logits (log2 domain), locations -----------------------------------------------
+      float y[NE], nl[NE], p[NE], e2[NE];
+      float ymax = -3.402823466e38f, yfm = 0.f, pmax = 0.f;
+      int kmax = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kb = 4 * u + kb0;
+        float n4[4], nl4[4], ya4[4];
+        if (FAST) {
+          const uint4 q = rng(kp.a.offset, (uint64_t)(r * P + kb));
+          sac_normal4(rng(kp.a.offset, kSacNormalStream | (uint64_t)(r * P + kb)), n4);
+          const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) nl4[j] = fmaxf(-lg2f(sac_bits_to_unit(w4[j])), 4e-8f);  // -log2 u, kept off 0
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = kb + 32 * j;
+            const bool ok = j < 3 || (u == 0 && tail_ok);
+            const float U = ok ? __ldg(&kp.a.ext_uniform[r * P + k]) : 0.5f;
+            n4[j] = ok ? __ldg(&kp.a.ext_normal[r * P + k]) : 0.f;
+            nl4[j] = fmaxf(-log2f(U), 4e-8f);
+            ya4[j] = -logf(-logf(U));  // the reference's Gumbel, natural-log domain: decides the argmax bit-exactly
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j == 3 && u > 0) continue;  // particles >= 100: only slot (0, 3) exists
+          const int e = j < 3 ? 3 * u + j : 12;
+          const int k = kb + 32 * j;
+          const bool ok = j < 3 || tail_ok;
+          const float x = ok ? lg[k] : 0.f;
+          const float yf = ok ? fmaf(x, kLog2e, -(FAST ? lg2f(nl4[j]) : log2f(nl4[j]))) : -3.402823466e38f;
+          const float ycmp = FAST ? yf : (ok ? x + ya4[j] : -3.402823466e38f);  // (G + logits) / T, T = 1
+          const float pk = FAST ? fmaf(n4[j], sd_r[ok ? k : 0], mu_r[ok ? k : 0])
+                                : __fadd_rn(__fmul_rn(n4[j], sd_r[ok ? k : 0]), mu_r[ok ? k : 0]);
+          nl[e] = nl4[j];
+          y[e] = yf;
+          p[e] = pk;
+          const bool take = FAST ? (ycmp > ymax) : (ycmp > ymax || (ycmp == ymax && k < kmax));  // ties -> smallest index (tf.argmax)
+          if (take) {
+            ymax = ycmp;
+            yfm = yf;
+            kmax = k;
+            pmax = pk;
+          }
+        }
+      }
+      // ---- step 2: row argmax over the 8 lanes, carrying the winner's location --------------------------------
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        const float oy = __shfl_xor_sync(0xffffffffu, ymax, o), of = __shfl_xor_sync(0xffffffffu, yfm, o);
+        const float op = __shfl_xor_sync(0xffffffffu, pmax, o);
+        const int ok_ = __shfl_xor_sync(0xffffffffu, kmax, o);
+        const bool take = oy > ymax || (oy == ymax && ok_ < kmax);
+        if (take) {
+          ymax = oy;
+          yfm = of;
+          kmax = ok_;
+          pmax = op;
+        }
+      }
+      const float uu = pmax;  // s_pre: the winner's pre-tanh location
+      const int arg = kmax;
+      // tanh and 1 - tanh^2 without cancellation: e = exp(-2|u|), sech^2 = 4 e / (1 + e)^2
+      const float e2m = ex2f(-2.f * kLog2e * fabsf(uu)), q1 = rcpf(1.f + e2m);
+      const float omt2 = 4.f * e2m * q1 * q1;
+      const float t = copysignf(1.f - 2.f * e2m * q1, uu);
+
+      // ---- step 3: particle terms and the five row sums ----------------------------------------------------------
+      float S1 = 0.f, S2 = 0.f, T = 0.f, Sw = 0.f, Swt = 0.f;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int u = e < 12 ? e / 3 : 0, j = e < 12 ? e % 3 : 3;
+        const int k = 4 * u + kb0 + 32 * j;
+        const bool ok = e < 12 || tail_ok;
+        const int kk = ok ? k : 0;
+        const float w = ex2f(y[e] - yfm);       // softmax(logits + G) numerator; 0 for the masked slot
+        const float e1 = w * nl[e];             // = 2^(log2e * logit - yfm): softmax(logits) numerator, no second ex2
+        const float th = sac_fast_tanh(p[e]);
+        const float z = (uu - mu_r[kk]) * isig_r[kk];
+        const float n = ex2f(fmaf(z * z, -0.5f * kLog2e, cst_r[kk]));
+        const float x2 = e1 * n;
+        y[e] = w;
+        p[e] = th;
+        e2[e] = x2;
+        S1 += e1;
+        S2 += x2;
+        T = fmaf(x2 * z, isig_r[kk], T);
+        Sw += w;
+        Swt = fmaf(w, th, Swt);
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        S1 += __shfl_xor_sync(0xffffffffu, S1, o);
+        S2 += __shfl_xor_sync(0xffffffffu, S2, o);
+        T += __shfl_xor_sync(0xffffffffu, T, o);
+        Sw += __shfl_xor_sync(0xffffffffu, Sw, o);
+        Swt += __shfl_xor_sync(0xffffffffu, Swt, o);
+      }
+      // ---- step 4: row scalars ---------------------------------------------------------------------------------------
+      const float is1 = rcpf(S1);
+      // ln(1 - tanh^2 u) = ln 4 - 2|u| - 2 ln(1 + e^{-2|u|})   (utils.py:132-133 in a cancellation-free form)
+      const float corr = 2.f * kLn2 - 2.f * fabsf(uu) - 2.f * kLn2 * lg2f(1.f + e2m);
+      const float lnp = kLn2 * (lg2f(S2) - lg2f(S1)) - corr;  // -inf when every term underflowed (p == 0)
+      const bool p_ok = S2 > 0.f;
+      const float g = row_ok ? __ldg(&kp.a.g_lp[b]) : 0.f;
+      const float g_row = p_ok ? g : 0.f;                       // guard of utils.py:109-117
+      const float gs2 = p_ok ? g_row * rcpf(S2) : 0.f;
+      const float ga = row_ok ? sbuf[TILE_F + slot * A + a] : 0.f;
+      const float gu = fmaf(g_row, 2.f * t, -T * gs2);          // dL/du through log_prob: g (-sum r z / sigma + 2 tanh u)
+      const float coef = fmaf(gu, rcpf(fmaxf(1e-6f, omt2)), ga);  // mask + mask2 (utils.py:164-183)
+      const float iw = rcpf(Sw);
+      const float wd = coef * fmaf(Swt, iw, -t);                // sum_j w_j D_j,  D_j = (tanh p_j - t) coef
+      const float c1 = g_row * is1;
+      float* stp = row_ok ? lg : nullptr;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int u = e < 12 ? e / 3 : 0, j = e < 12 ? e % 3 : 3;
+        const int k = 4 * u + kb0 + 32 * j;
+        const bool ok = e < 12 || tail_ok;
+        const int kk = ok ? k : 0;
+        const float w = y[e];
+        const float rr = e2[e] * gs2;                            // g r_k
+        const float z = (uu - mu_r[kk]) * isig_r[kk];
+        const float d = fmaf(w * iw, fmaf(coef, p[e] - t, -wd), fmaf(-(w * nl[e]), c1, rr));
+        acc1[e] = fmaf(rr, z, acc1[e]);
+        acc2[e] = fmaf(rr, fmaf(z, z, -1.f), acc2[e]);
+        if (ok && stp != nullptr) stp[k] = d;
+      }
+      if (c == 0 && row_ok) {
+        // the winner's straight-through terms: dL/dp_{k*} = (1 - t^2) g_a + g_u; this row's lanes are the only writers of
+        // acc_r (slot, a) -- plain read-modify-write.  Stored times sigma: the finalize kernel divides dloc by sigma.
+        const float gp = fmaf(omt2, ga, gu) * sd_r[arg];
+        const float zs = (uu - mu_r[arg]) * isig_r[arg];          // = eps of the winner
+        acc_r[arg] += gp;
+        acc_r[AP + arg] += gp * zs;
+        const size_t o = (size_t)b * A + a;
+        kp.a.sample[o] = t;
+        kp.a.s_pre[o] = uu;
+        kp.a.idx[o] = arg;
+      }
+      if (c == 0) rowbuf[st * SLOTS * A + slot * A + a] = row_ok ? lnp : 0.f;
+      if (is_tail) {  // ragged last tile: plain stores of the valid part
+        asm volatile("bar.sync 1, %0;" ::"r"(NTHR) : "memory");
+        const int nvalid = (B - b0) * AP;
+        for (int i = tid; i < nvalid; i += NTHR) g_dlogits[(size_t)b0 * AP + i] = sbuf[i];
+      }
+      fence_async_smem();  // gradient STS -> visible to the bulk store
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&done_bar[st])) : "memory");
+    }
+    // ---- fold the register accumulators into this slot's table (own entries only) --------------------------------
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int u = e < 12 ? e / 3 : 0, j = e < 12 ? e % 3 : 3;
+      const int k = 4 * u + kb0 + 32 * j;
+      if (e < 12 || tail_ok) {
+        acc_r[k] += acc1[e];
+        acc_r[AP + k] += acc2[e];
+      }
+    }
+  }
+  __syncthreads();  // (the producer has waited for every bulk store's read; all tables complete)
+  float* part = kp.part + (size_t)blockIdx.x * 2 * AP;
+  for (int i = tid; i < 2 * AP; i += NTHR + 32) {
+    float s = 0.f;
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; ++sl) s += acc_s[(size_t)sl * 2 * AP + i];
+    part[i] = s;
+  }
+}
+
+}  // namespace pfpn
+
+using namespace pfpn;
+
+// (defined in head_logprob.cu) deterministic second stage over per-CTA [2*AP] partials: dloc = sum / sigma, dlogstd = sum
+extern "C" int pfpn_head_finalize_partials(const float* part, int32_t nparts, const float* logstd, float* dloc, float* dlogstd,
+                                           int32_t AP, pfpn_stream_t stream);
+
+namespace {
+constexpr int kSacSlots = 2, kSacStages = 3;
+template <bool FAST>
+int sac_launch(const SacHeadK& kp, int grid, cudaStream_t st) {
+  constexpr int P = 100, A = 36, AP = A * P;
+  constexpr int stage_bytes = ((kSacSlots * AP + kSacSlots * A) * 4 + 127) & ~127;
+  constexpr int smem = kSacStages * stage_bytes + 16 * kSacStages + kSacStages * kSacSlots * A * 4 + 4 * AP * 4 +
+                       kSacSlots * 2 * AP * 4 + 128;
+  auto fn = sac_head_kernel<P, A, kSacSlots, kSacStages, FAST>;
+  PFPN_CUDA_OK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  fn<<<grid, kSacSlots * A * 8 + 32, smem, st>>>(kp);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
+}
+}  // namespace
+
+extern "C" int pfpn_sac_head_workspace_bytes(int32_t A, int32_t P, size_t* bytes) {
+  if (!bytes || A <= 0 || P <= 0) return PFPN_ERR_ARG;
+  *bytes = (size_t)kSacMaxCtas * 2 * A * P * sizeof(float);
+  return PFPN_OK;
+}
+
+extern "C" int pfpn_sac_head_fwd_bwd(const pfpn_sac_head_args* args, void* workspace, size_t workspace_bytes,
+                                     pfpn_stream_t stream_) {
+  if (!args) return PFPN_ERR_ARG;
+  const pfpn_sac_head_args& a = *args;
+  if (a.B < 0 || a.A <= 0 || a.P <= 0) return PFPN_ERR_ARG;
+  if (a.A != 36 || a.P != 100) return PFPN_ERR_UNSUPPORTED;  // the BASELINE c5 shape; other shapes: the three-launch form
+  if (a.B == 0) return PFPN_OK;
+  if (!a.logits || !a.loc || !a.logstd || !a.g_sample || !a.g_lp || !a.sample || !a.s_pre || !a.idx || !a.logp || !a.dlogits ||
+      !a.dloc || !a.dlogstd)
+    return PFPN_ERR_ARG;
+  if ((a.ext_uniform == nullptr) != (a.ext_normal == nullptr)) return PFPN_ERR_ARG;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  if (!al16(a.logits) || !al16(a.dlogits) || !al16(a.g_sample) || !al16(workspace)) return PFPN_ERR_ALIGN;
+  size_t need;
+  pfpn_sac_head_workspace_bytes(a.A, a.P, &need);
+  if (!workspace || workspace_bytes < need) return PFPN_ERR_WORKSPACE;
+  int dev = 0, sms = 0;
+  PFPN_CUDA_OK(cudaGetDevice(&dev));
+  PFPN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  SacHeadK kp;
+  kp.a = a;
+  kp.part = reinterpret_cast<float*>(workspace);
+  kp.num_tiles = (a.B + kSacSlots - 1) / kSacSlots;
+  int grid = sms;  // one 19-warp CTA per SM
+  if (grid > kp.num_tiles) grid = kp.num_tiles;
+  if (grid > kSacMaxCtas) grid = kSacMaxCtas;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  int rc = a.ext_uniform == nullptr ? sac_launch<true>(kp, grid, st) : sac_launch<false>(kp, grid, st);
+  if (rc != PFPN_OK) return rc;
+  return pfpn_head_finalize_partials(kp.part, grid, a.logstd, a.dloc, a.dlogstd, a.A * a.P, stream_);
+}

@@ -51,6 +51,7 @@ struct SyncK {
   float* sum_active;
   int S, AP;
   float* params;
+  float* params_lo;
   float* m;
   float* v;
   float lr, b1, b2, eps;
@@ -171,6 +172,14 @@ __device__ __forceinline__ float sync_lr_t(const SyncK& k) {
     reinterpret_cast<float4*>(k.m)[i] = mi;                                                                         \
     reinterpret_cast<float4*>(k.v)[i] = vi;                                                                         \
     reinterpret_cast<float4*>(k.params)[i] = pi;                                                                    \
+    if (k.params_lo != nullptr) { /* the part of the new weights a tf32 operand drops: the GEMMs' B_lo operand */     \
+      float4 lo;                                                                                                    \
+      lo.x = pi.x - __uint_as_float(__float_as_uint(pi.x) & 0xffffe000u);                                           \
+      lo.y = pi.y - __uint_as_float(__float_as_uint(pi.y) & 0xffffe000u);                                           \
+      lo.z = pi.z - __uint_as_float(__float_as_uint(pi.z) & 0xffffe000u);                                           \
+      lo.w = pi.w - __uint_as_float(__float_as_uint(pi.w) & 0xffffe000u);                                           \
+      reinterpret_cast<float4*>(k.params_lo)[i] = lo;                                                               \
+    }                                                                                                               \
   }
 
 // One-phase: every rank reads every staged bucket (N-1 bucket volumes over NVLink per GPU); also the N == 1 path.
@@ -291,7 +300,7 @@ extern "C" int pfpn_sync_step(const pfpn_sync_args* a, pfpn_stream_t stream_) {
   k.grads = a->grads; k.n_params = a->n_params; k.n_total = a->n_total; k.clip = a->clip;
   k.new_mean = a->new_mean; k.new_std = a->new_std; k.state_mean = a->state_mean; k.state_std = a->state_std;
   k.max_active = a->max_active; k.sum_active = a->sum_active; k.S = a->S; k.AP = a->AP;
-  k.params = a->params; k.m = a->m; k.v = a->v; k.lr = a->lr; k.b1 = a->beta1; k.b2 = a->beta2; k.eps = a->eps;
+  k.params = a->params; k.params_lo = a->params_lo; k.m = a->m; k.v = a->v; k.lr = a->lr; k.b1 = a->beta1; k.b2 = a->beta2; k.eps = a->eps;
   k.counters = a->counters; k.norm_scale = a->norm_scale; k.part = reinterpret_cast<double*>(a->scratch);
   k.rank = a->rank; k.nranks = a->nranks;
   const bool two_phase = a->two_phase != 0 && a->nranks > 1;

@@ -43,6 +43,8 @@ struct TcParams {
   int M, N, K, ldc, ldh, epi;
   int k_chunk;  // split-K: K range per blockIdx.z (multiple of TC_BK); C then is [splits][M][ldc]
   float* colsum;  // weight gradient only (B MN-major): [splits][N] column sums of the B operand (= bias gradient)
+  int b_lo_tma;   // the B operand's low part (x - tf32(x)) exists in global memory (weights: split once per optimizer
+                  // step) and arrives by TMA through mapBlo; the splitter then only converts the A operand
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
@@ -111,7 +113,8 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                         const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+                                                         const __grid_constant__ CUtensorMap mapB,
+                                                         const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -139,6 +142,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
     mbar_fence_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+    if (p.b_lo_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBlo)) : "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "n"(512));
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % TC_STAGES;
         mbar_wait(empty(s), (uint32_t)(((kb / TC_STAGES) & 1) ^ 1));
-        mbar_expect_tx(full(s), 2 * TC_TILE_BYTES);
+        mbar_expect_tx(full(s), (p.b_lo_tma ? 3 : 2) * TC_TILE_BYTES);
         const uint32_t a_dst = base + s * TC_STAGE_BYTES, b_dst = a_dst + TC_TILE_BYTES;
         const int k0 = k_begin + kb * TC_BK;
         if (A_MN) {
@@ -168,6 +172,15 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
           for (int q = 0; q < TC_BN / 32; ++q) tma_load_2d(b_dst + q * 4096, &mapB, n0 + 32 * q, k0, full(s));
         } else {
           tma_load_2d(b_dst, &mapB, k0, n0, full(s));
+        }
+        if (p.b_lo_tma) {
+          const uint32_t l_dst = b_dst + TC_TILE_BYTES;
+          if (B_MN) {
+#pragma unroll
+            for (int q = 0; q < TC_BN / 32; ++q) tma_load_2d(l_dst + q * 4096, &mapBlo, n0 + 32 * q, k0, full(s));
+          } else {
+            tma_load_2d(l_dst, &mapBlo, k0, n0, full(s));
+          }
         }
       }
     }
@@ -241,7 +254,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
       for (int r = 0; r < 32; ++r)
         xl[r] = __float_as_uint(__uint_as_float(xh[r]) - __uint_as_float(xh[r] & 0xffffe000u));
       // B_lo first: it only touches shared memory, so it overlaps the MMAs that still read the TMEM slot
-      {
+      if (!p.b_lo_tma) {
         const float4* hi = reinterpret_cast<const float4*>(sa + TC_TILE_BYTES);
         float4* lo = reinterpret_cast<float4*>(const_cast<unsigned char*>(sa) + 2 * TC_TILE_BYTES);
 #pragma unroll
@@ -422,7 +435,8 @@ static int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld,
 }
 
 template <bool A_MN, bool B_MN>
-static int tc_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcParams& p, dim3 grid, cudaStream_t st) {
+static int tc_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBlo, const TcParams& p, dim3 grid,
+                     cudaStream_t st) {
   static int attr_dev = -1;  // per instantiation; the attribute is per device
   int dev = 0;
   PFPN_CUDA_OK(cudaGetDevice(&dev));
@@ -431,27 +445,30 @@ static int tc_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcP
                                       TC_SMEM_BYTES));
     attr_dev = dev;
   }
-  tc_gemm_kernel<A_MN, B_MN><<<grid, 256, TC_SMEM_BYTES, st>>>(mapA, mapB, p);
+  tc_gemm_kernel<A_MN, B_MN><<<grid, 256, TC_SMEM_BYTES, st>>>(mapA, mapB, mapBlo, p);
   PFPN_CUDA_OK(cudaGetLastError());
   return PFPN_OK;
 }
 
-static int tc_gemm_common(const float* A, int lda, const float* Bm, int ldb, bool b_mn, float* Cout, int ldc, const float* bias,
-                          const float* Hm, int ldh, int M, int N, int K, int epi, cudaStream_t st) {
+static int tc_gemm_common(const float* A, int lda, const float* Bm, const float* Blo, int ldb, bool b_mn, float* Cout, int ldc,
+                          const float* bias, const float* Hm, int ldh, int M, int N, int K, int epi, cudaStream_t st) {
   if (!A || !Bm || !Cout || M < 0 || N <= 0 || K <= 0 || epi < 0 || epi > 3) return PFPN_ERR_ARG;
   if ((epi == TC_EPI_BIAS || epi == TC_EPI_BIAS_RELU6) && !bias) return PFPN_ERR_ARG;
   if (epi == TC_EPI_MASK6 && !Hm) return PFPN_ERR_ARG;
   if (M == 0) return PFPN_OK;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-  if ((lda & 3) || (ldb & 3) || (ldc & 3) || (N & 3) || (K & 3) || !al16(A) || !al16(Bm) || !al16(Cout)) return PFPN_ERR_ALIGN;
-  CUtensorMap mapA, mapB;
+  if ((lda & 3) || (ldb & 3) || (ldc & 3) || (N & 3) || (K & 3) || !al16(A) || !al16(Bm) || !al16(Cout) || !al16(Blo))
+    return PFPN_ERR_ALIGN;
+  CUtensorMap mapA, mapB, mapBlo;
   int rc = make_map(&mapA, A, M, K, lda, TC_BM);
   if (rc != PFPN_OK) return rc;
   rc = make_map(&mapB, Bm, N, K, ldb, TC_BN, b_mn);
   if (rc != PFPN_OK) return rc;
-  TcParams p{Cout, bias, Hm, M, N, K, ldc, ldh, epi, (K + TC_BK - 1) / TC_BK * TC_BK, nullptr};
+  rc = make_map(&mapBlo, Blo ? Blo : Bm, N, K, ldb, TC_BN, b_mn);
+  if (rc != PFPN_OK) return rc;
+  TcParams p{Cout, bias, Hm, M, N, K, ldc, ldh, epi, (K + TC_BK - 1) / TC_BK * TC_BK, nullptr, Blo ? 1 : 0};
   dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
-  return b_mn ? tc_launch<false, true>(mapA, mapB, p, grid, st) : tc_launch<false, false>(mapA, mapB, p, grid, st);
+  return b_mn ? tc_launch<false, true>(mapA, mapB, mapBlo, p, grid, st) : tc_launch<false, false>(mapA, mapB, mapBlo, p, grid, st);
 }
 
 }  // namespace pfpn
@@ -463,7 +480,15 @@ using namespace pfpn;
 extern "C" int pfpn_tc_gemm_nt(const float* A, int32_t lda, const float* Bt, int32_t ldb, float* Cout, int32_t ldc,
                                const float* bias, const float* Hm, int32_t ldh, int32_t M, int32_t N, int32_t K,
                                int32_t epi, pfpn_stream_t stream_) {
-  return tc_gemm_common(A, lda, Bt, ldb, false, Cout, ldc, bias, Hm, ldh, M, N, K, epi, reinterpret_cast<cudaStream_t>(stream_));
+  return tc_gemm_common(A, lda, Bt, nullptr, ldb, false, Cout, ldc, bias, Hm, ldh, M, N, K, epi, reinterpret_cast<cudaStream_t>(stream_));
+}
+// Same with the low part of the B operand supplied (Bt_lo = Bt - tf32(Bt), pfpn_split_lo; same layout and ldb): the weights
+// are constant within an optimizer step, so their split is done once per step instead of once per tile per GEMM.
+extern "C" int pfpn_tc_gemm_nt_lo(const float* A, int32_t lda, const float* Bt, const float* Bt_lo, int32_t ldb, float* Cout,
+                                  int32_t ldc, const float* bias, const float* Hm, int32_t ldh, int32_t M, int32_t N, int32_t K,
+                                  int32_t epi, pfpn_stream_t stream_) {
+  if (!Bt_lo) return PFPN_ERR_ARG;
+  return tc_gemm_common(A, lda, Bt, Bt_lo, ldb, false, Cout, ldc, bias, Hm, ldh, M, N, K, epi, reinterpret_cast<cudaStream_t>(stream_));
 }
 
 // C[M,N] = epi(A[M,K] * B[K,N]): the tensor-core twin of pfpn_mlp_linear_fwd with W as stored ([in, out] row-major,
@@ -471,7 +496,39 @@ extern "C" int pfpn_tc_gemm_nt(const float* A, int32_t lda, const float* Bt, int
 extern "C" int pfpn_tc_gemm_nn(const float* A, int32_t lda, const float* B, int32_t ldb, float* Cout, int32_t ldc,
                                const float* bias, const float* Hm, int32_t ldh, int32_t M, int32_t N, int32_t K,
                                int32_t epi, pfpn_stream_t stream_) {
-  return tc_gemm_common(A, lda, B, ldb, true, Cout, ldc, bias, Hm, ldh, M, N, K, epi, reinterpret_cast<cudaStream_t>(stream_));
+  return tc_gemm_common(A, lda, B, nullptr, ldb, true, Cout, ldc, bias, Hm, ldh, M, N, K, epi, reinterpret_cast<cudaStream_t>(stream_));
+}
+extern "C" int pfpn_tc_gemm_nn_lo(const float* A, int32_t lda, const float* B, const float* B_lo, int32_t ldb, float* Cout,
+                                  int32_t ldc, const float* bias, const float* Hm, int32_t ldh, int32_t M, int32_t N, int32_t K,
+                                  int32_t epi, pfpn_stream_t stream_) {
+  if (!B_lo) return PFPN_ERR_ARG;
+  return tc_gemm_common(A, lda, B, B_lo, ldb, true, Cout, ldc, bias, Hm, ldh, M, N, K, epi, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+// lo[i] = x[i] - tf32(x[i]) (tf32 = the top 19 bits; exact in fp32): the part of an fp32 operand the tensor core drops
+namespace pfpn {
+__global__ void split_lo_kernel(const float4* __restrict__ x, float4* __restrict__ lo, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    float4 l;
+    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+    lo[i] = l;
+  }
+}
+}  // namespace pfpn
+extern "C" int pfpn_split_lo(const float* x, float* lo, size_t n, pfpn_stream_t stream_) {
+  if (!x || !lo || (n & 3)) return PFPN_ERR_ARG;
+  if (n == 0) return PFPN_OK;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(lo)) & 15u) return PFPN_ERR_ALIGN;
+  size_t grid = (n / 4 + 255) / 256;
+  if (grid > 592) grid = 592;
+  pfpn::split_lo_kernel<<<(unsigned)grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(lo), n / 4);
+  PFPN_CUDA_OK(cudaGetLastError());
+  return PFPN_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -530,9 +587,9 @@ extern "C" int pfpn_tc_linear_bwd_weight(const float* X, int32_t ldx, const floa
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   float* out = splits > 1 ? reinterpret_cast<float*>(workspace) : dW;
   float* cs_part = db ? reinterpret_cast<float*>(workspace) + (size_t)splits * K * N : nullptr;
-  TcParams p{out, nullptr, nullptr, K, N, M, N, 0, TC_EPI_NONE, chunk, cs_part};
+  TcParams p{out, nullptr, nullptr, K, N, M, N, 0, TC_EPI_NONE, chunk, cs_part, 0};
   dim3 grid((N + TC_BN - 1) / TC_BN, (K + TC_BM - 1) / TC_BM, splits);
-  rc = tc_launch<true, true>(mapA, mapB, p, grid, st);
+  rc = tc_launch<true, true>(mapA, mapB, mapB, p, grid, st);
   if (rc != PFPN_OK) return rc;
   if (splits > 1) {
     const size_t n4 = (size_t)K * N / 4;

@@ -159,6 +159,8 @@ class SyncReplicasAdam:
             a.state_mean, a.state_std, a.S = net.state_mean.data_ptr(), net.state_std.data_ptr(), net.S
         a.max_active, a.sum_active, a.AP = net.max_active.data_ptr(), net.sum_active.data_ptr(), net.A * net.P
         a.params, a.m, a.v = net.params.data_ptr(), self.m.data_ptr(), self.v.data_ptr()
+        if getattr(net, "use_presplit", False) and getattr(net, "use_tensor_cores", False):
+            a.params_lo = net.params_lo.data_ptr()  # the step keeps the GEMMs' pre-split weight halves current
         a.lr, a.beta1, a.beta2, a.eps = self.lr, self.beta1, self.beta2, self.eps
         a.counters, a.norm_scale = net.dev_counters.data_ptr(), self.norm_scale.data_ptr()
         a.scratch, a.scratch_bytes = self._scratch.data_ptr(), self._scratch.numel()
@@ -187,6 +189,11 @@ class SyncReplicasAdam:
             op()
 
     def _launch_legacy(self, net, st):
+        if hasattr(net, "invalidate_lo"):
+            net.invalidate_lo()  # these kernels update the parameters through raw pointers without the low halves
+        return self._launch_legacy_impl(net, st)
+
+    def _launch_legacy_impl(self, net, st):
         """Round-1 chain, kept as the comparison point (PFPN_SYNC_STEP=0) and as the NCCL fallback: clip, pack, exchange
         (peer kernel or NCCL all-reduce), Adam, unpack -- host-side step numbers in the arguments."""
         # 1. local clip (before aggregation: optimizer/clip_by_global_norm/mul_* feed the accumulators)
@@ -286,7 +293,11 @@ class GraphedUpdate:
         self._set(state, action, value, log_prob, advantage)
         net, opt = self.net, self.opt
         args = tuple(self.inputs[k] for k in self.KEYS)
-        if self._warm > 0 or os.environ.get("PFPN_GRAPH", "1") == "0":  # eager steps: allocate every buffer, map the peers
+        # Replay pays where the update is a chain of launch-latency-sized kernels (<= ~16k states per GPU: 0.69 vs 0.71 ms at
+        # 8192, 1.18 vs 1.22 at 16384); at 65536 states the eager multi-stream issue order overlaps the branches better
+        # (4.43 vs 4.73 ms measured), so large shards stay eager.
+        too_big = self.B > int(os.environ.get("PFPN_GRAPH_MAX_BATCH", "24576"))
+        if self._warm > 0 or too_big or os.environ.get("PFPN_GRAPH", "1") == "0":  # eager steps (also: allocate buffers, map peers)
             self._warm -= 1
             self.losses = net.compute_gradients(*args)
             opt.apply_gradients(net)

@@ -109,6 +109,7 @@ class ParticleFilteringClipPPONetwork:
         # fp32 FFMA anchor is requested
         import os
         self.use_tensor_cores = os.environ.get("PFPN_TRUNK", "tc") != "ffma"
+        self.use_presplit = os.environ.get("PFPN_PRESPLIT", "1") != "0"
 
     # ------------------------------------------------------------------------------ build ----
     def _derive_sample_stream(self):
@@ -145,11 +146,16 @@ class ParticleFilteringClipPPONetwork:
         self.n_params = n = _pad4(sum(_pad4(l.k * l.n_out) + _pad4(l.n_out) if k == "lin" else _pad4(A * P)
                                       for k, l in order))
         self.params = torch.zeros(n, dtype=torch.float32, device=dev)
+        # params - tf32(params): the low halves of the weights for the 3xTF32 GEMMs' B operand, split once per optimizer
+        # step (written by the optimizer kernel) instead of once per tile per GEMM (K6)
+        self.params_lo = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._lo_version = -1
         # gradient bucket = [grads | pushed statistics] : one all-reduce (sync_model.py:92-96)
         self.bucket = torch.zeros(n + _pad4(self.n_stats), dtype=torch.float32, device=dev)
         self.grads = self.bucket[:n]
         for kind, l in order:
             if kind == "lin":
+                l.W_lo = self.params_lo[off:off + l.k * l.n_out].view(l.k, l.n_out)
                 l.W, l.dW = take(l.k * l.n_out, (l.k, l.n_out))
                 l.b, l.db = take(l.n_out, (l.n_out,))
             elif kind == "samples":
@@ -190,6 +196,7 @@ class ParticleFilteringClipPPONetwork:
         # the critic trunk is independent of the actor trunk + head: run it on a second stream (a parallel branch of the
         # captured graph); pays off when a rank's minibatch shard no longer fills the GPU with one GEMM
         self.overlap_critic = os.environ.get("PFPN_CRITIC_STREAM", "1") != "0"
+        self.overlap_wgrad = os.environ.get("PFPN_WGRAD_STREAM", "1") != "0"
 
     def _ensure_counters(self, calls=None, adam_step=None):
         """Upload the host-side step numbers when the device copy is stale (first use, checkpoint resume, a switch between
@@ -222,9 +229,29 @@ class ParticleFilteringClipPPONetwork:
             self._act[name] = t
         return t
 
+    def _lo_ok(self):
+        """The low halves follow the parameters: the optimizer kernel writes them; any OTHER in-place change of
+        ``self.params`` (initialisation, checkpoint load, a torch op -- they bump the tensor's version counter) or a kernel
+        that edits parameters through raw pointers (resample tick, legacy optimizer path: they call ``invalidate_lo``)
+        triggers one re-split here."""
+        if not self.use_presplit:
+            return False
+        if self._lo_version != self.params._version:
+            _cabi.check(_cabi.pfpn_split_lo(self.params.data_ptr(), self.params_lo.data_ptr(), self.n_params, _stream_ptr()))
+            self._lo_version = self.params._version
+        return True
+
+    def invalidate_lo(self):
+        self._lo_version = -1
+
     def _linear(self, l: _Linear, X, Y, relu6):
         if self.use_tensor_cores and l.n_out > 1:
             # W [in, out] as stored is the MN-major B operand: no transposed copy of the weights
+            if self._lo_ok():
+                _cabi.check(_cabi.pfpn_tc_gemm_nn_lo(X.data_ptr(), X.stride(0), l.W.data_ptr(), l.W_lo.data_ptr(), l.n_out,
+                                                     Y.data_ptr(), Y.stride(0), l.b.data_ptr(), None, 0, X.shape[0], l.n_out,
+                                                     l.k, 2 if relu6 else 1, _stream_ptr()))
+                return
             _cabi.check(_cabi.pfpn_tc_gemm_nn(X.data_ptr(), X.stride(0), l.W.data_ptr(), l.n_out, Y.data_ptr(), Y.stride(0),
                                               l.b.data_ptr(), None, 0, X.shape[0], l.n_out, l.k, 2 if relu6 else 1,
                                               _stream_ptr()))
@@ -407,15 +434,32 @@ class ParticleFilteringClipPPONetwork:
         """acts[i] is the input of layers[i]; dY is dL/d(output of the last layer).  `tag` names the scratch buffer (the
         actor and critic stacks may run concurrently on two streams)."""
         st = _stream_ptr()
+        # The weight gradient and the input gradient of a layer both only READ dY: the weight-gradient GEMMs run on an
+        # auxiliary stream (a further parallel branch of the captured graph), so that their CTAs fill the SMs the
+        # input-gradient GEMM's last wave leaves idle -- at 8192 states per GPU no GEMM of this net fills 148 SMs evenly.
+        cur = torch.cuda.current_stream(self.device) if self.device.type == "cuda" else None
+        aux = self._aux_stream(tag) if (getattr(self, "overlap_wgrad", False) and cur is not None) else None
+        aux_used = False
         for i in range(len(layers) - 1, -1, -1):
             l, X = layers[i], acts[i]
             M = X.shape[0]
             if self.use_tensor_cores and l.n_out > 1 and M >= 512:
-                self._tc_wgrad(l, X, dY, M, tag)
+                if aux is not None:
+                    aux.wait_stream(cur)  # dY of this layer (and everything before it) is complete on `cur`
+                    aux_used = True
+                    with torch.cuda.stream(aux):
+                        self._tc_wgrad(l, X, dY, M, tag + "w")
+                else:
+                    self._tc_wgrad(l, X, dY, M, tag)
                 if i > 0:
                     dX = self._buf(f"d_{l.name}", M, l.k)
-                    _cabi.check(_cabi.pfpn_tc_gemm_nt(dY.data_ptr(), dY.stride(0), l.W.data_ptr(), l.n_out, dX.data_ptr(),
-                                                      dX.stride(0), None, X.data_ptr(), X.stride(0), M, l.k, l.n_out, 3, st))
+                    if self._lo_ok():
+                        _cabi.check(_cabi.pfpn_tc_gemm_nt_lo(dY.data_ptr(), dY.stride(0), l.W.data_ptr(), l.W_lo.data_ptr(), l.n_out,
+                                                             dX.data_ptr(), dX.stride(0), None, X.data_ptr(), X.stride(0), M, l.k,
+                                                             l.n_out, 3, st))
+                    else:
+                        _cabi.check(_cabi.pfpn_tc_gemm_nt(dY.data_ptr(), dY.stride(0), l.W.data_ptr(), l.n_out, dX.data_ptr(),
+                                                          dX.stride(0), None, X.data_ptr(), X.stride(0), M, l.k, l.n_out, 3, st))
                     dY = dX
                 continue
             n = C.c_size_t(0)
@@ -435,6 +479,14 @@ class ParticleFilteringClipPPONetwork:
                 _cabi.check(_cabi.pfpn_mlp_linear_bwd_input(dY.data_ptr(), ldy, l.W.data_ptr(), X.data_ptr(), dX.data_ptr(),
                                                             dX.stride(0), M, l.k, l.n_out, st))
                 dY = dX
+        if aux_used:  # (joining a stream that never forked would break a graph capture)
+            cur.wait_stream(aux)
+
+    def _aux_stream(self, tag):
+        d = self.__dict__.setdefault("_aux_streams", {})
+        if tag not in d:
+            d[tag] = torch.cuda.Stream(self.device)
+        return d[tag]
 
     def _tc_wgrad(self, l, X, dY, M, tag=""):
         """dW and db on the tensor cores: X and dY as stored (MN-major operands), split-K GEMM; the bias
@@ -470,6 +522,8 @@ class ParticleFilteringClipPPONetwork:
                                   self.policy_weight, resample=self.resample, threshold=self.resample_threshold,
                                   tanh=self.normalize_policy_output_, seed=self.seed + 1, offset=3 * self.global_step)
             self.train_flag = 0
+            self.invalidate_lo()  # the resampler rewired fc_policy columns through raw pointers:
+            self._lo_ok()         # re-split now (a graph-replayed next step never runs the Python check)
             return True
         return False
 

@@ -44,6 +44,7 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
     def init(self):
         S, A, P, dev = self.S, self.A, self.P, self.device
         self._derive_sample_stream()
+        self.use_presplit = False  # (the SAC optimizer keeps no pre-split weight halves: the GEMMs split on the fly)
         self.Sp, self.QI = _pad4(S), _pad4(S + A)
         dims_a = [self.Sp] + self.actor_net_shape
         self.actor = [_Linear(f"actor/fc{i+1}", (S if i == 0 else dims_a[i]), dims_a[i + 1], dims_a[i])

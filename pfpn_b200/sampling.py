@@ -97,6 +97,47 @@ def rsample_bwd(logits, loc, logstd, g_sample, g_s_pre, *, seed=0, offset=0, ext
     return dlogits, dloc, dlogstd
 
 
+def sac_head_fused(logits, loc, logstd, g_sample, g_lp, *, seed=0, offset=0, ext_uniform=None, ext_normal=None,
+                   out: Optional[dict] = None, dlogits_out=None):
+    """K3f: rsample forward + tanh log_prob forward + the backward of both in one pass (utils.py:108-144,156-186).
+    Returns dict(sample, s_pre, idx, logp, dlogits, dloc, dlogstd).  A = 36, P = 100 only (PfpnError -3 otherwise)."""
+    logits, loc, logstd = _f32c(logits, "logits"), _f32c(loc, "loc"), _f32c(logstd, "logstd")
+    g_sample, g_lp = _f32c(g_sample, "g_sample"), _f32c(g_lp, "g_lp")
+    B, A, P = logits.shape
+    if g_sample.shape != (B, A) or g_lp.shape != (B,):
+        raise ValueError("g_sample [B, A], g_lp [B]")
+    dev = logits.device
+    a = _cabi.SacHeadArgs()
+    a.logits, a.loc, a.logstd, a.g_sample, a.g_lp = (t.data_ptr() for t in (logits, loc, logstd, g_sample, g_lp))
+    keep = [logits, loc, logstd, g_sample, g_lp]
+    if (ext_uniform is None) != (ext_normal is None):
+        raise ValueError("pass both ext_uniform and ext_normal or neither")
+    if ext_uniform is not None:
+        ext_uniform, ext_normal = _f32c(ext_uniform, "ext_uniform"), _f32c(ext_normal, "ext_normal")
+        keep += [ext_uniform, ext_normal]
+        a.ext_uniform, a.ext_normal = ext_uniform.data_ptr(), ext_normal.data_ptr()
+    out = {} if out is None else out
+    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    if out.get("sample") is None:
+        out.update(sample=f(B, A), s_pre=f(B, A), idx=_i32(B, A, device=dev), logp=f(B), dloc=f(A, P), dlogstd=f(A, P))
+    if dlogits_out is not None:
+        out["dlogits"] = dlogits_out
+    if out.get("dlogits") is None:
+        out["dlogits"] = f(B, A, P)
+    a.sample, a.s_pre, a.idx, a.logp = (out[k].data_ptr() for k in ("sample", "s_pre", "idx", "logp"))
+    a.dlogits, a.dloc, a.dlogstd = (out[k].data_ptr() for k in ("dlogits", "dloc", "dlogstd"))
+    a.seed, a.offset, a.B, a.A, a.P = seed, offset, B, A, P
+    n = C.c_size_t(0)
+    _cabi.check(_cabi.pfpn_sac_head_workspace_bytes(A, P, C.byref(n)))
+    key = (dev, "sacf", n.value)
+    ws = _stats_ws.get(key)
+    if ws is None:
+        ws = _stats_ws[key] = torch.empty(n.value, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.pfpn_sac_head_fwd_bwd(C.byref(a), ws.data_ptr(), ws.numel(), _stream_ptr()))
+    return out
+
+
 def mean_action(logits, loc, tanh: bool = False):
     """utils.py:202-236 (forward).  Returns (action [B,A], idx [B,A])."""
     logits, loc = _f32c(logits, "logits"), _f32c(loc, "loc")

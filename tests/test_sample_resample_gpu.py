@@ -290,3 +290,70 @@ def test_resample_philox_mode_is_replica_deterministic(cuda_dev):
     for k in ("loc", "logstd", "bias", "weight"):
         assert torch.equal(outs[0][0][k], outs[1][0][k])
     assert torch.equal(outs[0][1]["src"], outs[1][1]["src"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K3f: the SAC head in one pass (pfpn_sac_head_fwd_bwd) -- rsample forward + tanh log_prob forward + backward of both
+# ---------------------------------------------------------------------------------------------------------------------
+def _sac_inputs(B, A, P, seed):
+    from pfpn_b200.network import initial_particles
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(B, A, P, generator=g) * 2.0
+    loc, logstd = initial_particles(A, P, True)
+    loc = loc + 0.02 * torch.randn(A, P, generator=g)
+    logstd = logstd + 0.1 * torch.randn(A, P, generator=g)
+    g_sample = torch.randn(B, A, generator=g)
+    g_lp = torch.randn(B, generator=g) * 0.3
+    tiny = float(np.finfo(np.float32).tiny)
+    U = torch.rand(B, A, P, generator=g).clamp_min(tiny)
+    EPS = torch.randn(B, A, P, generator=g)
+    return logits, loc, logstd, g_sample, g_lp, U, EPS
+
+
+@pytest.mark.parametrize("B", [37, 256])
+def test_fused_sac_head_matches_oracle_with_external_draws(cuda_dev, B):
+    """Verification mode against the fp64 oracle fed the same uniforms / normals (utils.py:108-144,156-186 with the three
+    custom gradients): argmax particle bit-exact, everything else 1e-5 norm-wise.  B = 37: ragged last tile."""
+    from oracle import head as oh
+    from pfpn_b200 import sampling
+    A, P = 36, 100
+    logits, loc, logstd, g_sample, g_lp, U, EPS = _sac_inputs(B, A, P, seed=B)
+    lg, lc, ls = (t.double().requires_grad_(True) for t in (logits, loc, logstd))
+    dist = oh.MixtureGaussianOracle(lg, lc, ls.exp(), True)
+    smp, s_ = dist.sample(1, uniform=U.double(), normal=EPS.double())
+    logp = dist.log_prob((smp[0], s_[0]))
+    (torch.sum(g_sample.double() * smp[0]) + torch.sum(g_lp.double() * logp)).backward()
+    cu = lambda t: t.to(cuda_dev)
+    out = sampling.sac_head_fused(cu(logits), cu(loc), cu(logstd), cu(g_sample), cu(g_lp), ext_uniform=cu(U), ext_normal=cu(EPS))
+    torch.cuda.synchronize()
+    assert np.array_equal(out["idx"].cpu().numpy(), dist.dis_action.numpy())
+    assert rel(out["s_pre"], s_[0].detach()) < TOL and rel(out["sample"], smp[0].detach()) < TOL
+    assert rel(out["logp"], logp.detach()) < TOL
+    assert rel(out["dlogits"], lg.grad) < TOL
+    assert rel(out["dloc"], lc.grad) < TOL and rel(out["dlogstd"], ls.grad) < TOL
+
+
+def test_fused_sac_head_equals_the_three_launch_form_in_production_mode(cuda_dev):
+    """Philox mode: with the same (seed, offset) the fused kernel draws the same variates as pfpn_head_rsample_fwd / _bwd, so
+    it must reproduce the boundary-faithful three-launch composition (rsample fwd, tanh log_prob fwd+bwd with dvalue,
+    rsample bwd) at a size no external-draw test reaches -- and be bit-reproducible."""
+    from pfpn_b200 import _cabi, head, sampling
+    B, A, P = 4099, 36, 100
+    logits, loc, logstd, g_sample, g_lp, _, _ = _sac_inputs(B, A, P, seed=5)
+    cu = lambda t: t.to(cuda_dev)
+    logits, loc, logstd, g_sample, g_lp = map(cu, (logits, loc, logstd, g_sample, g_lp))
+    smp, s_pre, idx = sampling.rsample_fwd(logits, loc, logstd, seed=11, offset=6)
+    o = head.head_call(_cabi.HEAD_GRAD, logits, loc, logstd, s_pre, tanh=True, g_lp=g_lp, want_dvalue=True)
+    dl2, dloc2, dls2 = sampling.rsample_bwd(logits, loc, logstd, g_sample, o["dvalue"], seed=11, offset=6)
+    ref = dict(dlogits=o["dlogits"] + dl2, dloc=o["dloc"] + dloc2, dlogstd=o["dlogstd"] + dls2)
+    f1 = sampling.sac_head_fused(logits, loc, logstd, g_sample, g_lp, seed=11, offset=6)
+    f2 = sampling.sac_head_fused(logits, loc, logstd, g_sample, g_lp, seed=11, offset=6)
+    torch.cuda.synchronize()
+    assert torch.equal(f1["idx"], idx)
+    assert rel(f1["s_pre"], s_pre) < 1e-6 and rel(f1["sample"], smp) < 1e-6
+    assert rel(f1["logp"], o["lp"]) < TOL
+    for k in ("dlogits", "dloc", "dlogstd"):
+        assert rel(f1[k], ref[k]) < 2 * TOL, k
+        assert torch.equal(f1[k], f2[k]), k  # no atomics, fixed summation order
+    f3 = sampling.sac_head_fused(logits, loc, logstd, g_sample, g_lp, seed=11, offset=8)
+    assert not torch.equal(f3["idx"], idx)  # another call counter -> other draws

@@ -85,3 +85,30 @@ def test_tc_wgrad_operands_as_stored(cuda_dev, M, K, N):
     _cabi.check(_cabi.pfpn_tc_linear_bwd_weight(Xd.data_ptr(), K, Yd.data_ptr(), N, dW2.data_ptr(), db2.data_ptr(), M, K, N,
                                                 ws.data_ptr(), ws.numel(), _stream_ptr()))
     assert torch.equal(dW, dW2) and torch.equal(db, db2)
+
+
+@pytest.mark.parametrize("M,N,K", [(777, 512, 1024), (300, 1260, 512)])
+def test_presplit_weight_operand_is_bit_identical(cuda_dev, M, N, K):
+    """pfpn_tc_gemm_{nn,nt}_lo (B_lo = B - tf32(B) precomputed by pfpn_split_lo, fetched by TMA) vs the on-the-fly splitter."""
+    from pfpn_b200 import _cabi
+    from pfpn_b200.head import _stream_ptr
+    g = torch.Generator().manual_seed(M)
+    X = torch.randn(M, K, generator=g).to(cuda_dev)
+    W = (torch.randn(K, N, generator=g) * 0.05).to(cuda_dev)
+    b = torch.randn(N, generator=g).to(cuda_dev)
+    dY = torch.randn(M, N, generator=g).to(cuda_dev)
+    Wlo = torch.empty_like(W)
+    st = _stream_ptr()
+    _cabi.check(_cabi.pfpn_split_lo(W.data_ptr(), Wlo.data_ptr(), W.numel(), st))
+    hi = (W.view(torch.int32) & -8192).view(torch.float32)
+    assert torch.equal(Wlo, W - hi)
+    Y0, Y1 = torch.empty(M, N, device=cuda_dev), torch.empty(M, N, device=cuda_dev)
+    _cabi.check(_cabi.pfpn_tc_gemm_nn(X.data_ptr(), K, W.data_ptr(), N, Y0.data_ptr(), N, b.data_ptr(), None, 0, M, N, K, 2, st))
+    _cabi.check(_cabi.pfpn_tc_gemm_nn_lo(X.data_ptr(), K, W.data_ptr(), Wlo.data_ptr(), N, Y1.data_ptr(), N, b.data_ptr(), None, 0,
+                                         M, N, K, 2, st))
+    assert torch.equal(Y0, Y1)
+    D0, D1 = torch.empty(M, K, device=cuda_dev), torch.empty(M, K, device=cuda_dev)
+    _cabi.check(_cabi.pfpn_tc_gemm_nt(dY.data_ptr(), N, W.data_ptr(), N, D0.data_ptr(), K, None, X.data_ptr(), K, M, K, N, 3, st))
+    _cabi.check(_cabi.pfpn_tc_gemm_nt_lo(dY.data_ptr(), N, W.data_ptr(), Wlo.data_ptr(), N, D1.data_ptr(), K, None, X.data_ptr(), K,
+                                         M, K, N, 3, st))
+    assert torch.equal(D0, D1)

@@ -36,7 +36,23 @@ ms = e0.elapsed_time(e1) / n
 cpu_issue_ms = (w1 - w0) * 1e3 / n
 t = torch.tensor([ms], device=dev)
 if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+# ---- the same update captured once in a CUDA graph and replayed ----
+from pfpn_b200.learner import GraphedUpdate
+gu = GraphedUpdate(net, opt, B, warmup=0)
+gu._set(state, action, value, lp_old, adv)
+for _ in range(3): gu.run()
+torch.cuda.synchronize()
+if world > 1: dist.barrier()
+e0.record(); w0 = time.perf_counter()
+for _ in range(n): gu.run()
+w1 = time.perf_counter()
+e1.record(); torch.cuda.synchronize()
+tg = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+if world > 1: dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+graph_issue_ms = (w1 - w0) * 1e3 / n
 if rank == 0:
+    print(json.dumps({"graph_ms_per_update": round(float(tg), 3), "graph_host_issue_ms": round(graph_issue_ms, 3),
+                      "critic_stream": os.environ.get("PFPN_CRITIC_STREAM", "1")}))
     flops = 12.6e6 * B_total
     print(json.dumps({"world": world, "B_total": B_total, "ms_per_update": round(float(t), 3), "samples_per_s": round(B_total / float(t) * 1e3),
                       "trunk_TFLOPs": round(flops / float(t) / 1e9, 1), "host_issue_ms_per_update": round(cpu_issue_ms, 3), "params_equal_hash": float(net.params.double().sum())}))
