@@ -568,6 +568,26 @@ def run_extra(dev, rank, world, stream, maxr):
     out["c2_head_B4096_per_gpu"] = {"ppo_fwd_bwd_us": maxr(ms) * 1e3, "fwd_only_us": maxr(ms_f) * 1e3, "plain_sample_us": maxr(ms_s) * 1e3,
                                     "Mstates_s_all_gpus": world * B2 / maxr(ms) / 1e3,
                                     "note": "41.9 MB working set is L2-resident: a latency case, not a roofline case"}
+    # ---- rollout side at the headline shape: one fused pass vs the three-kernel form (K2 + K1 forward + K4) ----
+    Br = B_PER_GPU
+    gr = torch.Generator(device="cuda")
+    gr.manual_seed(SEED + 7 + rank)
+    lgr = torch.randn(Br, A, P, device=dev, generator=gr) * 2.0
+    locr, lsr = (x.to(dev) for x in synth.particle_grid(A, P, torch.Generator().manual_seed(SEED)))
+    mxa, sma = torch.zeros(A, P, device=dev), torch.zeros(A, P, device=dev)
+    t_s, _ = timed(lambda: sampling.sample_plain(lgr, locr, lsr, seed=1, offset=2), 10, stream)
+    act_r, _ = sampling.sample_plain(lgr, locr, lsr, seed=1, offset=2)
+    bufr = {}
+    t_f, _ = timed(lambda: head.head_call(_cabi.HEAD_FWD, lgr, locr, lsr, act_r, out=bufr), 10, stream)
+    t_k, _ = timed(lambda: sampling.stats_update(lgr, mxa, sma), 10, stream)
+    t_z, _ = timed(lambda: sampling.rollout_fused(lgr, locr, lsr, seed=1, offset=2, max_active=mxa, sum_active=sma), 10, stream)
+    ro_bytes = (4 * A * P + 8 * A + 8) * Br
+    out["rollout_head_B65536_per_gpu"] = {
+        "fused_one_pass_us": maxr(t_z) * 1e3, "frac_of_hbm_peak": ro_bytes / (maxr(t_z) * 1e-3) / 1e9 / peak,
+        "alg_bytes_per_state": 4 * A * P + 8 * A + 8,
+        "three_kernel_form_us": {"sample": maxr(t_s) * 1e3, "log_prob_fwd": maxr(t_f) * 1e3, "stats": maxr(t_k) * 1e3},
+        "note": "sample + log_prob + activity statistics of a batched rollout step (ppo.py:56-62, a2c.py:346-365)"}
+    del lgr
     # ---- c3 ----
     res = {}
     for P3 in (10, 35, 100):

@@ -137,6 +137,31 @@ typedef struct pfpn_sample_args {
 } pfpn_sample_args;
 int pfpn_head_sample(const pfpn_sample_args* args, pfpn_stream_t stream);
 
+/* K2f  the rollout side of the head in ONE pass over logits: particle index (TF Multinomial CPU semantics, bit-exact
+ * with ext_uniform), action, mixture log_prob of that action, categorical entropy, and the running activity statistics
+ * (max_active = max(max_active, max_b softmax), sum_active += sum_b softmax; both NULL to skip them).
+ * Replaces: what ClipPPONetwork.run executes per step -- policy.sample + policy.log_prob + running_update_ops:
+ *           networks/utils.py:187-194,108-151, networks/actor_critic/a2c.py:346-365, ppo.py:56-62.
+ * Same Philox streams as pfpn_head_sample (uniform: (offset, row), normal: (offset + 1, row)).
+ * Compiled for the shipped DPPO-PFPN shape A = 36, P = 35 (PFPN_ERR_UNSUPPORTED otherwise: use K2 + K1 + K4). */
+typedef struct pfpn_rollout_args {
+  const float* logits;       /* [B, A, P]                                            */
+  const float* loc;          /* [A, P]                                               */
+  const float* logstd;       /* [A, P]                                               */
+  const double* ext_uniform; /* [B, A] fp64 in [0,1), or NULL = Philox                */
+  const float* ext_normal;   /* [B, A, P] (read at [b,a,idx]) or NULL                 */
+  float* action;             /* [B, A]  out                                          */
+  int32_t* idx;              /* [B, A]  out: chosen particle ("dis_action")          */
+  float* lp;                 /* [B]     out: log_prob(action)                        */
+  float* ent;                /* [B]     out: sum_a H[b,a], may be NULL               */
+  float* max_active;         /* [A, P]  in/out, may be NULL (with sum_active)        */
+  float* sum_active;         /* [A, P]  in/out                                       */
+  uint64_t seed, offset;
+  int32_t B, A, P;
+} pfpn_rollout_args;
+int pfpn_rollout_workspace_bytes(int32_t A, int32_t P, size_t* bytes);
+int pfpn_head_rollout(const pfpn_rollout_args* args, void* workspace, size_t workspace_bytes, pfpn_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * K3  reparameterised sampling (SAC, normalize_output=True) forward / backward.
  * Replaces: MixtureGaussianDistribution.sample, rsample branch  networks/utils.py:156-186

@@ -53,6 +53,17 @@ class HeadPush(C.Structure):
                 ("nranks", C.c_int32), ("value", C.c_int32)]
 
 
+class RolloutArgs(C.Structure):
+    """Mirror of ``pfpn_rollout_args``."""
+    _fields_ = [
+        ("logits", _f32p), ("loc", _f32p), ("logstd", _f32p), ("ext_uniform", C.c_void_p), ("ext_normal", _f32p),
+        ("action", _f32p), ("idx", C.c_void_p), ("lp", _f32p), ("ent", _f32p),
+        ("max_active", _f32p), ("sum_active", _f32p),
+        ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("B", C.c_int32), ("A", C.c_int32), ("P", C.c_int32),
+    ]
+
+
 class SacHeadArgs(C.Structure):
     """Mirror of ``pfpn_sac_head_args``."""
     _fields_ = [
@@ -155,6 +166,8 @@ pfpn_head_sample = _sig("pfpn_head_sample", C.c_int, [C.POINTER(SampleArgs), C.c
 pfpn_head_rsample_fwd = _sig("pfpn_head_rsample_fwd", C.c_int, [C.POINTER(RSampleArgs), C.c_void_p])
 pfpn_rsample_bwd_workspace_bytes = _sig("pfpn_rsample_bwd_workspace_bytes", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)])
 pfpn_head_rsample_bwd = _sig("pfpn_head_rsample_bwd", C.c_int, [C.POINTER(RSampleArgs), C.c_void_p, C.c_size_t, C.c_void_p])
+pfpn_rollout_workspace_bytes = _sig("pfpn_rollout_workspace_bytes", C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)])
+pfpn_head_rollout = _sig("pfpn_head_rollout", C.c_int, [C.POINTER(RolloutArgs), C.c_void_p, C.c_size_t, C.c_void_p])
 pfpn_sac_head_workspace_bytes = _sig("pfpn_sac_head_workspace_bytes", C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)])
 pfpn_sac_head_fwd_bwd = _sig("pfpn_sac_head_fwd_bwd", C.c_int, [C.POINTER(SacHeadArgs), C.c_void_p, C.c_size_t, C.c_void_p])
 pfpn_head_finalize_partials = _sig("pfpn_head_finalize_partials", C.c_int,

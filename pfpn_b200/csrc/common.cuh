@@ -110,10 +110,13 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// ---- Philox4x32-10 (counter-based RNG; Salmon et al. 2011) -----------------
-struct Philox {
+// ---- Philox4x32-R (counter-based RNG; Salmon et al. 2011) -----------------
+// R = 10 is the standard variant; R = 7 is the fewest rounds that still passes BigCrush in the paper ("Philox4x32-7") and
+// is what the RNG-bound SAC head kernels (K3 / K3f: ~40 % of their instructions were Philox) use.
+template <int ROUNDS>
+struct PhiloxR {
   uint32_t key[2];
-  __device__ __forceinline__ Philox(uint64_t seed) {
+  __device__ __forceinline__ PhiloxR(uint64_t seed) {
     key[0] = (uint32_t)seed;
     key[1] = (uint32_t)(seed >> 32);
   }
@@ -122,7 +125,7 @@ struct Philox {
              c3 = (uint32_t)(ctr_hi >> 32);
     uint32_t k0 = key[0], k1 = key[1];
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
       const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;  // one IMAD.WIDE each
       const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
       c0 = hi1 ^ c1 ^ k0;
@@ -135,6 +138,8 @@ struct Philox {
     return make_uint4(c0, c1, c2, c3);
   }
 };
+using Philox = PhiloxR<10>;
+using Philox7 = PhiloxR<7>;
 // uniform in (0,1): (x + 0.5) * 2^-32 never returns 0 or 1 in fp32? (rounding may give 1.0f) -> clamp
 __device__ __forceinline__ float u32_to_unit_open(uint32_t x) {
   float u = ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);  // 24-bit, strictly inside (0,1)

@@ -12,7 +12,7 @@
 // Two arithmetic modes:
 //   * verification (ext_uniform / ext_normal supplied): accurate libm functions, so that the argmax
 //     particle is bit-exact against the oracle fed with the same draws;
-//   * production (Philox): two counter streams -- one Philox4x32-10 block gives the Gumbel uniforms
+//   * production (Philox): two counter streams -- one Philox4x32-7 block gives the Gumbel uniforms
 //     of FOUR particles, one more gives their four N(0,1) draws (two Box-Muller pairs).  The forward
 //     only regenerates the winner's normal block; the backward needs tanh(p_k) of every particle and
 //     draws them all.  Transcendental work is on the MUFU pipe (lg2 / ex2 / sin / cos / rsq / rcp).
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(BWD ? 384 : kRsWarps * 32) rsample_kernel(cons
   const long long rows = (long long)ar.B * A;
   const long long nchunks = (rows + chunk_rows - 1) / chunk_rows;
   const int nw = blockDim.x >> 5;
-  const Philox rng(ar.seed);
+  const Philox7 rng(ar.seed);
   // forward: c = chunk of consecutive rows per warp; backward: c = state per CTA, its rows split over the warps by a
   const long long c_begin = BWD ? (long long)blockIdx.x : (long long)blockIdx.x * nw + warp;
   const long long c_step = BWD ? (long long)gridDim.x : (long long)gridDim.x * nw;

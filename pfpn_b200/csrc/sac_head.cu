@@ -55,17 +55,34 @@ __device__ __forceinline__ float sac_fast_tanh(float x) {  // 1 - 2 / (1 + e^{2x
   return 1.f - 2.f * rcpf(1.f + e);
 }
 
+constexpr int kSacRounds = 7;  // Philox4x32-7, as csrc/rsample.cu
 struct SacHeadK {
   pfpn_sac_head_args a;
   float* part;  // [grid][2 * A * P]
   int num_tiles;
+  uint32_t rk[2 * kSacRounds];  // Philox round keys, precomputed on the host: they reach the XORs as constant-bank operands
 };
+// Philox4x32-7 with the key schedule taken from the kernel parameters (identical output to PhiloxR<7>(seed))
+__device__ __forceinline__ uint4 sac_philox(const SacHeadK& kp, uint64_t ctr_lo, uint64_t ctr_hi) {
+  uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+#pragma unroll
+  for (int r = 0; r < kSacRounds; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    c0 = hi1 ^ c1 ^ kp.rk[2 * r];
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ kp.rk[2 * r + 1];
+    c3 = lo0;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
 
 // P = PT particles (32 < PT <= 128, so that every lane's four Philox blocks exist), A = AT action dims, 8 lanes per row.
 template <int PT, int AT, int SLOTS, int NSTAGE, bool FAST>
 __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const SacHeadK kp) {
   constexpr int P = PT, A = AT, AP = A * P, LPR = 8;
   constexpr int NE = 13;                       // particle slots per lane: (u, j<3) -> 3u + j, (u = 0, j = 3) -> 12
+  constexpr int NP = (NE + 1) / 2;             // ... held as register pairs for the packed fp32x2 instructions
   constexpr int NTHR = SLOTS * A * LPR;        // compute threads
   constexpr int TILE_F = SLOTS * AP;           // logits floats per tile
   constexpr int STAGE_BYTES = ((TILE_F + SLOTS * A) * 4 + 127) & ~127;
@@ -80,10 +97,9 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* done_bar = full_bar + NSTAGE;
   float* rowbuf = reinterpret_cast<float*>(tail + 16 * NSTAGE);  // [NSTAGE][SLOTS * A] per-row log p
-  float* mu_s = rowbuf + NSTAGE * SLOTS * A;                     // [AP] each
-  float* sd_s = mu_s + AP;
-  float* isig_s = sd_s + AP;
-  float* cst_s = isig_s + AP;
+  float2* ms_s = reinterpret_cast<float2*>(rowbuf + NSTAGE * SLOTS * A);  // [AP] {mu, sigma}
+  float2* mi_s = ms_s + AP;                                                 // [AP] {-mu, 1 / sigma}
+  float* cst_s = reinterpret_cast<float*>(mi_s + AP);                       // [AP] -(logstd + ln sqrt(2 pi)) log2 e
   float* acc_s = cst_s + AP;  // [SLOTS][2][AP] straight-through terms of the winning particles
 
   if (is_producer && lane == 0) {
@@ -96,9 +112,8 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
   }
   for (int i = tid; i < AP; i += NTHR + 32) {
     const float ls = __ldg(&kp.a.logstd[i]), mu = __ldg(&kp.a.loc[i]);
-    mu_s[i] = mu;
-    sd_s[i] = FAST ? ex2f(ls * kLog2e) : expf(ls);  // (FAST: the same scale the split kernels use -> the same locations)
-    isig_s[i] = expf(-ls);
+    ms_s[i] = make_float2(mu, FAST ? ex2f(ls * kLog2e) : expf(ls));  // (FAST: the scale the split kernels use -> the same locations)
+    mi_s[i] = make_float2(-mu, expf(-ls));
     cst_s[i] = -(ls + kHalfLog2Pi) * kLog2e;
   }
   for (int i = tid; i < SLOTS * 2 * AP; i += NTHR + 32) acc_s[i] = 0.f;
@@ -161,15 +176,13 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
     const int a = rem >> 3, c = rem & 7;
     const int kb0 = 16 * (c >> 2) + (c & 3);
     const bool tail_ok = c < P - 96;  // slot (u = 0, j = 3): particle 96 + kb0
-    const float* mu_r = mu_s + a * P;
-    const float* sd_r = sd_s + a * P;
-    const float* isig_r = isig_s + a * P;
+    const float2* ms_r = ms_s + a * P;
+    const float2* mi_r = mi_s + a * P;
     const float* cst_r = cst_s + a * P;
     float* acc_r = acc_s + (size_t)slot * 2 * AP + a * P;
-    const Philox rng(kp.a.seed);
-    float acc1[NE], acc2[NE];
+    float2 acc1[NP], acc2[NP];
 #pragma unroll
-    for (int e = 0; e < NE; ++e) acc1[e] = acc2[e] = 0.f;
+    for (int i = 0; i < NP; ++i) acc1[i] = acc2[i] = make_float2(0.f, 0.f);
 
     for (int it = 0; it < my_tiles; ++it) {
       const int st = it % NSTAGE;
@@ -191,24 +204,32 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
       float* lg = sbuf + (row_ok ? slot : 0) * AP + a * P;
 
       // ---- step 1: draws, noisy logits (log2 domain), locations -----------------------------------------------
-      float y[NE], nl[NE], p[NE], e2[NE];
+      // Slots are kept as register PAIRS (slot e -> pair e / 2, half e % 2) so that steps 3 / 4 run on packed fp32x2
+      // instructions; the 14th half-slot is a permanently masked dummy.
+      float2 y2[NP], nl2[NP], p2[NP], e22[NP];
+      y2[NP - 1].y = -3.402823466e38f;
+      nl2[NP - 1].y = 0.f;
+      p2[NP - 1].y = 0.f;
       float ymax = -3.402823466e38f, yfm = 0.f, pmax = 0.f;
       int kmax = 0;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int kb = 4 * u + kb0;
+        const int nj = u == 0 ? 4 : 3;  // particles >= 100: only slot (0, 3) exists
         float n4[4], nl4[4], ya4[4];
         if (FAST) {
-          const uint4 q = rng(kp.a.offset, (uint64_t)(r * P + kb));
-          sac_normal4(rng(kp.a.offset, kSacNormalStream | (uint64_t)(r * P + kb)), n4);
+          const uint4 q = sac_philox(kp, kp.a.offset, (uint64_t)(r * P + kb));
+          sac_normal4(sac_philox(kp, kp.a.offset, kSacNormalStream | (uint64_t)(r * P + kb)), n4);
           const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) nl4[j] = fmaxf(-lg2f(sac_bits_to_unit(w4[j])), 4e-8f);  // -log2 u, kept off 0
+          for (int j = 0; j < 4; ++j)
+            if (j < nj) nl4[j] = fmaxf(-lg2f(sac_bits_to_unit(w4[j])), 4e-8f);  // -log2 u, kept off 0
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
+            if (j >= nj) continue;
             const int k = kb + 32 * j;
-            const bool ok = j < 3 || (u == 0 && tail_ok);
+            const bool ok = j < 3 || tail_ok;
             const float U = ok ? __ldg(&kp.a.ext_uniform[r * P + k]) : 0.5f;
             n4[j] = ok ? __ldg(&kp.a.ext_normal[r * P + k]) : 0.f;
             nl4[j] = fmaxf(-log2f(U), 4e-8f);
@@ -217,18 +238,24 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (j == 3 && u > 0) continue;  // particles >= 100: only slot (0, 3) exists
+          if (j >= nj) continue;
           const int e = j < 3 ? 3 * u + j : 12;
           const int k = kb + 32 * j;
           const bool ok = j < 3 || tail_ok;
           const float x = ok ? lg[k] : 0.f;
+          const float2 ms = ms_r[ok ? k : 0];  // {mu, sigma}
           const float yf = ok ? fmaf(x, kLog2e, -(FAST ? lg2f(nl4[j]) : log2f(nl4[j]))) : -3.402823466e38f;
           const float ycmp = FAST ? yf : (ok ? x + ya4[j] : -3.402823466e38f);  // (G + logits) / T, T = 1
-          const float pk = FAST ? fmaf(n4[j], sd_r[ok ? k : 0], mu_r[ok ? k : 0])
-                                : __fadd_rn(__fmul_rn(n4[j], sd_r[ok ? k : 0]), mu_r[ok ? k : 0]);
-          nl[e] = nl4[j];
-          y[e] = yf;
-          p[e] = pk;
+          const float pk = FAST ? fmaf(n4[j], ms.y, ms.x) : __fadd_rn(__fmul_rn(n4[j], ms.y), ms.x);
+          if (e & 1) {
+            nl2[e >> 1].y = nl4[j];
+            y2[e >> 1].y = yf;
+            p2[e >> 1].y = pk;
+          } else {
+            nl2[e >> 1].x = nl4[j];
+            y2[e >> 1].x = yf;
+            p2[e >> 1].x = pk;
+          }
           const bool take = FAST ? (ycmp > ymax) : (ycmp > ymax || (ycmp == ymax && k < kmax));  // ties -> smallest index (tf.argmax)
           if (take) {
             ymax = ycmp;
@@ -259,29 +286,41 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
       const float omt2 = 4.f * e2m * q1 * q1;
       const float t = copysignf(1.f - 2.f * e2m * q1, uu);
 
-      // ---- step 3: particle terms and the five row sums ----------------------------------------------------------
-      float S1 = 0.f, S2 = 0.f, T = 0.f, Sw = 0.f, Swt = 0.f;
-#pragma unroll
-      for (int e = 0; e < NE; ++e) {
+      // ---- step 3: particle terms and the five row sums (packed fp32x2) ------------------------------------------
+      // slot e of this lane <-> particle k = 4 u + kb0 + 32 j, (u, j) = (e / 3, e % 3) for e < 12, (0, 3) for e = 12
+      auto slot_k = [&](int e) -> int {
         const int u = e < 12 ? e / 3 : 0, j = e < 12 ? e % 3 : 3;
         const int k = 4 * u + kb0 + 32 * j;
-        const bool ok = e < 12 || tail_ok;
-        const int kk = ok ? k : 0;
-        const float w = ex2f(y[e] - yfm);       // softmax(logits + G) numerator; 0 for the masked slot
-        const float e1 = w * nl[e];             // = 2^(log2e * logit - yfm): softmax(logits) numerator, no second ex2
-        const float th = sac_fast_tanh(p[e]);
-        const float z = (uu - mu_r[kk]) * isig_r[kk];
-        const float n = ex2f(fmaf(z * z, -0.5f * kLog2e, cst_r[kk]));
-        const float x2 = e1 * n;
-        y[e] = w;
-        p[e] = th;
-        e2[e] = x2;
-        S1 += e1;
-        S2 += x2;
-        T = fmaf(x2 * z, isig_r[kk], T);
-        Sw += w;
-        Swt = fmaf(w, th, Swt);
+        return (e < 12 || (e == 12 && tail_ok)) ? k : 0;  // masked half-slots read entry 0 (their terms are exactly 0)
+      };
+      const float2 uu2 = splat2(uu), nyf2 = splat2(-yfm), one2 = splat2(1.f), mtwo2 = splat2(-2.f);
+      const float2 tl2 = splat2(2.f * kLog2e), nhl2 = splat2(-0.5f * kLog2e);
+      float2 S1v = splat2(0.f), S2v = S1v, Tv = S1v, Swv = S1v, Swtv = S1v;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const int k0 = slot_k(2 * i), k1 = slot_k(2 * i + 1);
+        const float2 m0 = mi_r[k0], m1 = mi_r[k1];  // {-mu, 1 / sigma}
+        const float2 nmu = make_float2(m0.x, m1.x), is2 = make_float2(m0.y, m1.y);
+        const float2 cs2 = make_float2(cst_r[k0], cst_r[k1]);
+        const float2 dy = add2(y2[i], nyf2);
+        const float2 w = make_float2(ex2f(dy.x), ex2f(dy.y));  // softmax(logits + G) numerator; 0 for a masked slot
+        const float2 e1 = mul2(w, nl2[i]);                     // = 2^(log2e logit - yfm): softmax(logits) numerator, no 2nd ex2
+        const float2 a2 = mul2(p2[i], tl2);
+        const float2 den = add2(make_float2(ex2f(a2.x), ex2f(a2.y)), one2);
+        const float2 th = fma2(make_float2(rcpf(den.x), rcpf(den.y)), mtwo2, one2);  // tanh p = 1 - 2 / (1 + e^{2p})
+        const float2 z = mul2(add2(uu2, nmu), is2);
+        const float2 t2 = fma2(mul2(z, z), nhl2, cs2);
+        const float2 x2 = mul2(e1, make_float2(ex2f(t2.x), ex2f(t2.y)));
+        y2[i] = w;
+        p2[i] = th;
+        e22[i] = x2;
+        S1v = add2(S1v, e1);
+        S2v = add2(S2v, x2);
+        Tv = fma2(mul2(x2, z), is2, Tv);
+        Swv = add2(Swv, w);
+        Swtv = fma2(w, th, Swtv);
       }
+      float S1 = S1v.x + S1v.y, S2 = S2v.x + S2v.y, T = Tv.x + Tv.y, Sw = Swv.x + Swv.y, Swt = Swtv.x + Swtv.y;
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) {
         S1 += __shfl_xor_sync(0xffffffffu, S1, o);
@@ -290,7 +329,7 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
         Sw += __shfl_xor_sync(0xffffffffu, Sw, o);
         Swt += __shfl_xor_sync(0xffffffffu, Swt, o);
       }
-      // ---- step 4: row scalars ---------------------------------------------------------------------------------------
+      // ---- step 4: row scalars, gradients ---------------------------------------------------------------------------
       const float is1 = rcpf(S1);
       // ln(1 - tanh^2 u) = ln 4 - 2|u| - 2 ln(1 + e^{-2|u|})   (utils.py:132-133 in a cancellation-free form)
       const float corr = 2.f * kLn2 - 2.f * fabsf(uu) - 2.f * kLn2 * lg2f(1.f + e2m);
@@ -304,27 +343,30 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
       const float coef = fmaf(gu, rcpf(fmaxf(1e-6f, omt2)), ga);  // mask + mask2 (utils.py:164-183)
       const float iw = rcpf(Sw);
       const float wd = coef * fmaf(Swt, iw, -t);                // sum_j w_j D_j,  D_j = (tanh p_j - t) coef
-      const float c1 = g_row * is1;
+      const float2 gs2v = splat2(gs2), iwv = splat2(iw), coefv = splat2(coef), nt2 = splat2(-t), nwd2 = splat2(-wd);
+      const float2 nc1 = splat2(-g_row * is1), neg1 = splat2(-1.f);
       float* stp = row_ok ? lg : nullptr;
 #pragma unroll
-      for (int e = 0; e < NE; ++e) {
-        const int u = e < 12 ? e / 3 : 0, j = e < 12 ? e % 3 : 3;
-        const int k = 4 * u + kb0 + 32 * j;
-        const bool ok = e < 12 || tail_ok;
-        const int kk = ok ? k : 0;
-        const float w = y[e];
-        const float rr = e2[e] * gs2;                            // g r_k
-        const float z = (uu - mu_r[kk]) * isig_r[kk];
-        const float d = fmaf(w * iw, fmaf(coef, p[e] - t, -wd), fmaf(-(w * nl[e]), c1, rr));
-        acc1[e] = fmaf(rr, z, acc1[e]);
-        acc2[e] = fmaf(rr, fmaf(z, z, -1.f), acc2[e]);
-        if (ok && stp != nullptr) stp[k] = d;
+      for (int i = 0; i < NP; ++i) {
+        const int k0 = slot_k(2 * i), k1 = slot_k(2 * i + 1);
+        const float2 m0 = mi_r[k0], m1 = mi_r[k1];
+        const float2 z = mul2(add2(uu2, make_float2(m0.x, m1.x)), make_float2(m0.y, m1.y));
+        const float2 w = y2[i];
+        const float2 rr = mul2(e22[i], gs2v);                                           // g r_k
+        const float2 X = fma2(coefv, add2(p2[i], nt2), nwd2);                          // D_k - sum_j w_j D_j
+        const float2 d = fma2(mul2(w, iwv), X, fma2(mul2(w, nl2[i]), nc1, rr));        // g (r - pi) + w (D - sum w D)
+        acc1[i] = fma2(rr, z, acc1[i]);
+        acc2[i] = fma2(rr, fma2(z, z, neg1), acc2[i]);
+        if (stp != nullptr) {
+          if (2 * i < 12 || tail_ok) stp[k0] = d.x;  // (slot 12 exists on lanes c < 4 only)
+          if (2 * i + 1 < 12) stp[k1] = d.y;
+        }
       }
       if (c == 0 && row_ok) {
         // the winner's straight-through terms: dL/dp_{k*} = (1 - t^2) g_a + g_u; this row's lanes are the only writers of
         // acc_r (slot, a) -- plain read-modify-write.  Stored times sigma: the finalize kernel divides dloc by sigma.
-        const float gp = fmaf(omt2, ga, gu) * sd_r[arg];
-        const float zs = (uu - mu_r[arg]) * isig_r[arg];          // = eps of the winner
+        const float gp = fmaf(omt2, ga, gu) * ms_r[arg].y;
+        const float zs = (uu + mi_r[arg].x) * mi_r[arg].y;        // = eps of the winner
         acc_r[arg] += gp;
         acc_r[AP + arg] += gp * zs;
         const size_t o = (size_t)b * A + a;
@@ -348,8 +390,8 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
       const int u = e < 12 ? e / 3 : 0, j = e < 12 ? e % 3 : 3;
       const int k = 4 * u + kb0 + 32 * j;
       if (e < 12 || tail_ok) {
-        acc_r[k] += acc1[e];
-        acc_r[AP + k] += acc2[e];
+        acc_r[k] += (e & 1) ? acc1[e >> 1].y : acc1[e >> 1].x;
+        acc_r[AP + k] += (e & 1) ? acc2[e >> 1].y : acc2[e >> 1].x;
       }
     }
   }
@@ -377,7 +419,7 @@ template <bool FAST>
 int sac_launch(const SacHeadK& kp, int grid, cudaStream_t st) {
   constexpr int P = 100, A = 36, AP = A * P;
   constexpr int stage_bytes = ((kSacSlots * AP + kSacSlots * A) * 4 + 127) & ~127;
-  constexpr int smem = kSacStages * stage_bytes + 16 * kSacStages + kSacStages * kSacSlots * A * 4 + 4 * AP * 4 +
+  constexpr int smem = kSacStages * stage_bytes + 16 * kSacStages + kSacStages * kSacSlots * A * 4 + 5 * AP * 4 +
                        kSacSlots * 2 * AP * 4 + 128;
   auto fn = sac_head_kernel<P, A, kSacSlots, kSacStages, FAST>;
   PFPN_CUDA_OK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -416,6 +458,15 @@ extern "C" int pfpn_sac_head_fwd_bwd(const pfpn_sac_head_args* args, void* works
   kp.a = a;
   kp.part = reinterpret_cast<float*>(workspace);
   kp.num_tiles = (a.B + kSacSlots - 1) / kSacSlots;
+  {
+    uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    for (int r = 0; r < kSacRounds; ++r) {
+      kp.rk[2 * r] = k0;
+      kp.rk[2 * r + 1] = k1;
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+  }
   int grid = sms;  // one 19-warp CTA per SM
   if (grid > kp.num_tiles) grid = kp.num_tiles;
   if (grid > kSacMaxCtas) grid = kSacMaxCtas;

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -307,6 +308,16 @@ class ParticleFilteringClipPPONetwork:
         statistics like the reference's running_update_ops do on every rollout step."""
         s = self._dev_state(state)
         logits, _, value, _ = self._forward(s)
+        want_stats = self.trainable and self.resample
+        if self.random_action and not self.normalize_policy_output_ and self.A == 36 and self.P == 35 and \
+                os.environ.get("PFPN_ROLLOUT_FUSED", "1") != "0":
+            # K2f: sample + log_prob + activity statistics in ONE pass over the logits (the shipped DPPO-PFPN shape)
+            out = _sampling.rollout_fused(logits, self.loc, self.logstd, seed=self.sample_seed, offset=self._rng_offset,
+                                          ext_uniform=ext_uniform, ext_normal=ext_normal,
+                                          max_active=self.max_active if want_stats else None,
+                                          sum_active=self.sum_active if want_stats else None)
+            self._rng_offset += 2
+            return out["action"], out["lp"], value.clone()
         if self.random_action:
             if self.normalize_policy_output_:
                 smp, s_pre, _ = _sampling.rsample_fwd(logits, self.loc, self.logstd, seed=self.sample_seed, offset=self._rng_offset,
@@ -321,7 +332,7 @@ class ParticleFilteringClipPPONetwork:
             action, _ = _sampling.mean_action(logits, self.loc, tanh=self.normalize_policy_output_)
             val = torch.atanh(action) if self.normalize_policy_output_ else action
         out = _head.head_call(_cabi.HEAD_FWD, logits, self.loc, self.logstd, val, tanh=self.normalize_policy_output_)
-        if self.trainable and self.resample:
+        if want_stats:
             _sampling.stats_update(logits, self.max_active, self.sum_active)
         return action, out["lp"], value.clone()
 

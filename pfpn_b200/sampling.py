@@ -97,6 +97,54 @@ def rsample_bwd(logits, loc, logstd, g_sample, g_s_pre, *, seed=0, offset=0, ext
     return dlogits, dloc, dlogstd
 
 
+def rollout_fused(logits, loc, logstd, *, seed=0, offset=0, ext_uniform=None, ext_normal=None, max_active=None,
+                  sum_active=None, want_ent=False):
+    """K2f: sample + log_prob + entropy + activity statistics in one pass over the logits (utils.py:187-194,108-151,
+    a2c.py:346-365).  Returns dict(action, idx, lp[, ent]); max_active / sum_active are updated in place when given.
+    A = 36, P = 35 only (PfpnError -3 otherwise: the caller falls back to the three-kernel form)."""
+    logits, loc, logstd = _f32c(logits, "logits"), _f32c(loc, "loc"), _f32c(logstd, "logstd")
+    B, A, P = logits.shape
+    dev = logits.device
+    a = _cabi.RolloutArgs()
+    a.logits, a.loc, a.logstd = logits.data_ptr(), loc.data_ptr(), logstd.data_ptr()
+    keep = [logits, loc, logstd]
+    if ext_uniform is not None:
+        if ext_uniform.dtype != torch.float64 or ext_uniform.shape != (B, A):
+            raise ValueError("ext_uniform must be float64 [B, A]")
+        ext_uniform = ext_uniform.contiguous()
+        keep.append(ext_uniform)
+        a.ext_uniform = ext_uniform.data_ptr()
+    if ext_normal is not None:
+        ext_normal = _f32c(ext_normal, "ext_normal")
+        keep.append(ext_normal)
+        a.ext_normal = ext_normal.data_ptr()
+    out = dict(action=torch.empty(B, A, dtype=torch.float32, device=dev), idx=_i32(B, A, device=dev),
+               lp=torch.empty(B, dtype=torch.float32, device=dev))
+    a.action, a.idx, a.lp = out["action"].data_ptr(), out["idx"].data_ptr(), out["lp"].data_ptr()
+    if want_ent:
+        out["ent"] = torch.empty(B, dtype=torch.float32, device=dev)
+        a.ent = out["ent"].data_ptr()
+    if (max_active is None) != (sum_active is None):
+        raise ValueError("pass both max_active and sum_active or neither")
+    ws_ptr, ws_n = None, 0
+    if max_active is not None:
+        for t, n in ((max_active, "max_active"), (sum_active, "sum_active")):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape == (A, P)):
+                raise ValueError(f"{n}: expected contiguous float32 CUDA [A, P]")
+        a.max_active, a.sum_active = max_active.data_ptr(), sum_active.data_ptr()
+        n = C.c_size_t(0)
+        _cabi.check(_cabi.pfpn_rollout_workspace_bytes(A, P, C.byref(n)))
+        key = (dev, "ro", n.value)
+        ws = _stats_ws.get(key)
+        if ws is None:
+            ws = _stats_ws[key] = torch.empty(n.value, dtype=torch.uint8, device=dev)
+        ws_ptr, ws_n = ws.data_ptr(), ws.numel()
+    a.seed, a.offset, a.B, a.A, a.P = seed, offset, B, A, P
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.pfpn_head_rollout(C.byref(a), ws_ptr, ws_n, _stream_ptr()))
+    return out
+
+
 def sac_head_fused(logits, loc, logstd, g_sample, g_lp, *, seed=0, offset=0, ext_uniform=None, ext_normal=None,
                    out: Optional[dict] = None, dlogits_out=None):
     """K3f: rsample forward + tanh log_prob forward + the backward of both in one pass (utils.py:108-144,156-186).

@@ -153,7 +153,9 @@ def test_rsample_philox_mode_distribution_and_fwd_bwd_consistency(cuda_dev, P):
     ds_ref = torch.zeros(A, P, dtype=torch.float64).index_put_(
         (a_ix.reshape(-1), idx_l.reshape(-1)), (gp * (s64 - loc.double()[a_ix, idx_l])).reshape(-1), accumulate=True)
     assert rel(dc, dc_ref) < 1e-4 and rel(ds, ds_ref) < 1e-4
-    assert float(dl.sum(-1).abs().max()) < 1e-4  # softmax Jacobian rows sum to zero
+    # softmax Jacobian rows sum to zero -- up to fp32 rounding of the row's own terms (the straight-through coefficient
+    # g_u / max(1e-6, 1 - t^2) can be huge for a saturated tanh, so the bound is relative to the row's magnitude)
+    assert bool((dl.sum(-1).abs() <= 4e-6 * dl.abs().sum(-1) + 1e-6).all())
     assert torch.isfinite(dl).all()
 
 
@@ -357,3 +359,80 @@ def test_fused_sac_head_equals_the_three_launch_form_in_production_mode(cuda_dev
         assert torch.equal(f1[k], f2[k]), k  # no atomics, fixed summation order
     f3 = sampling.sac_head_fused(logits, loc, logstd, g_sample, g_lp, seed=11, offset=8)
     assert not torch.equal(f3["idx"], idx)  # another call counter -> other draws
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K2f: the rollout side in one pass (pfpn_head_rollout) -- sample + log_prob + entropy + activity statistics
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B", [2050, 7])
+def test_fused_rollout_matches_oracle_with_external_draws(cuda_dev, B):
+    A, P = 36, 35
+    d = synth.head_inputs(B, A, P, seed=34114 + B, far_frac=0.0)
+    g = torch.Generator().manual_seed(B)
+    u = torch.rand(B, A, dtype=torch.float64, generator=g)
+    eps = torch.randn(B, A, P, generator=g)
+    d["logits"][0, 0, :3] = float("-inf")  # non-finite logits carry no mass in TF's Multinomial kernel
+    dist = oh.MixtureGaussianOracle(d["logits"].double(), d["loc"].double(), d["logstd"].double().exp(), False)
+    act_ref = dist.sample(1, uniform=u, normal=eps.double())[0]
+    cu = lambda t: t.to(cuda_dev)
+    max0, sum0 = torch.rand(A, P, generator=g) * 0.05, torch.rand(A, P, generator=g)
+    mx, sm = cu(max0), cu(sum0)
+    out = sampling.rollout_fused(cu(d["logits"]), cu(d["loc"]), cu(d["logstd"]), ext_uniform=cu(u), ext_normal=cu(eps),
+                                 max_active=mx, sum_active=sm, want_ent=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out["idx"].cpu().long(), dist.dis_action)          # bit-exact particle selection
+    assert rel(out["action"], act_ref) < 1e-6
+    # log_prob / entropy / statistics on finite rows (row (0,0) holds -inf logits: softmax of it is the same in both)
+    lp_ref = dist.log_prob(act_ref)
+    assert rel(out["lp"], lp_ref) < TOL
+    lg = d["logits"].double().clone()
+    probs = torch.softmax(lg, -1)
+    ent_ref = -(torch.where(probs > 0, probs * probs.clamp_min(1e-300).log(), torch.zeros_like(probs))).sum(-1).sum(-1)
+    assert rel(out["ent"], ent_ref) < TOL
+    assert rel(mx, torch.maximum(max0.double(), probs.amax(0))) < TOL
+    assert rel(sm, sum0.double() + probs.sum(0)) < TOL
+
+
+def test_fused_rollout_uniforms_on_cdf_boundaries_take_the_exact_fp64_path(cuda_dev):
+    """Same adversarial uniforms as the K2 test: 1e-9 .. 1e-6 of the total away from an fp64 CDF interval end."""
+    import numpy as np
+    B, A, P = 170, 36, 35
+    rows = B * A
+    rng = np.random.RandomState(7)
+    logits = (rng.randn(rows, P) * 2).astype(np.float32)
+    logits[5, :4] = -np.inf
+    logits[6, 10] = -120.0  # underflows in fp32, not in fp64
+    mxv = logits.max(1, keepdims=True).astype(np.float64)
+    e = np.where(np.isfinite(logits), np.exp(logits.astype(np.float64) - mxv), 0.0)
+    cdf = np.cumsum(e, 1)
+    k = rng.randint(0, P - 1, size=rows)
+    off = 10.0 ** rng.uniform(-9, -6, size=rows) * rng.choice([-1.0, 1.0], size=rows)
+    u = np.clip(cdf[np.arange(rows), k] / cdf[:, -1] + off, 0.0, np.nextafter(1.0, 0.0))
+    ref = oh.tf_multinomial_cpu(logits, u[:, None])[:, 0]
+    lg = torch.tensor(logits, device=cuda_dev).view(B, A, P)
+    loc = torch.zeros(A, P, device=cuda_dev)
+    ls = torch.zeros(A, P, device=cuda_dev)
+    out = sampling.rollout_fused(lg, loc, ls, ext_uniform=torch.tensor(u, device=cuda_dev).view(B, A),
+                                 ext_normal=torch.zeros(B, A, P, device=cuda_dev))
+    assert np.array_equal(out["idx"].cpu().numpy().reshape(-1), ref)
+
+
+def test_fused_rollout_equals_the_three_kernel_form_in_production_mode(cuda_dev):
+    """Philox mode at a size the oracle does not reach: same streams as K2, so index and action are bit-identical to
+    pfpn_head_sample, log_prob / entropy to K1's forward, the statistics to K4 -- from ONE pass over the logits."""
+    from pfpn_b200 import _cabi, head
+    B, A, P = 16387, 36, 35
+    d = {k: (v.to(cuda_dev) if torch.is_tensor(v) else v) for k, v in synth.head_inputs(B, A, P, seed=3).items()}
+    act, idx = sampling.sample_plain(d["logits"], d["loc"], d["logstd"], seed=77, offset=4)
+    ref = head.head_call(_cabi.HEAD_FWD, d["logits"], d["loc"], d["logstd"], act)
+    mx0, sm0 = torch.zeros(A, P, device=cuda_dev), torch.zeros(A, P, device=cuda_dev)
+    sampling.stats_update(d["logits"], mx0, sm0)
+    mx1, sm1 = torch.zeros(A, P, device=cuda_dev), torch.zeros(A, P, device=cuda_dev)
+    out = sampling.rollout_fused(d["logits"], d["loc"], d["logstd"], seed=77, offset=4, max_active=mx1, sum_active=sm1,
+                                 want_ent=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out["idx"], idx) and torch.equal(out["action"], act)
+    assert rel(out["lp"], ref["lp"]) < TOL and rel(out["ent"], ref["ent"]) < TOL
+    assert rel(mx1, mx0) < 1e-6 and rel(sm1, sm0) < 1e-5
+    out2 = sampling.rollout_fused(d["logits"], d["loc"], d["logstd"], seed=77, offset=4, want_ent=True)
+    assert torch.equal(out2["lp"], out["lp"]) and torch.equal(out2["idx"], out["idx"])  # reproducible; statistics optional
