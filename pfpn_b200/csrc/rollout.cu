@@ -44,26 +44,39 @@ __device__ __forceinline__ float ro_exp_term(float d) {  // e^d for d <= 0, rela
   return ex2f(f) * scale;
 }
 
-// the literal fp64 algorithm for one row (fallback; also the semantic definition), logits in shared memory
-__device__ __noinline__ int ro_multinomial_fp64(const float* x, int P, double u) {
+// The literal fp64 algorithm for one row (fallback; also the semantic definition), executed by a whole WARP for one row
+// at a time in warp-uniform control flow: every lane evaluates exp(double(logit) - max) for its particles (the expensive
+// part), the values go through a shared-memory scratch row, and ONE lane replays TF's sequential fp64 running total and
+// upper_bound on them -- so the additions happen in exactly the reference's order.  (A per-lane subroutine call inside
+// divergent code ahead of the warp shuffles below deadlocked on sm_100a; this form has no divergent collective at all.)
+__device__ __forceinline__ int ro_multinomial_fp64_warp(const float* x, int P, double u, double* scratch, int lane) {
   float m = -3.402823466e38f;
-  for (int k = 0; k < P; ++k) {
+  for (int k = lane; k < P; k += 32) {
     const float v = x[k];
     if (isfinite(v)) m = fmaxf(m, v);
   }
-  double total = 0.0;
-  for (int k = 0; k < P; ++k) {
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  for (int k = lane; k < P; k += 32) {
     const float v = x[k];
-    if (isfinite(v)) total += exp((double)v - (double)m);
+    scratch[k] = isfinite(v) ? exp((double)v - (double)m) : 0.0;
   }
-  const double to_find = u * total;
-  double run = 0.0;
-  for (int k = 0; k < P; ++k) {
-    const float v = x[k];
-    if (isfinite(v)) run += exp((double)v - (double)m);
-    if (to_find < run) return k;
+  __syncwarp();
+  int res = P - 1;  // (u * total == total through rounding: TF would return the undefined class P; clamp as the oracle does)
+  if (lane == 0) {
+    double total = 0.0;
+    for (int k = 0; k < P; ++k) total += scratch[k];
+    const double to_find = u * total;
+    double run = 0.0;
+    for (int k = 0; k < P; ++k) {  // first k with cdf[k] > to_find == std::upper_bound on the running totals
+      run += scratch[k];
+      if (to_find < run) {
+        res = k;
+        break;
+      }
+    }
   }
-  return P - 1;  // (u * total == total through rounding: TF would return the undefined class P; clamp as the oracle does)
+  __syncwarp();
+  return __shfl_sync(0xffffffffu, res, 0);
 }
 
 template <int SLOTS, int NSTAGE>
@@ -82,6 +95,7 @@ __global__ void __launch_bounds__(SLOTS * 72 + 32, 2) rollout_kernel(const Rollo
   uint64_t* done_bar = full_bar + NSTAGE;
   float2* rowbuf = reinterpret_cast<float2*>(tail + 16 * NSTAGE);  // [NSTAGE][SLOTS * A] per-row (log p, H)
   float* cs = reinterpret_cast<float*>(rowbuf + NSTAGE * SLOTS * A);  // [EPL * 3][A * LPR] per-thread-column constants
+  double* fb_s = reinterpret_cast<double*>(cs + EPL * 3 * A * LPR);  // [compute warps][40] fp64 fallback scratch
   float* red = reinterpret_cast<float*>(smem_raw);  // [SLOTS][2][AP] end-of-kernel combine, aliases the (then idle) stages
   static_assert(SLOTS * 2 * AP * 4 <= NSTAGE * STAGE_BYTES, "the combine tables reuse the stage ring");
 
@@ -243,25 +257,36 @@ __global__ void __launch_bounds__(SLOTS * 72 + 32, 2) rollout_kernel(const Rollo
         }
       }
       cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
-      near = near || __shfl_xor_sync(0xffffffffu, (int)near, 1) != 0;
+      {  // (no short-circuit around the shuffle: every lane must execute it)
+        const int near_o = __shfl_xor_sync(0xffffffffu, (int)near, 1);
+        near = near || near_o != 0;
+      }
       int idx = cnt;
       const bool fallback = near || idx >= P || !(total > 0.f) || !isfinite(total);
-      int k64 = 0;
-      if (fallback && c == 0) k64 = ro_multinomial_fp64(lg, P, u);
-      k64 = __shfl_sync(0xffffffffu, k64, lane & ~1);  // (outside the divergent region: every lane participates)
-      if (fallback) idx = k64;
+      // rows that need the literal fp64 algorithm (~0.1 %): one at a time, by the whole warp, in warp-uniform control flow
+      unsigned fb_mask = __ballot_sync(0xffffffffu, fallback && c == 0);
+      while (fb_mask != 0u) {
+        const int src = __ffs(fb_mask) - 1;
+        fb_mask &= fb_mask - 1;
+        const int off = __shfl_sync(0xffffffffu, (int)(lg - sbuf), src);
+        const unsigned ulo = __shfl_sync(0xffffffffu, (unsigned)__double2loint(u), src);
+        const unsigned uhi = __shfl_sync(0xffffffffu, (unsigned)__double2hiint(u), src);
+        const int k64 = ro_multinomial_fp64_warp(sbuf + off, P, __hiloint2double((int)uhi, (int)ulo), fb_s + warp * 40, lane);
+        if ((lane & ~1) == src) idx = k64;  // both lanes of that row
+      }
+      __syncwarp();
       // ---- the action: Normal(loc, scale).sample()[idx] = eps * scale + loc (utils.py:190-194) -------------------
       float eps;
       if (kp.a.ext_normal != nullptr) {
         eps = __ldg(&kp.a.ext_normal[r * P + idx]);
       } else {
         const uint4 q = rng(kp.a.offset + 1, (uint64_t)r);
-        eps = sqrtf(-2.f * logf(u32_to_unit_open(q.x))) * cospif(2.f * u32_to_unit_open(q.y));
+        eps = __fsqrt_rn(-2.f * logf(u32_to_unit_open(q.x))) * cospif(2.f * u32_to_unit_open(q.y));  // (= K2's sqrtf)
       }
       const float mu_s = __ldg(&kp.a.loc[a * P + idx]), sd_s = expf(__ldg(&kp.a.logstd[a * P + idx]));
       const float v = __fadd_rn(__fmul_rn(eps, sd_s), mu_s);
       // ---- log_prob of the action (utils.py:108-134, plain variant), entropy (:146-151), statistics (a2c.py:346-365) ---
-      const float is1 = 1.f / total;
+      const float is1 = rcpf(total);
       float S2 = 0.f;
 #pragma unroll
       for (int i = 0; i < EPL; ++i) {
@@ -272,6 +297,7 @@ __global__ void __launch_bounds__(SLOTS * 72 + 32, 2) rollout_kernel(const Rollo
         vmax[i] = row_ok ? fmaxf(vmax[i], pr) : vmax[i];
         vsum[i] += row_ok ? pr : 0.f;
       }
+      __syncwarp();
       S2 += __shfl_xor_sync(0xffffffffu, S2, 1);
       const float lnp = kLn2 * (lg2f(S2) - lg2f(total));  // -inf when every term underflowed (p == 0)
       const float Hval = logf(total) - Hs * is1;            // sum_k p_k (ln s1 - (l_k - m))
@@ -361,7 +387,7 @@ extern "C" int pfpn_head_rollout(const pfpn_rollout_args* args, void* workspace,
   if (stats && (!workspace || workspace_bytes < need)) return PFPN_ERR_WORKSPACE;
   constexpr int SLOTS = 4, NSTAGE = 4, AP = 36 * 35;
   constexpr int stage_bytes = (SLOTS * AP * 4 + 127) & ~127;
-  constexpr int smem = NSTAGE * stage_bytes + 16 * NSTAGE + NSTAGE * SLOTS * 36 * 8 + 18 * 3 * 72 * 4 + 128;
+  constexpr int smem = NSTAGE * stage_bytes + 16 * NSTAGE + NSTAGE * SLOTS * 36 * 8 + 18 * 3 * 72 * 4 + 9 * 40 * 8 + 128;
   int dev = 0, sms = 0;
   PFPN_CUDA_OK(cudaGetDevice(&dev));
   PFPN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

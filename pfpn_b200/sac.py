@@ -234,7 +234,11 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
         logits, a_acts = self._actor_forward(x, "0")
         off = self._rng_offset
         self._rng_offset += 4
-        smp, logp, leaves = self._policy(logits, B, True, off, None if draws is None else (draws[0], draws[1]))
+        # K3f (A = 36, P = 100): the head's backward -- rsample backward + tanh log_prob forward/backward -- is ONE pass that
+        # regenerates the forward's draws; the forward sample below then needs no autograd graph
+        import os
+        fused = (self.A, self.P) == (36, 100) and os.environ.get("PFPN_SAC_FUSED", "1") != "0"
+        smp, logp, leaves = self._policy(logits, B, not fused, off, None if draws is None else (draws[0], draws[1]))
         logits2, _ = self._actor_forward(x2, "1")
         with torch.no_grad():
             a2, logp2, _ = self._policy(logits2, B, False, off + 2, None if draws is None else (draws[2], draws[3]))
@@ -260,11 +264,20 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
             dxin = self._input_grad(self.q[i], q_a[i][1], dq_a[i], f"a{i}")
             part = dxin[:, self.S:self.S + self.A]
             da = part.clone() if da is None else da + part
-        lg, loc_l, ls_l = leaves
-        torch.autograd.backward([logp, smp], [dlogp, da])
-        self._backward_stack(self.actor + [self.fc_policy], a_acts, lg.grad.reshape(B, self.A * self.P).contiguous())
-        self.dloc.copy_(loc_l.grad)
-        self.dlogstd.copy_(ls_l.grad)
+        if fused:
+            from . import sampling as _sampling
+            ext = {} if draws is None else dict(ext_uniform=draws[0], ext_normal=draws[1])
+            fo = _sampling.sac_head_fused(logits.view(B, self.A, self.P), self.loc, self.logstd, da.contiguous(), dlogp,
+                                          seed=self.sample_seed, offset=off, **ext)
+            self._backward_stack(self.actor + [self.fc_policy], a_acts, fo["dlogits"].view(B, self.A * self.P))
+            self.dloc.copy_(fo["dloc"])
+            self.dlogstd.copy_(fo["dlogstd"])
+        else:
+            lg, loc_l, ls_l = leaves
+            torch.autograd.backward([logp, smp], [dlogp, da])
+            self._backward_stack(self.actor + [self.fc_policy], a_acts, lg.grad.reshape(B, self.A * self.P).contiguous())
+            self.dloc.copy_(loc_l.grad)
+            self.dlogstd.copy_(ls_l.grad)
         self.dlog_alpha.copy_(out4[2:3])
         return out4[0] + out4[1], None, out4[1], out4[0]
 

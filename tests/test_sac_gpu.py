@@ -106,3 +106,29 @@ def test_sac_reference_facing_calls(cuda_dev):
     for n in (n1, n2):
         n.train(None, SACOptimizer(), None, *(b1[k].numpy() for k in ("state", "action", "reward", "not_terminal", "state_")))
     assert torch.equal(n1.params, n2.params) and torch.equal(n1.target_params, n2.target_params)
+
+
+def test_sac_step_with_the_fused_head_kernel_equals_the_autograd_composition(cuda_dev):
+    """P = 100 (BASELINE c5 shape): compute_gradients through K3f (one pass: rsample backward + tanh log_prob fwd/bwd,
+    draws regenerated from the forward's Philox counters) vs the three-launch autograd composition."""
+    import os
+    from pfpn_b200.sac import ParticleFilteringSACNetwork
+    S, A, P, B = 197, 36, 100, 300
+    grads = {}
+    for mode in ("1", "0"):
+        os.environ["PFPN_SAC_FUSED"] = mode
+        try:
+            net = ParticleFilteringSACNetwork(True, [S], [A], action_lower_bound=[-1.] * A, action_upper_bound=[1.] * A,
+                                              particles=P, resample=-1, resample_interval=12000, normalize_state=True,
+                                              clip_state=5.0, device=cuda_dev, seed=3).init()
+            g = torch.Generator().manual_seed(9)
+            net.params.add_((0.05 * torch.randn(net.params.shape, generator=g)).to(cuda_dev))
+            batch = (torch.randn(B, S, generator=g), torch.rand(B, A, generator=g) * 1.9 - 0.95, torch.randn(B, generator=g),
+                     (torch.rand(B, generator=g) > 0.1).float(), torch.randn(B, S, generator=g))
+            losses = net.compute_gradients(*batch)
+            torch.cuda.synchronize()
+            grads[mode] = (net.grads.clone(), [float(x) for x in losses if x is not None])
+        finally:
+            os.environ.pop("PFPN_SAC_FUSED", None)
+    assert rel(grads["1"][0], grads["0"][0]) < 2 * TOL
+    assert np.allclose(grads["1"][1], grads["0"][1], rtol=1e-6, atol=1e-7)
