@@ -216,7 +216,7 @@ def timed(fn, n, stream, warm=3):
 
 
 def tensor_hash(t: torch.Tensor) -> torch.Tensor:
-    bits = t.detach().contiguous().view(torch.int32).to(torch.int64)
+    bits = t.detach().contiguous().reshape(-1).view(torch.int32).to(torch.int64)
     w = torch.arange(1, bits.numel() + 1, device=bits.device, dtype=torch.int64) % 65521
     return torch.stack([bits.sum(), (bits * w).sum()])
 

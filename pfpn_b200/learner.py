@@ -53,7 +53,7 @@ def assert_replicas_identical(params: torch.Tensor, group=None, what: str = "par
     checksum of the raw fp32 bits; a no-op for a single process."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2:
         return
-    bits = params.detach().contiguous().view(torch.int32).to(torch.int64)
+    bits = params.detach().contiguous().reshape(-1).view(torch.int32).to(torch.int64)
     w = torch.arange(1, bits.numel() + 1, device=bits.device, dtype=torch.int64)
     h = torch.stack([bits.sum(), (bits * (w % 65521)).sum()])
     hs = [torch.empty_like(h) for _ in range(dist.get_world_size(group))]
