@@ -314,8 +314,11 @@ def main():
         if use_peer:
             # the path's only exchange: [2, A, P] particle gradients.  K1's finalize kernel PUSHES them into
             # every rank's gather buffer and raises the flags; the consumer sums its N local rows in rank order.
+            # The consumer runs on a second stream, so the next step's head kernel overlaps the wait for the slowest rank;
+            # `gather.wait()` is what a reader of the sum (the optimizer) calls.
+            gather.begin_step(stream)
             _cabi.check(_cabi.pfpn_head_logprob_push(a, ws.data_ptr(), ws.numel(), gather.push_args(), stream.cuda_stream))
-            gather.reduce(flat_small.view(-1), 1.0, stream.cuda_stream)
+            gather.reduce_async(flat_small.view(-1), 1.0, stream)
         else:
             _cabi.check(_cabi.pfpn_head_logprob(a, ws.data_ptr(), ws.numel(), stream.cuda_stream))
             if world > 1:
@@ -325,6 +328,8 @@ def main():
     launches_per_step = 3 + (1 if use_peer else 0)
 
     def barrier():
+        if use_peer:
+            gather.wait(stream)  # the timed region ends when the last exchange has been consumed
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -337,6 +342,8 @@ def main():
     evs[0].record(stream)
     for i in range(args.steps):
         step()
+        if use_peer and i == args.steps - 1:
+            gather.wait(stream)  # (inside the timed region: the last exchange is consumed before the closing event)
         evs[i + 1].record(stream)
     barrier()
     per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
@@ -349,7 +356,11 @@ def main():
         xcheck = {}
         step()
         torch.cuda.synchronize()
-        mine = torch.stack([dloc, dlogstd]).clone() if not use_peer else gather.gather[gather.calls & 1, rank].view(2, A, P).clone()
+        if use_peer:
+            gather.wait(stream)
+            torch.cuda.synchronize()
+        mine = torch.stack([dloc, dlogstd]).clone() if not use_peer else \
+            gather.gather[gather.slot_of(gather.calls), rank].view(2, A, P).clone()
         allc = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allc, mine)
         ordered = allc[0].clone()

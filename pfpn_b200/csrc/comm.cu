@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) peer_sum_kernel(PeerPtrs pp, int rank, in
 // gather buffer and raised this rank's flag words; wait for the N flags, then sum the N local rows in rank order.
 // Launched with programmatic stream serialization: it becomes resident behind K1's finalize and is already polling
 // when the flags arrive.  No CTA waits on another CTA of this grid, so there is no co-residency requirement.
-__global__ void __launch_bounds__(256) peer_gather_sum_kernel(const float* __restrict__ gather, const int* __restrict__ flags,
+__global__ void __launch_bounds__(64) peer_gather_sum_kernel(const float* __restrict__ gather, const int* __restrict__ flags,
                                                               int nranks, int value, size_t n4, float* __restrict__ out,
                                                               float scale) {
   asm volatile("griddepcontrol.wait;" ::: "memory");  // (orders the previous consumer of `out` / this rank's own push)
@@ -206,12 +206,14 @@ using namespace pfpn;
 extern "C" int pfpn_peer_gather_sum(const float* gather, const int32_t* flags, int32_t nranks, int32_t value, size_t n,
                                     float* out, float scale, pfpn_stream_t stream_) {
   if (!gather || !flags || !out || nranks < 1 || nranks > kMaxPeers || (n & 3) || n == 0 || value < 1) return PFPN_ERR_ARG;
+  // 64-thread CTAs (~2 K registers each): small enough to become resident NEXT TO the persistent head kernel's CTAs (which
+  // leave 4 K registers and 28 KB of shared memory per SM), so a consumer on a second stream overlaps the next step
   const size_t n4 = n / 4;
-  size_t grid = (n4 + 255) / 256;
-  if (grid > 148) grid = 148;
+  size_t grid = (n4 + 63) / 64;
+  if (grid > 296) grid = 296;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(64);
   cfg.stream = reinterpret_cast<cudaStream_t>(stream_);
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -34,16 +34,6 @@ struct RolloutK {
   int num_tiles;
 };
 
-__device__ __forceinline__ float ro_exp_term(float d) {  // e^d for d <= 0, relative error ~5e-7 (as K2)
-  const float t = d * kLog2e;
-  const float n = rintf(t);
-  float f = fmaf(d, kLog2e, -n);    // single rounding of d*log2e - n
-  f = fmaf(d, 1.925963033e-8f, f);  // low part of log2(e) beyond its fp32 value
-  const int ni = (int)n;
-  const float scale = ni >= -126 ? __int_as_float((ni + 127) << 23) : 0.f;
-  return ex2f(f) * scale;
-}
-
 // The literal fp64 algorithm for one row (fallback; also the semantic definition), executed by a whole WARP for one row
 // at a time in warp-uniform control flow: every lane evaluates exp(double(logit) - max) for its particles (the expensive
 // part), the values go through a shared-memory scratch row, and ONE lane replays TF's sequential fp64 running total and
@@ -200,21 +190,26 @@ __global__ void __launch_bounds__(SLOTS * 72 + 32, 2) rollout_kernel(const Rollo
       const float* lg = sbuf + (row_ok ? slot : 0) * AP + a * P;
 
       // ---- softmax terms (TF: max over the FINITE logits; a non-finite logit contributes nothing) -------------
+      // Non-finite logits (and the unused 36th half-slot) are mapped to -FLT_MAX once: their term is then exactly 0 with
+      // no further test.  e^d = 2^(d log2 e) straight on the MUFU pipe: |relative error| <= 2^-22 + |d| 6e-8, weighted by
+      // the term itself that is < 5e-7 of the total -- well inside the budget `delta` of the margin test below.
       float e1[EPL];
       float m = -3.402823466e38f;
 #pragma unroll
       for (int i = 0; i < EPL; ++i) {
         const bool ok = i < 17 || c == 0;
-        e1[i] = ok ? lg[kof(i)] : __int_as_float(0x7f800000);  // (+inf = "not a particle")
-        if (isfinite(e1[i])) m = fmaxf(m, e1[i]);
+        const float x = ok ? lg[kof(i)] : -3.402823466e38f;
+        e1[i] = fabsf(x) <= 3.402823466e38f ? x : -3.402823466e38f;
+        m = fmaxf(m, e1[i]);
       }
       m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      const bool degenerate = !(m > -3.402823466e38f);  // no finite logit at all: the literal algorithm decides
       float T = 0.f, Hs = 0.f;  // block total (slots < 16); sum e (l - m) for the entropy
 #pragma unroll
       for (int i = 0; i < EPL; ++i) {
-        const float d = e1[i] - m;
-        const float e = isfinite(e1[i]) ? ro_exp_term(d) : 0.f;
-        Hs = fmaf(e, isfinite(e1[i]) ? d : 0.f, Hs);
+        const float d = fmaxf(e1[i] - m, -1e30f);  // (finite: 0 * d below stays 0)
+        const float e = ex2f(d * kLog2e);
+        Hs = fmaf(e, d, Hs);
         e1[i] = e;
         if (i < 16) T += e;  // running total inside this lane's block of 16 consecutive particles
       }
@@ -262,7 +257,7 @@ __global__ void __launch_bounds__(SLOTS * 72 + 32, 2) rollout_kernel(const Rollo
         near = near || near_o != 0;
       }
       int idx = cnt;
-      const bool fallback = near || idx >= P || !(total > 0.f) || !isfinite(total);
+      const bool fallback = near || idx >= P || !(total > 0.f) || !isfinite(total) || degenerate;
       // rows that need the literal fp64 algorithm (~0.1 %): one at a time, by the whole warp, in warp-uniform control flow
       unsigned fb_mask = __ballot_sync(0xffffffffu, fallback && c == 0);
       while (fb_mask != 0u) {

@@ -105,9 +105,17 @@ class PeerSum:
 class PeerGather:
     """PUSH protocol for the sharded head's [2, A, P] exchange (`pfpn_head_logprob_push` + `pfpn_peer_gather_sum`): K1's
     finalize kernel stores this rank's dloc / dlogstd into row `rank` of EVERY rank's gather buffer and raises the flags;
-    ``reduce`` waits for the N flags and sums the N local rows in rank order.  No exchange kernel sits behind K1.
+    the consumer waits for the N flags and sums the N local rows in rank order.  No exchange kernel sits behind K1.
 
-    Per rank: gather [2 parities][world][n] floats, flags int32[64] (word r = last call rank r pushed), one local ticket."""
+    The consumer can run on a SECOND stream (``reduce_async``): the next step's head kernel then overlaps the wait for the
+    slowest rank, and whoever needs the sum calls ``wait``.  Buffers rotate over NBUF = 4 call slots; with
+    ``begin_step`` making the main stream wait for this rank's own consumer of two steps ago, a slot is provably consumed
+    by every rank before any rank overwrites it: consume(v) < head(v+2) < push(v+2) on rank p, which rank r observes in
+    its consumer of v+2, which its head(v+4) -- and therefore its push(v+4) into the same slot -- waits for.
+
+    Per rank: gather [NBUF][world][n] floats, flags int32[64] (word r = last call rank r pushed), one local ticket."""
+
+    NBUF = 4
 
     def __init__(self, n: int, device: torch.device, group=None):
         if n % 4:
@@ -115,32 +123,64 @@ class PeerGather:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.n, self.calls, self.dev = n, 0, device
         with torch.cuda.device(device):
-            gather = _alloc(2 * self.world * n * 4)
+            gather = _alloc(self.NBUF * self.world * n * 4)
             flag = _alloc(64 * 4)
             self._gather_ptr, self._flag_ptr = gather[0], flag[0]
             self._gather_ptrs, self._flag_ptrs = _share([gather, flag], device, group)
-        self.gather = torch.as_tensor(_CudaArray(self._gather_ptr, 2 * self.world * n, "<f4"), device=device).view(2, self.world, n)
+        self.gather = torch.as_tensor(_CudaArray(self._gather_ptr, self.NBUF * self.world * n, "<f4"),
+                                      device=device).view(self.NBUF, self.world, n)
         self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
-        self._push = [self._make_push(par) for par in (0, 1)]
+        self._push = [self._make_push(slot) for slot in range(self.NBUF)]
+        self.side = torch.cuda.Stream(device, priority=-1)
+        self._pushed = [torch.cuda.Event() for _ in range(self.NBUF)]
+        self._done = [torch.cuda.Event() for _ in range(self.NBUF)]
 
-    def _make_push(self, parity: int):
+    def _make_push(self, slot: int):
         p = _cabi.HeadPush()
         for r in range(self.world):
-            p.out[r] = self._gather_ptrs[r] + ((parity * self.world + self.rank) * self.n) * 4
+            p.out[r] = self._gather_ptrs[r] + ((slot * self.world + self.rank) * self.n) * 4
             p.flags[r] = self._flag_ptrs[r] + 4 * self.rank
         p.ticket = self.ticket.data_ptr()
         p.nranks = self.world
         return p
 
+    def slot_of(self, call: int) -> int:
+        return call % self.NBUF
+
+    def begin_step(self, stream=None):
+        """Call before launching the producer of the next exchange: bounds the consumer's lag to two steps."""
+        v = self.calls + 1
+        if v - 2 >= 1:
+            (stream or torch.cuda.current_stream(self.dev)).wait_event(self._done[self.slot_of(v - 2)])
+
     def push_args(self):
-        """The `pfpn_head_push` of the NEXT exchange (pass to pfpn_head_logprob_push, then call ``reduce``)."""
-        p = self._push[(self.calls + 1) & 1]
+        """The `pfpn_head_push` of the NEXT exchange (pass to pfpn_head_logprob_push, then call ``reduce[_async]``)."""
+        p = self._push[self.slot_of(self.calls + 1)]
         p.value = self.calls + 1
         return p
 
-    def reduce(self, out: torch.Tensor, scale: float = 1.0, stream_ptr: int = 0):
+    def reduce_async(self, out: torch.Tensor, scale: float = 1.0, stream=None):
+        """Consume the exchange just produced on `stream` (default: current) on the side stream; ``wait`` before reading `out`."""
+        main = stream or torch.cuda.current_stream(self.dev)
         self.calls += 1
-        par = self.calls & 1
-        _cabi.check(_cabi.pfpn_peer_gather_sum(self._gather_ptr + par * self.world * self.n * 4, self._flag_ptr, self.world,
+        slot = self.slot_of(self.calls)
+        self._pushed[slot].record(main)
+        self.side.wait_event(self._pushed[slot])
+        _cabi.check(_cabi.pfpn_peer_gather_sum(self._gather_ptr + slot * self.world * self.n * 4, self._flag_ptr, self.world,
+                                               self.calls, self.n, out.data_ptr(), scale, self.side.cuda_stream))
+        self._done[slot].record(self.side)
+        return out
+
+    def wait(self, stream=None):
+        """Make `stream` (default: current) wait for the latest consumer."""
+        if self.calls >= 1:
+            (stream or torch.cuda.current_stream(self.dev)).wait_event(self._done[self.slot_of(self.calls)])
+
+    def reduce(self, out: torch.Tensor, scale: float = 1.0, stream_ptr: int = 0):
+        """Synchronous form: the consumer runs on the producer's stream (`stream_ptr`)."""
+        self.calls += 1
+        slot = self.slot_of(self.calls)
+        _cabi.check(_cabi.pfpn_peer_gather_sum(self._gather_ptr + slot * self.world * self.n * 4, self._flag_ptr, self.world,
                                                self.calls, self.n, out.data_ptr(), scale, stream_ptr))
+        self._done[slot].record(torch.cuda.current_stream(self.dev))
         return out

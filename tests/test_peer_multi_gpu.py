@@ -25,7 +25,7 @@ def test_fused_peer_allreduce_adam_matches_nccl():
         assert d["max_abs_param_diff_fused_vs_nccl"] < 1e-7
         assert d["small_sum_ok"]  # the head's [2,A,P] exchange (pfpn_peer_allreduce_sum) vs NCCL, replicas bit-identical
         assert d["graph_replays"] == 4 and d["graph_equals_eager"] and d["graph_replicas_equal"]  # CUDA-graph replay of the update
-        assert d["push_sum_ok"]   # push form (pfpn_head_logprob_push + pfpn_peer_gather_sum): bit-equal to the rank-ordered sum
+        assert d["push_sum_ok"] and d["push_async_ok"]   # push form (pfpn_head_logprob_push + pfpn_peer_gather_sum): bit-equal to the rank-ordered sum
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")

@@ -97,6 +97,37 @@ if os.path.exists(rep):
     mix = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_opmix.py"), tmp], capture_output=True, text=True).stdout
     open(os.path.join(out, f"{rnd}_tc_gemm_kernel.md"), "a").write("\n## SASS opcode mix (UTCHMMA = tcgen05.mma, UTMALDG = TMA load) and stall samples\n\n```\n" + mix + "```\n")
     print("tc gemm summary written")
+# ---- generic summaries: K3f (sac_full.ncu-rep) and K2f (rollout_full.ncu-rep) ------------------------------------------
+def summarize(rep_name, out_name, title, alg_bytes=None):
+    rep = os.path.join(src, rep_name)
+    if not os.path.exists(rep):
+        return
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines())); hdr, units, vals = rows[0], rows[1], rows[2]
+    keys = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
+            "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.max"] + \
+           [k for k in hdr if k.startswith("smsp__average_warps_issue_stalled") and k.endswith("_per_issue_active.ratio")]
+    with open(os.path.join(out, out_name), "w") as f:
+        f.write(f"# {rnd}: `ncu --set full` of {title}\n\n| metric | unit | value |\n|---|---|---|\n")
+        for k in keys:
+            if k in hdr:
+                f.write(f"| {k} | {units[hdr.index(k)]} | {vals[hdr.index(k)]} |\n")
+        if alg_bytes:
+            f.write(f"\nalgorithmic bytes per launch = {alg_bytes/1e6:.1f} MB\n")
+    srcp = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+    tmp = os.path.join(src, rep_name.replace(".ncu-rep", "_src.csv")); open(tmp, "w").write(srcp)
+    mix = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_opmix.py"), tmp], capture_output=True, text=True).stdout
+    open(os.path.join(out, out_name), "a").write("\n## SASS opcode mix (warp-instructions executed) and stall samples\n\n```\n" + mix + "```\n")
+    print(out_name, "written")
+
+
+summarize("sac_full.ncu-rep", f"{rnd}_sac_head_kernel.md", "K3f, the fused SAC head kernel (B=65536, A=36, P=100, fwd+bwd)", 29240 * 65536)
+summarize("rollout_full.ncu-rep", f"{rnd}_rollout_kernel.md", "K2f, the fused rollout kernel (B=65536, A=36, P=35)", 5336 * 65536)
 for extra in ("configs_r01.json",):
     pth = os.path.join(src, extra)
     if os.path.exists(pth):
