@@ -79,6 +79,9 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
   // 16 (c / 4) + c % 4 -- the four rows of a warp land on banks 4r + {0..3, 16..19}, all 32 distinct in every round
   // (P = 100).  Both maps keep the validity rule "slot i < P / LPR for every lane, slot P / LPR for c < P % LPR".
   constexpr bool SPL = (OPT & 4) != 0;
+  // OPT bit 3 (HINT): barrier waits carry a suspend-time hint -- 17 % of the warp instructions of the round-2 profile were
+  // SYNCS / BRA / YIELD of spinning try_wait loops
+  constexpr bool HINT = (OPT & 8) != 0;
   static_assert(!SPL || (LPR == 2 && PT == 35) || (LPR == 8 && PT == 100), "split ownership: P=35 / 2 lanes or P=100 / 8 lanes");
   constexpr bool LEAN = KM >= 2;
   constexpr int EP2 = (EPL + 1) / 2;  // packed pairs per lane
@@ -270,7 +273,8 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
         }
       }
       if (it >= 1) {
-        mbar_wait(cta_bar_a, (uint32_t)((it - 1) & 1));
+        if (HINT) mbar_wait_hint(cta_bar_a, (uint32_t)((it - 1) & 1), 2000u);
+        else mbar_wait(cta_bar_a, (uint32_t)((it - 1) & 1));
         if (lane == 0) {
           if (BWD && it >= 2) {
             const int ptile = first_tile + (it - 2) * tile_step;
@@ -387,7 +391,8 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
       load_values(it + 1);
 
       if (!is_tail) {
-        mbar_wait(smem_u32(&full_bar[st]), (uint32_t)((it / NSTAGE) & 1));
+        if (HINT) mbar_wait_hint(smem_u32(&full_bar[st]), (uint32_t)((it / NSTAGE) & 1), 1000u);
+        else mbar_wait(smem_u32(&full_bar[st]), (uint32_t)((it / NSTAGE) & 1));
       } else {
         const int nvalid = (B - b0) * AP;
         const float* src = g_logits + (size_t)b0 * AP;
@@ -487,7 +492,8 @@ __global__ void __launch_bounds__(((MAXT + 31) / 32) * 32 + 32) __maxnreg__(NREG
       const float2* rb = rowbuf + (pit % NSTAGE) * TS * A;
 
       if (SIP && BWD) {
-        mbar_wait(smem_u32(&g_bar[pit & 1]), (uint32_t)((pit >> 1) & 1));  // the producer published dL/dlp of tile it-1
+        if (HINT) mbar_wait_hint(smem_u32(&g_bar[pit & 1]), (uint32_t)((pit >> 1) & 1), 1000u);
+        else mbar_wait(smem_u32(&g_bar[pit & 1]), (uint32_t)((pit >> 1) & 1));  // the producer published dL/dlp of tile it-1
       } else {  // (forward: keeps the compute warps within one step of each other and of the producer)
         mbar_wait(cta_bar_a, (uint32_t)(pit & 1));  // every compute thread finished iteration it-1
       }
@@ -894,7 +900,8 @@ static const HeadVariant kHeadVariants[] = {
     // (.165), GRAD .1537 (.165; 4 lanes per row with carried terms .179), FWD .0799 (.084), tanh + dvalue .169 (.177).
     PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 4, 288, 96, 35, 36, 7, 1 | 2 | 4 | 8),
     PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 4, 288, 96, 35, 36, 3, 0),  // [1] interleaved ownership (round 1 default)
-    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, 1, 0),   // [2] 4 lanes per row, carried terms
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 2, 18, 1, 4, 288, 96, 35, 36, 15, 0), // [2] split ownership + suspend-time hints (measured: no change, .1544 vs .1545)
+    PFPN_HEAD_VARIANT_ENTRY(35, 35, 4, 9, 1, 5, 288, 96, 35, 36, 1, 0),   // [3] 4 lanes per row, carried terms
     // P = 100 (SAC sweep): 13 particles per lane spill in the backward modes when the particle terms are carried,
     // so the backward runs 8 lanes per row WITH recompute (no carried terms, no spills, two CTAs per SM);
     // 16 lanes per row / 7 per lane (one 19-warp CTA per SM) is the carried-terms alternative.  Forward: 8 lanes,

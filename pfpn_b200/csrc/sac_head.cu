@@ -110,10 +110,20 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
     }
     mbar_fence_init();
   }
+  // The two float2 tables are stored PERMUTED inside every 32-particle block: an 8-byte access is served per half warp
+  // (2 rows x 8 lanes), rows are 100 float2 = 4 (mod 16) slots apart, so the 8 lanes of a row must cover {0..3, 8..11}
+  // (+ 4 for odd u): pos(32 j + 4 u + 16 h + w) = 32 j + 16 (u / 2) + 4 (u % 2) + 8 h + w.  (61 M bank conflicts per
+  // launch in the first round-2 profile came from these two tables in natural order.)
+  auto perm = [](int k) -> int {
+    const int r = k & 31;
+    return (k & ~31) + 16 * ((r >> 3) & 1) + 4 * ((r >> 2) & 1) + 8 * (r >> 4) + (r & 3);
+  };
   for (int i = tid; i < AP; i += NTHR + 32) {
     const float ls = __ldg(&kp.a.logstd[i]), mu = __ldg(&kp.a.loc[i]);
-    ms_s[i] = make_float2(mu, FAST ? ex2f(ls * kLog2e) : expf(ls));  // (FAST: the scale the split kernels use -> the same locations)
-    mi_s[i] = make_float2(-mu, expf(-ls));
+    const int ai = i / P, ki = i - ai * P;
+    const int ip = ai * P + perm(ki);
+    ms_s[ip] = make_float2(mu, FAST ? ex2f(ls * kLog2e) : expf(ls));  // (FAST: the scale the split kernels use -> the same locations)
+    mi_s[ip] = make_float2(-mu, expf(-ls));
     cst_s[i] = -(ls + kHalfLog2Pi) * kLog2e;
   }
   for (int i = tid; i < SLOTS * 2 * AP; i += NTHR + 32) acc_s[i] = 0.f;
@@ -175,6 +185,7 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
     const int rem = tid - slot * (A * LPR);
     const int a = rem >> 3, c = rem & 7;
     const int kb0 = 16 * (c >> 2) + (c & 3);
+    const int pb0 = 8 * (c >> 2) + (c & 3);  // this lane's offset inside a permuted 32-block of the float2 tables
     const bool tail_ok = c < P - 96;  // slot (u = 0, j = 3): particle 96 + kb0
     const float2* ms_r = ms_s + a * P;
     const float2* mi_r = mi_s + a * P;
@@ -243,7 +254,7 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
           const int k = kb + 32 * j;
           const bool ok = j < 3 || tail_ok;
           const float x = ok ? lg[k] : 0.f;
-          const float2 ms = ms_r[ok ? k : 0];  // {mu, sigma}
+          const float2 ms = ms_r[ok ? 32 * j + 16 * (u >> 1) + 4 * (u & 1) + pb0 : 0];  // {mu, sigma}, permuted table
           const float yf = ok ? fmaf(x, kLog2e, -(FAST ? lg2f(nl4[j]) : log2f(nl4[j]))) : -3.402823466e38f;
           const float ycmp = FAST ? yf : (ok ? x + ya4[j] : -3.402823466e38f);  // (G + logits) / T, T = 1
           const float pk = FAST ? fmaf(n4[j], ms.y, ms.x) : __fadd_rn(__fmul_rn(n4[j], ms.y), ms.x);
@@ -293,13 +304,18 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
         const int k = 4 * u + kb0 + 32 * j;
         return (e < 12 || (e == 12 && tail_ok)) ? k : 0;  // masked half-slots read entry 0 (their terms are exactly 0)
       };
+      auto slot_p = [&](int e) -> int {  // position of slot e's particle in the permuted float2 tables
+        const int u = e < 12 ? e / 3 : 0, j = e < 12 ? e % 3 : 3;
+        const int q = 32 * j + 16 * (u >> 1) + 4 * (u & 1) + pb0;
+        return (e < 12 || (e == 12 && tail_ok)) ? q : 0;
+      };
       const float2 uu2 = splat2(uu), nyf2 = splat2(-yfm), one2 = splat2(1.f), mtwo2 = splat2(-2.f);
       const float2 tl2 = splat2(2.f * kLog2e), nhl2 = splat2(-0.5f * kLog2e);
       float2 S1v = splat2(0.f), S2v = S1v, Tv = S1v, Swv = S1v, Swtv = S1v;
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
         const int k0 = slot_k(2 * i), k1 = slot_k(2 * i + 1);
-        const float2 m0 = mi_r[k0], m1 = mi_r[k1];  // {-mu, 1 / sigma}
+        const float2 m0 = mi_r[slot_p(2 * i)], m1 = mi_r[slot_p(2 * i + 1)];  // {-mu, 1 / sigma}
         const float2 nmu = make_float2(m0.x, m1.x), is2 = make_float2(m0.y, m1.y);
         const float2 cs2 = make_float2(cst_r[k0], cst_r[k1]);
         const float2 dy = add2(y2[i], nyf2);
@@ -349,7 +365,7 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
         const int k0 = slot_k(2 * i), k1 = slot_k(2 * i + 1);
-        const float2 m0 = mi_r[k0], m1 = mi_r[k1];
+        const float2 m0 = mi_r[slot_p(2 * i)], m1 = mi_r[slot_p(2 * i + 1)];
         const float2 z = mul2(add2(uu2, make_float2(m0.x, m1.x)), make_float2(m0.y, m1.y));
         const float2 w = y2[i];
         const float2 rr = mul2(e22[i], gs2v);                                           // g r_k
@@ -365,8 +381,10 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
       if (c == 0 && row_ok) {
         // the winner's straight-through terms: dL/dp_{k*} = (1 - t^2) g_a + g_u; this row's lanes are the only writers of
         // acc_r (slot, a) -- plain read-modify-write.  Stored times sigma: the finalize kernel divides dloc by sigma.
-        const float gp = fmaf(omt2, ga, gu) * ms_r[arg].y;
-        const float zs = (uu + mi_r[arg].x) * mi_r[arg].y;        // = eps of the winner
+        const int ra = arg & 31;
+        const int parg = (arg & ~31) + 16 * ((ra >> 3) & 1) + 4 * ((ra >> 2) & 1) + 8 * (ra >> 4) + (ra & 3);
+        const float gp = fmaf(omt2, ga, gu) * ms_r[parg].y;
+        const float zs = (uu + mi_r[parg].x) * mi_r[parg].y;      // = eps of the winner
         acc_r[arg] += gp;
         acc_r[AP + arg] += gp * zs;
         const size_t o = (size_t)b * A + a;

@@ -22,6 +22,7 @@
 // Pipelines: full[s] (TMA -> splitter), conv[s] (splitter -> MMA), empty[s] (MMA -> TMA),
 // tmem_full (MMA -> epilogue).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -403,6 +404,327 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent form (round 2): one CTA per SM walks the output tiles (tile = z * tiles_m * tiles_n + m * tiles_n + n).
+// The operand ring, the TMEM allocation and the barriers live for the whole kernel, the TMA producer prefetches the next
+// tile's k-blocks while the current tile drains, and the epilogue is split: warps 4-7 (the splitters) move the three
+// accumulators from TMEM into a dedicated 64 KiB staging area and hand the accumulators back to the MMA warp at once;
+// warps 8-11 then apply bias / relu6 / Relu6Grad mask and write the tile to global memory WHILE the next tile's main
+// loop runs.  (A second accumulator set does not fit: 3 x 128 accumulator columns + 128 A-operand columns = 512.)
+// Barriers: full / conv / empty per ring stage (phases follow a global k-block counter), acc_full (MMA -> splitters),
+// acc_free (splitters -> MMA), stage_full (splitters -> store warps), stage_free (store warps -> splitters).
+// ------------------------------------------------------------------------------------------------
+constexpr int TCP_STAGES = 3;
+constexpr int TCP_RING_BYTES = TCP_STAGES * TC_STAGE_BYTES;
+constexpr int TCP_STAGING_BYTES = 4 * TC_TILE_BYTES;   // 128 x 128 fp32
+constexpr int TCP_SCR_BYTES = 16 * 128 * 4;            // bias-gradient scratch
+constexpr int TCP_SMEM_BYTES = TCP_RING_BYTES + TCP_STAGING_BYTES + TCP_SCR_BYTES + 1024 + 256;
+constexpr int TCP_THREADS = 384;
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                         const __grid_constant__ CUtensorMap mapB,
+                                                                         const __grid_constant__ CUtensorMap mapBlo,
+                                                                         const TcParams p, const int tiles_m, const int tiles_n,
+                                                                         const int num_tiles) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char* gbase = smem_dyn + (base - raw);
+  unsigned char* staging = gbase + TCP_RING_BYTES;
+  float* scr = reinterpret_cast<float*>(staging + TCP_STAGING_BYTES);
+  const uint32_t bar0 = base + TCP_RING_BYTES + TCP_STAGING_BYTES + TCP_SCR_BYTES;
+  auto full = [&](int s) { return bar0 + 8 * s; };
+  auto conv = [&](int s) { return bar0 + 8 * (TCP_STAGES + s); };
+  auto empty = [&](int s) { return bar0 + 8 * (2 * TCP_STAGES + s); };
+  const uint32_t acc_full = bar0 + 8 * 3 * TCP_STAGES, acc_free = acc_full + 8, stage_full = acc_full + 16,
+                 stage_free = acc_full + 24;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + TCP_RING_BYTES + TCP_STAGING_BYTES + TCP_SCR_BYTES +
+                                                                       8 * (3 * TCP_STAGES + 4));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TCP_STAGES; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(conv(s), 128);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_free, 128);
+    mbar_init(stage_full, 128);
+    mbar_init(stage_free, 128);
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+    if (p.b_lo_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBlo)) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  const int tiles_mn = tiles_m * tiles_n;
+  auto decode = [&](int t, int& z, int& m0, int& n0, int& k_begin, int& nkb) {
+    z = t / tiles_mn;
+    const int rem = t - z * tiles_mn;
+    const int mb = rem / tiles_n;
+    m0 = mb * TC_BM;
+    n0 = (rem - mb * tiles_n) * TC_BN;
+    k_begin = z * p.k_chunk;
+    const int k_end = min(p.K, k_begin + p.k_chunk);
+    nkb = (k_end - k_begin + TC_BK - 1) / TC_BK;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int g = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int z, m0, n0, k_begin, nkb;
+        decode(t, z, m0, n0, k_begin, nkb);
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int s = g % TCP_STAGES;
+          mbar_wait(empty(s), (uint32_t)(((g / TCP_STAGES) & 1) ^ 1));
+          mbar_expect_tx(full(s), (p.b_lo_tma ? 3 : 2) * TC_TILE_BYTES);
+          const uint32_t a_dst = base + s * TC_STAGE_BYTES, b_dst = a_dst + TC_TILE_BYTES, l_dst = b_dst + TC_TILE_BYTES;
+          const int k0 = k_begin + kb * TC_BK;
+          if (A_MN) {
+#pragma unroll
+            for (int q = 0; q < TC_BM / 32; ++q) tma_load_2d(a_dst + q * 4096, &mapA, m0 + 32 * q, k0, full(s));
+          } else {
+            tma_load_2d(a_dst, &mapA, k0, m0, full(s));
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int q = 0; q < TC_BN / 32; ++q) tma_load_2d(b_dst + q * 4096, &mapB, n0 + 32 * q, k0, full(s));
+          } else {
+            tma_load_2d(b_dst, &mapB, k0, n0, full(s));
+          }
+          if (p.b_lo_tma) {
+            if (B_MN) {
+#pragma unroll
+              for (int q = 0; q < TC_BN / 32; ++q) tma_load_2d(l_dst + q * 4096, &mapBlo, n0 + 32 * q, k0, full(s));
+            } else {
+              tma_load_2d(l_dst, &mapBlo, k0, n0, full(s));
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int g = 0, ti = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+        int z, m0, n0, k_begin, nkb;
+        decode(t, z, m0, n0, k_begin, nkb);
+        if (ti > 0) mbar_wait(acc_free, (uint32_t)((ti - 1) & 1));  // the previous tile's accumulators were read out
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int s = g % TCP_STAGES;
+          mbar_wait(conv(s), (uint32_t)((g / TCP_STAGES) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t b_hi = base + s * TC_STAGE_BYTES + TC_TILE_BYTES, b_lo = b_hi + TC_TILE_BYTES;
+          const uint32_t a_hi = tmem + TC_TMEM_A + (uint32_t)((g & 1) * 64), a_lo = a_hi + 32;
+#pragma unroll
+          for (int ks = 0; ks < TC_BK / 8; ++ks) {
+            const uint64_t db_hi = B_MN ? umma_desc_mn(b_hi + ks * 1024) : umma_desc(b_hi + ks * 32);
+            const uint64_t db_lo = B_MN ? umma_desc_mn(b_lo + ks * 1024) : umma_desc(b_lo + ks * 32);
+            const uint32_t dmain = tmem + (uint32_t)((kb & 1) * TC_BN);
+            umma_tf32_ts(dmain, a_hi + ks * 8, db_hi, idesc, (kb >= 2 || ks != 0) ? 1u : 0u);
+            umma_tf32_ts(tmem + 2 * TC_BN, a_lo + ks * 8, db_hi, idesc, (kb | ks) != 0);
+            umma_tf32_ts(tmem + 2 * TC_BN, a_hi + ks * 8, db_lo, idesc, 1u);
+          }
+          umma_commit(empty(s));
+        }
+        umma_commit(acc_full);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int t128 = threadIdx.x - 128;
+    const int wq = warp & 3;
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    int g = 0, ti = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+      int z, m0, n0, k_begin, nkb;
+      decode(t, z, m0, n0, k_begin, nkb);
+      const bool do_cs = B_MN && p.colsum != nullptr && m0 == 0;
+      float4 cs[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cs[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int kb = 0; kb < nkb; ++kb, ++g) {
+        const int s = g % TCP_STAGES;
+        mbar_wait(full(s), (uint32_t)((g / TCP_STAGES) & 1));
+        const unsigned char* sa = gbase + (size_t)s * TC_STAGE_BYTES;
+        uint32_t xh[32], xl[32];
+        if (A_MN) {
+          const unsigned char* pa = sa + (t128 >> 5) * 4096 + (t128 & 7) * 4;
+          const int c = (t128 & 31) >> 3;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) xh[r] = *reinterpret_cast<const uint32_t*>(pa + r * 128 + ((c ^ (r & 3)) << 5));
+        } else {
+          const unsigned char* pa = sa + t128 * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 v = *reinterpret_cast<const uint4*>(pa + ((c ^ (t128 & 7)) << 4));
+            xh[4 * c] = v.x; xh[4 * c + 1] = v.y; xh[4 * c + 2] = v.z; xh[4 * c + 3] = v.w;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          xl[r] = __float_as_uint(__uint_as_float(xh[r]) - __uint_as_float(xh[r] & 0xffffe000u));
+        if (!p.b_lo_tma) {
+          const float4* hi = reinterpret_cast<const float4*>(sa + TC_TILE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(const_cast<unsigned char*>(sa) + 2 * TC_TILE_BYTES);
+#pragma unroll
+          for (int j = 0; j < TC_TILE_BYTES / 16 / 128; ++j) {
+            const int i = t128 + 128 * j;
+            const float4 x = hi[i];
+            float4 l;
+            l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+            l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+            l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+            l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+            lo[i] = l;
+            if (B_MN && do_cs) {
+              cs[j >> 1].x += x.x; cs[j >> 1].y += x.y; cs[j >> 1].z += x.z; cs[j >> 1].w += x.w;
+            }
+          }
+        }
+        if (g >= 2) mbar_wait(empty((g - 2) % TCP_STAGES), (uint32_t)(((g - 2) / TCP_STAGES) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t ta = tmem + lane_base + TC_TMEM_A + (uint32_t)((g & 1) * 64);
+        tmem_st32(ta, xh);
+        tmem_st32(ta + 32, xl);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        fence_async_smem();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(conv(s));
+      }
+      // ---- epilogue, first half: TMEM -> staging; then the accumulators are free again -------------------
+      mbar_wait(acc_full, (uint32_t)(ti & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (ti > 0) mbar_wait(stage_free, (uint32_t)((ti - 1) & 1));  // the store warps are done with the previous tile
+      if (B_MN && do_cs) {
+        const int noff = ((((t128 & 7) >> 1) ^ ((t128 >> 3) & 3)) << 3) + ((t128 & 1) << 2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(scr + (t128 >> 3) * 128 + q * 32 + noff) = cs[q];
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+        uint32_t r[32], q[32], o[32];
+        const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+              "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]),
+              "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]),
+              "=r"(q[25]), "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+            : "r"(taddr + (uint32_t)(2 * TC_BN)));
+        if (nkb > 1) {
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]), "=r"(o[8]),
+                "=r"(o[9]), "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15]), "=r"(o[16]),
+                "=r"(o[17]), "=r"(o[18]), "=r"(o[19]), "=r"(o[20]), "=r"(o[21]), "=r"(o[22]), "=r"(o[23]), "=r"(o[24]),
+                "=r"(o[25]), "=r"(o[26]), "=r"(o[27]), "=r"(o[28]), "=r"(o[29]), "=r"(o[30]), "=r"(o[31])
+              : "r"(taddr + (uint32_t)TC_BN));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = 0u;
+        }
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        unsigned char* srow = staging + (size_t)(c0 >> 5) * TC_TILE_BYTES + (size_t)(wq * 32 + lane) * 128;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 v = make_float4((__uint_as_float(r[j]) + __uint_as_float(o[j])) + __uint_as_float(q[j]),
+                                       (__uint_as_float(r[j + 1]) + __uint_as_float(o[j + 1])) + __uint_as_float(q[j + 1]),
+                                       (__uint_as_float(r[j + 2]) + __uint_as_float(o[j + 2])) + __uint_as_float(q[j + 2]),
+                                       (__uint_as_float(r[j + 3]) + __uint_as_float(o[j + 3])) + __uint_as_float(q[j + 3]));
+          *reinterpret_cast<float4*>(srow + ((((j >> 2) ^ (lane & 7))) << 4)) = v;
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(acc_free);    // TMEM accumulators may be overwritten by the next tile
+      mbar_arrive(stage_full);  // (release: the staging writes above are visible to the store warps)
+    }
+  } else if (warp >= 8) {
+    // ---- epilogue, second half: staging -> bias / relu6 / mask -> global, overlapping the next tile's main loop ----
+    const int w8 = warp - 8, t8 = threadIdx.x - 256;
+    int ti = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+      int z, m0, n0, k_begin, nkb;
+      decode(t, z, m0, n0, k_begin, nkb);
+      mbar_wait(stage_full, (uint32_t)(ti & 1));
+      if (B_MN && p.colsum != nullptr && m0 == 0) {
+        float sum = 0.f;
+#pragma unroll
+        for (int gq = 0; gq < 16; ++gq) sum += scr[gq * 128 + t8];
+        if (n0 + t8 < p.N) p.colsum[(size_t)z * p.N + n0 + t8] = sum;
+      }
+      const int n = n0 + lane * 4;
+      const bool n_ok = n < p.N;  // N % 4 == 0
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n_ok && (p.epi == TC_EPI_BIAS || p.epi == TC_EPI_BIAS_RELU6)) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+      const unsigned char* sbuf = staging + (size_t)(lane >> 3) * TC_TILE_BYTES;
+      const int rows_here = min(TC_BM, p.M - m0);
+      float* crow = p.C + ((size_t)z * p.M + m0) * p.ldc + n;
+      if (n_ok) {
+#pragma unroll 1
+        for (int r0 = w8; r0 < rows_here; r0 += 32) {
+          float4 h[8];
+          if (p.epi == TC_EPI_MASK6) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int row = r0 + 4 * u;
+              h[u] = row < rows_here ? __ldg(reinterpret_cast<const float4*>(p.Hm + (size_t)(m0 + row) * p.ldh + n))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int row = r0 + 4 * u;
+            if (row >= rows_here) break;
+            float4 v = *reinterpret_cast<const float4*>(sbuf + (size_t)row * 128 + ((((lane & 7) ^ (row & 7))) << 4));
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            if (p.epi == TC_EPI_BIAS_RELU6) {
+              v.x = fminf(fmaxf(v.x, 0.f), 6.f); v.y = fminf(fmaxf(v.y, 0.f), 6.f);
+              v.z = fminf(fmaxf(v.z, 0.f), 6.f); v.w = fminf(fmaxf(v.w, 0.f), 6.f);
+            }
+            if (p.epi == TC_EPI_MASK6) {
+              v.x = (h[u].x > 0.f && h[u].x < 6.f) ? v.x : 0.f; v.y = (h[u].y > 0.f && h[u].y < 6.f) ? v.y : 0.f;
+              v.z = (h[u].z > 0.f && h[u].z < 6.f) ? v.z : 0.f; v.w = (h[u].w > 0.f && h[u].w < 6.f) ? v.w : 0.f;
+            }
+            *reinterpret_cast<float4*>(crow + (size_t)row * p.ldc) = v;
+          }
+        }
+      }
+      mbar_arrive(stage_free);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -444,6 +766,29 @@ static int tc_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUt
     PFPN_CUDA_OK(cudaFuncSetAttribute((const void*)tc_gemm_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       TC_SMEM_BYTES));
     attr_dev = dev;
+  }
+  static const int persist = []() {
+    const char* e = getenv("PFPN_TC_PERSISTENT");
+    return e ? atoi(e) : 1;
+  }();
+  const int num_tiles = (int)(grid.x * grid.y * grid.z);
+  // Measured at M = 65536 (ms, persistent vs one-tile-per-CTA): forward K=200 0.180 vs 0.235, N=1260 K=512 0.415 vs 0.464,
+  // input gradient N=1024 K=512 0.356 vs 0.425, K=1024 0.326 vs 0.325; the split-K weight gradients (MN-major A) are 3-6 %
+  // slower persistent (0.443 vs 0.427), so they keep the one-tile form.
+  if (persist && num_tiles > 1 && !A_MN) {
+    static int attr_dev_p = -1;
+    static int sms = 0;
+    if (dev != attr_dev_p) {
+      PFPN_CUDA_OK(cudaFuncSetAttribute((const void*)tc_gemm_persist_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        TCP_SMEM_BYTES));
+      PFPN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      attr_dev_p = dev;
+    }
+    const int ctas = num_tiles < sms ? num_tiles : sms;
+    tc_gemm_persist_kernel<A_MN, B_MN><<<ctas, TCP_THREADS, TCP_SMEM_BYTES, st>>>(mapA, mapB, mapBlo, p, (int)grid.y, (int)grid.x,
+                                                                                  num_tiles);
+    PFPN_CUDA_OK(cudaGetLastError());
+    return PFPN_OK;
   }
   tc_gemm_kernel<A_MN, B_MN><<<grid, 256, TC_SMEM_BYTES, st>>>(mapA, mapB, mapBlo, p);
   PFPN_CUDA_OK(cudaGetLastError());
