@@ -442,18 +442,26 @@ def main():
             opt.apply_gradients(net)
         for _ in range(3):
             upd_eager()
-        um_eager = time_updates(upd_eager, args.dppo_steps)
-        # the same update captured once in a CUDA graph (device-resident step counters) and replayed
-        gu = GraphedUpdate(net, opt, Bs, warmup=0)
-        gu._set(st_, ac_, v_, lpo_, adv_)
-        gu.run()  # capture + first replay
-        for _ in range(2):
-            gu.run()
-        um = time_updates(gu.run, args.dppo_steps)
-        dppo = {"workload": f"DPPO minibatch update, B_total={B_PER_GPU} sharded over {world} GPU(s): 197-1024-512 actor+critic trunk (tcgen05 3xTF32 GEMMs, critic on a parallel graph branch), PFPN head, local clip -> staged bucket -> rank-ordered mean over NVLink peer memory -> Adam: 3 launches; whole update replayed as ONE CUDA graph",
+        # the shard size decides the default mode (learner.GraphedUpdate): small shards replay ONE captured CUDA graph,
+        # large ones stay eager.  The default mode is timed FIRST (the second measurement of a back-to-back pair runs
+        # ~10 % slower at 65536 states: the part settles at its power cap), the other one is reported beside it.
+        graph_max = int(os.environ.get("PFPN_GRAPH_MAX_BATCH", "24576"))
+        um_graph = None
+        if Bs <= graph_max:
+            gu = GraphedUpdate(net, opt, Bs, warmup=0)
+            gu._set(st_, ac_, v_, lpo_, adv_)
+            for _ in range(3):
+                gu.run()  # capture + first replays
+            um_graph = time_updates(gu.run, args.dppo_steps)
+            um_eager = time_updates(upd_eager, args.dppo_steps)
+            um = um_graph
+        else:
+            um_eager = time_updates(upd_eager, args.dppo_steps)
+            um = um_eager
+        dppo = {"workload": f"DPPO minibatch update, B_total={B_PER_GPU} sharded over {world} GPU(s): 197-1024-512 actor+critic trunk (tcgen05 3xTF32 GEMMs, critic on a parallel graph branch), PFPN head, local clip -> staged bucket -> rank-ordered mean over NVLink peer memory -> Adam: 3 launches" + ("; whole update replayed as ONE CUDA graph" if um_graph is not None else "; eager multi-stream issue (shard above the graph-replay threshold)"),
                 "ms_per_update": um, "samples_per_s": B_PER_GPU / (um * 1e-3), "scaling": "strong",
                 "trunk_tflops": 12.6e6 * B_PER_GPU / (um * 1e-3) / 1e12,
-                "ms_per_update_eager": um_eager, "optimizer_chain_launches": getattr(opt, "launches_last_step", None),
+                "ms_per_update_eager": um_eager, "ms_per_update_graph": um_graph, "optimizer_chain_launches": getattr(opt, "launches_last_step", None),
                 "exchange": opt._mode + (f", {'two' if world >= int(os.environ.get('PFPN_PEER_TWO_PHASE_MIN', '6')) else 'one'}-phase peer kernel" if world > 1 else "")}
         if world > 1:
             # one more update from IDENTICAL state through each exchange implementation: the round-1 chain with an NCCL
