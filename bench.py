@@ -314,11 +314,11 @@ def main():
         if use_peer:
             # the path's only exchange: [2, A, P] particle gradients.  K1's finalize kernel PUSHES them into
             # every rank's gather buffer and raises the flags; the consumer sums its N local rows in rank order.
-            # The consumer runs on a second stream, so the next step's head kernel overlaps the wait for the slowest rank;
-            # `gather.wait()` is what a reader of the sum (the optimizer) calls.
-            gather.begin_step(stream)
+            # The sum is consumed ONE exchange late (it feeds the optimizer, not the next head launch): by then every
+            # rank's flags arrived a step ago, so no step waits for the slowest rank; everything stays on one stream.
             _cabi.check(_cabi.pfpn_head_logprob_push(a, ws.data_ptr(), ws.numel(), gather.push_args(), stream.cuda_stream))
-            gather.reduce_async(flat_small.view(-1), 1.0, stream)
+            if gather.pending > 1:
+                gather.reduce(flat_small.view(-1), 1.0, stream.cuda_stream)
         else:
             _cabi.check(_cabi.pfpn_head_logprob(a, ws.data_ptr(), ws.numel(), stream.cuda_stream))
             if world > 1:
@@ -327,9 +327,12 @@ def main():
                 dist.all_reduce(flat_small)
     launches_per_step = 3 + (1 if use_peer else 0)
 
+    def drain():
+        while use_peer and gather.pending > 0:  # the last exchange(s): consumed inside the timed region
+            gather.reduce(flat_small.view(-1), 1.0, stream.cuda_stream)
+
     def barrier():
-        if use_peer:
-            gather.wait(stream)  # the timed region ends when the last exchange has been consumed
+        drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -342,8 +345,8 @@ def main():
     evs[0].record(stream)
     for i in range(args.steps):
         step()
-        if use_peer and i == args.steps - 1:
-            gather.wait(stream)  # (inside the timed region: the last exchange is consumed before the closing event)
+        if i == args.steps - 1:
+            drain()  # (inside the timed region: every exchange is consumed before the closing event)
         evs[i + 1].record(stream)
     barrier()
     per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
@@ -356,11 +359,10 @@ def main():
         xcheck = {}
         step()
         torch.cuda.synchronize()
-        if use_peer:
-            gather.wait(stream)
-            torch.cuda.synchronize()
+        drain()
+        torch.cuda.synchronize()
         mine = torch.stack([dloc, dlogstd]).clone() if not use_peer else \
-            gather.gather[gather.slot_of(gather.calls), rank].view(2, A, P).clone()
+            gather.gather[gather.slot_of(gather.pushed), rank].view(2, A, P).clone()
         allc = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allc, mine)
         ordered = allc[0].clone()

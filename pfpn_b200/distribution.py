@@ -35,6 +35,32 @@ class _LogProbFn(torch.autograd.Function):
                 out.get("dvalue") if ctx.needs_input_grad[3] else None, None)
 
 
+class _LogProbEntropyFn(torch.autograd.Function):
+    """log_prob [B] AND the categorical entropy [B, A] from ONE K1 forward; their gradients arrive together in ONE K1
+    backward (dL/dlog_prob + dL/dentropy).  `MixtureGaussianDistribution.log_prob` goes through this node and keeps the
+    entropy for a later `.entropy()` call on the same object, so a loss that uses both (A3C / IMPALA settings:
+    policy loss + entropy_beta * entropy) costs two passes over [B,A,P] instead of four."""
+
+    @staticmethod
+    def forward(ctx, logits, loc, logstd, value, tanh):
+        out = _head.head_call(_cabi.HEAD_FWD, logits, loc, logstd, value, tanh=tanh, want_ent_ba=True)
+        ctx.save_for_backward(logits, loc, logstd, value)
+        ctx.tanh = tanh
+        return out["lp"], out["ent_ba"]
+
+    @staticmethod
+    def backward(ctx, g_lp, g_ent_ba):
+        logits, loc, logstd, value = ctx.saved_tensors
+        B = logits.shape[0]
+        if g_lp is None:
+            g_lp = torch.zeros(B, dtype=torch.float32, device=logits.device)
+        out = _head.head_call(_cabi.HEAD_GRAD, logits, loc, logstd, value, tanh=ctx.tanh, g_lp=g_lp.contiguous(),
+                              g_ent_ba=None if g_ent_ba is None else g_ent_ba.contiguous(),
+                              want_dvalue=ctx.needs_input_grad[3])
+        return (out["dlogits"], out["dloc"], out["dlogstd"],
+                out.get("dvalue") if ctx.needs_input_grad[3] else None, None)
+
+
 class _EntropyFn(torch.autograd.Function):
     """Categorical entropy per action dim [B, A] (utils.py:146-151)."""
 
@@ -118,8 +144,9 @@ class MixtureGaussianDistribution:
                 value_before_tanh = torch.atanh(value)
         else:
             value_before_tanh = value
-        return _LogProbFn.apply(self.logits, self.loc, self.logstd, value_before_tanh,
-                                self.normalize_output)
+        lp, ent_ba = _LogProbEntropyFn.apply(self.logits, self.loc, self.logstd, value_before_tanh, self.normalize_output)
+        self._ent_ba = ent_ba  # same K1 forward; `.entropy()` on this object reuses it (one joint backward)
+        return lp
 
     # utils.py:103-106
     def prob(self, value, name="prob"):
@@ -127,6 +154,9 @@ class MixtureGaussianDistribution:
 
     # utils.py:146-151
     def entropy(self, name="entropy"):
+        ent = getattr(self, "_ent_ba", None)
+        if ent is not None:
+            return ent
         return _EntropyFn.apply(self.logits, self.loc, self.logstd)
 
     # utils.py:153-200

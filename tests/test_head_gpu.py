@@ -217,3 +217,26 @@ def test_push_form_single_rank_equals_plain_call(cuda_dev):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_autograd_wrapper_entropy_before_log_prob_and_entropy_only(cuda_dev):
+    """`.entropy()` before `.log_prob()` takes its own node; after it the two share ONE forward and ONE backward."""
+    B, A, P = 130, 36, 35
+    d = make(B, A, P, seed=6)
+    w = torch.randn(B, generator=torch.Generator().manual_seed(3))
+    ref = oh.head_fwd_bwd(d["logits"], d["loc"], d["logstd"], d["value"], w, torch.full((B,), 0.02))
+    for order in ("entropy_first", "entropy_only"):
+        lg = d["logits"].to(cuda_dev).requires_grad_(True)
+        loc = d["loc"].to(cuda_dev).requires_grad_(True)
+        ls = d["logstd"].to(cuda_dev).requires_grad_(True)
+        dist = MixtureGaussianDistribution(lg, loc, torch.exp(ls), False, logstd=ls)
+        ent = dist.entropy()
+        assert rel(ent, ref["ent"]) < TOL
+        if order == "entropy_first":
+            lp = dist.log_prob(d["value"].to(cuda_dev))
+            ((lp * w.to(cuda_dev)).sum() + 0.02 * ent.sum()).backward()
+            assert rel(lg.grad, ref["dlogits"]) < TOL and rel(loc.grad, ref["dloc"]) < TOL and rel(ls.grad, ref["dlogstd"]) < TOL
+        else:
+            (0.02 * ent.sum()).backward()
+            only = oh.head_fwd_bwd(d["logits"], d["loc"], d["logstd"], d["value"], torch.zeros(B), torch.full((B,), 0.02))
+            assert rel(lg.grad, only["dlogits"]) < TOL

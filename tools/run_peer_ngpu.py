@@ -105,16 +105,18 @@ for it in range(5):
     for r in range(1, world):
         ordered += allc[r]
     ok_push = ok_push and bool(torch.equal(outg, ordered))  # bit-equal to the rank-ordered sum, on every rank
-# the same with the consumer on a second stream (reduce_async): up to two exchanges in flight, 4 rotating slots
+# the same consumed ONE exchange late (lag 1: produce v+1, then consume v), 4 rotating slots
 ok_async, outs = True, [torch.empty(n, device=dev) for _ in range(8)]
-exp = []
+exp, nxt = [], 0
 for it in range(8):
     glp2 = glp * (1.0 + 0.05 * it)
-    pg.begin_step()
     o2 = head.head_call(_cabi.HEAD_GRAD, lg, locp, lsp, val, g_lp=glp2, push=pg)
-    pg.reduce_async(outs[it], 1.0)
     exp.append(torch.cat([o2["dloc"].reshape(-1), o2["dlogstd"].reshape(-1)]))
-pg.wait(); torch.cuda.synchronize()
+    if pg.pending > 1:
+        pg.reduce(outs[nxt], 1.0, _stream_ptr()); nxt += 1
+while pg.pending > 0:
+    pg.reduce(outs[nxt], 1.0, _stream_ptr()); nxt += 1
+torch.cuda.synchronize()
 for it in range(8):
     allc = [torch.empty_like(exp[it]) for _ in range(world)]
     dist.all_gather(allc, exp[it])
