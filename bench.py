@@ -309,19 +309,22 @@ def main():
         except (RuntimeError, ValueError):  # collective outcome: every rank falls back together
             use_peer = False
 
-    def step():
+    def step(mode="full"):
+        """mode (N > 1, diagnostic breakdown only): "none" = no exchange at all, "push" = K1 pushes but nobody sums."""
         _cabi.check(_cabi.pfpn_adv_stats(adv.data_ptr(), B, stats.data_ptr(), stream.cuda_stream))
-        if use_peer:
+        if use_peer and mode != "none":
             # the path's only exchange: [2, A, P] particle gradients (SURVEY 8e).  K1's finalize kernel PUSHES them into
             # every rank's gather buffer and raises the flags; the consumer sums its N local rows in rank order.
             # The sum is consumed ONE exchange late (it feeds the optimizer, not the next head launch): by then every
             # rank's flags arrived a step ago, so no step waits for the slowest rank; everything stays on one stream.
             _cabi.check(_cabi.pfpn_head_logprob_push(a, ws.data_ptr(), ws.numel(), gather.push_args(), stream.cuda_stream))
-            if gather.pending > 1:
+            if mode == "push":
+                gather.consumed = gather.pushed  # (diagnostic: the rows are never read)
+            elif gather.pending > 1:
                 gather.reduce(flat_small.view(-1), 1.0, stream.cuda_stream)
         else:
             _cabi.check(_cabi.pfpn_head_logprob(a, ws.data_ptr(), ws.numel(), stream.cuda_stream))
-            if world > 1:
+            if world > 1 and mode != "none":
                 flat_small[0].copy_(dloc)
                 flat_small[1].copy_(dlogstd)
                 dist.all_reduce(flat_small)
@@ -350,7 +353,28 @@ def main():
         evs[i + 1].record(stream)
     barrier()
     per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
-    total_ms = maxr(evs[0].elapsed_time(evs[-1]))
+    local_ms = evs[0].elapsed_time(evs[-1])
+    total_ms = maxr(local_ms)
+    rank_ms, breakdown = None, None
+    if world > 1:
+        # where the weak-scaling loss comes from: every rank's own step time (the line reports the MAX), and the same loop
+        # without the exchange / with the push only (diagnostic, outside the timed region above)
+        t_all = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(t_all, torch.tensor([local_ms / args.steps], device=dev, dtype=torch.float64))
+        rank_ms = [round(float(t.item()), 5) for t in t_all]
+        breakdown = {}
+        for mode in ("none", "push"):
+            for _ in range(5):
+                step(mode)
+            barrier()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record(stream)
+            for _ in range(args.steps):
+                step(mode)
+            b1.record(stream)
+            barrier()
+            breakdown[f"ms_per_step_{mode}"] = round(maxr(b0.elapsed_time(b1)) / args.steps, 5)
+        breakdown["note"] = "max over ranks; none = K1 alone on every rank (GPU-to-GPU spread only), push = + the peer stores and flags"
     value_rate = world * B * args.steps / (total_ms * 1e-3)
 
     # ---- N > 1: the exchange against NCCL, in the driver's record (outside every timed region) -------------------
@@ -527,7 +551,7 @@ def main():
             "metric": METRIC, "value": value_rate, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": cfg, "step_ms_median": per[len(per) // 2],
+            "config": cfg, "step_ms_median": per[len(per) // 2], "rank_ms_per_step": rank_ms, "exchange_breakdown": breakdown,
             "clocks": clocks,
             "e2e": {"value": e2e_rate, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
                     "d2h_bytes_per_step": pipe.d2h_bytes, "steps": args.e2e_steps,

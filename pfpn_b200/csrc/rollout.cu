@@ -32,6 +32,7 @@ struct RolloutK {
   pfpn_rollout_args a;
   float* part;  // [grid][2][A*P]: per-CTA max / sum of the probabilities
   int num_tiles;
+  uint32_t wait_ns;  // producer back-off while the compute threads work on a tile
 };
 
 // The literal fp64 algorithm for one row (fallback; also the semantic definition), executed by a whole WARP for one row
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(SLOTS * 72 + 32, 2) rollout_kernel(const Rollo
     for (int it = 0; it < my_tiles; ++it) {
       const int st = it % NSTAGE;
       const int tile = first_tile + it * tile_step;
-      mbar_wait(smem_u32(&done_bar[st]), (uint32_t)((it / NSTAGE) & 1));  // every compute thread is done with this stage
+      mbar_wait_sleep(smem_u32(&done_bar[st]), (uint32_t)((it / NSTAGE) & 1), kp.wait_ns);  // every compute thread is done with this stage
       if (lane < SLOTS) {
         const int b = tile * SLOTS + lane;
         if (b < B) {
@@ -390,6 +391,7 @@ extern "C" int pfpn_head_rollout(const pfpn_rollout_args* args, void* workspace,
   kp.a = a;
   kp.part = stats ? reinterpret_cast<float*>(workspace) : nullptr;
   kp.num_tiles = (a.B + SLOTS - 1) / SLOTS;
+  kp.wait_ns = pfpn_wait_ns(256u);
   int grid = 2 * sms;
   if (grid > kp.num_tiles) grid = kp.num_tiles;
   if (grid > kRoMaxCtas) grid = kRoMaxCtas;

@@ -60,6 +60,7 @@ struct SacHeadK {
   pfpn_sac_head_args a;
   float* part;  // [grid][2 * A * P]
   int num_tiles;
+  uint32_t wait_ns;  // producer back-off while the compute threads work on a tile
   uint32_t rk[2 * kSacRounds];  // Philox round keys, precomputed on the host: they reach the XORs as constant-bank operands
 };
 // Philox4x32-7 with the key schedule taken from the kernel parameters (identical output to PhiloxR<7>(seed))
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
     for (int it = 0; it < my_tiles; ++it) {
       const int st = it % NSTAGE;
       const int tile = first_tile + it * tile_step;
-      mbar_wait(smem_u32(&done_bar[st]), (uint32_t)((it / NSTAGE) & 1));  // every compute thread finished (and fenced) this tile
+      mbar_wait_sleep(smem_u32(&done_bar[st]), (uint32_t)((it / NSTAGE) & 1), kp.wait_ns);  // every compute thread finished (and fenced) this tile
       if (lane < SLOTS) {  // log_prob of the state = sum over a of the per-row log p, fixed order
         const int b = tile * SLOTS + lane;
         if (b < B) {
@@ -476,6 +477,7 @@ extern "C" int pfpn_sac_head_fwd_bwd(const pfpn_sac_head_args* args, void* works
   kp.a = a;
   kp.part = reinterpret_cast<float*>(workspace);
   kp.num_tiles = (a.B + kSacSlots - 1) / kSacSlots;
+  kp.wait_ns = pfpn_wait_ns(256u);
   {
     uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     for (int r = 0; r < kSacRounds; ++r) {

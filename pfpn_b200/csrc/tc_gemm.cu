@@ -44,6 +44,7 @@ struct TcParams {
   int M, N, K, ldc, ldh, epi;
   int k_chunk;  // split-K: K range per blockIdx.z (multiple of TC_BK); C then is [splits][M][ldc]
   float* colsum;  // weight gradient only (B MN-major): [splits][N] column sums of the B operand (= bias gradient)
+  uint32_t wait_ns;  // persistent kernel: back-off of the TMA and store warps' long waits
   int b_lo_tma;   // the B operand's low part (x - tf32(x)) exists in global memory (weights: split once per optimizer
                   // step) and arrives by TMA through mapBlo; the splitter then only converts the A operand
 };
@@ -485,7 +486,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persist_kernel(const _
         decode(t, z, m0, n0, k_begin, nkb);
         for (int kb = 0; kb < nkb; ++kb, ++g) {
           const int s = g % TCP_STAGES;
-          mbar_wait(empty(s), (uint32_t)(((g / TCP_STAGES) & 1) ^ 1));
+          mbar_wait_sleep(empty(s), (uint32_t)(((g / TCP_STAGES) & 1) ^ 1), p.wait_ns);
           mbar_expect_tx(full(s), (p.b_lo_tma ? 3 : 2) * TC_TILE_BYTES);
           const uint32_t a_dst = base + s * TC_STAGE_BYTES, b_dst = a_dst + TC_TILE_BYTES, l_dst = b_dst + TC_TILE_BYTES;
           const int k0 = k_begin + kb * TC_BK;
@@ -670,7 +671,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persist_kernel(const _
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
       int z, m0, n0, k_begin, nkb;
       decode(t, z, m0, n0, k_begin, nkb);
-      mbar_wait(stage_full, (uint32_t)(ti & 1));
+      mbar_wait_sleep(stage_full, (uint32_t)(ti & 1), p.wait_ns);
       if (B_MN && p.colsum != nullptr && m0 == 0) {
         float sum = 0.f;
 #pragma unroll
@@ -811,7 +812,7 @@ static int tc_gemm_common(const float* A, int lda, const float* Bm, const float*
   if (rc != PFPN_OK) return rc;
   rc = make_map(&mapBlo, Blo ? Blo : Bm, N, K, ldb, TC_BN, b_mn);
   if (rc != PFPN_OK) return rc;
-  TcParams p{Cout, bias, Hm, M, N, K, ldc, ldh, epi, (K + TC_BK - 1) / TC_BK * TC_BK, nullptr, Blo ? 1 : 0};
+  TcParams p{Cout, bias, Hm, M, N, K, ldc, ldh, epi, (K + TC_BK - 1) / TC_BK * TC_BK, nullptr, pfpn_wait_ns(64u), Blo ? 1 : 0};
   dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
   return b_mn ? tc_launch<false, true>(mapA, mapB, mapBlo, p, grid, st) : tc_launch<false, false>(mapA, mapB, mapBlo, p, grid, st);
 }
@@ -932,7 +933,7 @@ extern "C" int pfpn_tc_linear_bwd_weight(const float* X, int32_t ldx, const floa
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   float* out = splits > 1 ? reinterpret_cast<float*>(workspace) : dW;
   float* cs_part = db ? reinterpret_cast<float*>(workspace) + (size_t)splits * K * N : nullptr;
-  TcParams p{out, nullptr, nullptr, K, N, M, N, 0, TC_EPI_NONE, chunk, cs_part, 0};
+  TcParams p{out, nullptr, nullptr, K, N, M, N, 0, TC_EPI_NONE, chunk, cs_part, pfpn_wait_ns(64u), 0};
   dim3 grid((N + TC_BN - 1) / TC_BN, (K + TC_BM - 1) / TC_BM, splits);
   rc = tc_launch<true, true>(mapA, mapB, mapB, p, grid, st);
   if (rc != PFPN_OK) return rc;

@@ -14,6 +14,7 @@ try:
     print({k:d[k] for k in ('value','ms_per_step','n_gpus')}, d['roofline']['frac'])
     print('xcheck', json.dumps(d.get('xcheck'), indent=1))
     print('dppo', d['dppo_update']['ms_per_update'], d['dppo_update']['ms_per_update_eager'], d['dppo_update']['exchange'])
+    print('rank_ms', d.get('rank_ms_per_step'), d.get('exchange_breakdown'))
     print('e2e', d['e2e']['value'])
     print('c5', d['extra']['c5_sac_head'].get('fused_Mstates_s_all_gpus'), d['extra']['c5_sac_head'].get('fused_frac_of_8d_roofline'))
 except Exception as e:
