@@ -314,21 +314,22 @@ def main():
         _cabi.check(_cabi.pfpn_adv_stats(adv.data_ptr(), B, stats.data_ptr(), stream.cuda_stream))
         if use_peer and mode != "none":
             # the path's only exchange: [2, A, P] particle gradients.  K1's finalize kernel PUSHES them into
-            # every rank's gather buffer and raises the flags; the consumer sums its N local rows in rank order.
-            # The sum is consumed ONE exchange late (it feeds the optimizer, not the next head launch): by then every
-            # rank's flags arrived a step ago, so no step waits for the slowest rank; everything stays on one stream.
-            _cabi.check(_cabi.pfpn_head_logprob_push(a, ws.data_ptr(), ws.numel(), gather.push_args(), stream.cuda_stream))
+            # every rank's gather buffer as 8-byte {value, sequence} packets (no fence / flag round trip behind the data).
+            # The sum is produced ONE exchange late (it feeds the optimizer, not the next head launch) by the finalize
+            # kernel of the NEXT step: the packets arrived a step ago, nothing waits, no kernel of its own.
             if mode == "push":
+                pa = gather.push_args()
                 gather.consumed = gather.pushed  # (diagnostic: the rows are never read)
-            elif gather.pending > 1:
-                gather.reduce(flat_small.view(-1), 1.0, stream.cuda_stream)
+            else:
+                pa = gather.push_args(consume_into=flat_small.view(-1))  # the same launch sums the PREVIOUS exchange
+            _cabi.check(_cabi.pfpn_head_logprob_push(a, ws.data_ptr(), ws.numel(), pa, stream.cuda_stream))
         else:
             _cabi.check(_cabi.pfpn_head_logprob(a, ws.data_ptr(), ws.numel(), stream.cuda_stream))
             if world > 1 and mode != "none":
                 flat_small[0].copy_(dloc)
                 flat_small[1].copy_(dlogstd)
                 dist.all_reduce(flat_small)
-    launches_per_step = 3 + (1 if use_peer else 0)
+    launches_per_step = 3  # adv_stats, K1, K1 finalize (+ push + the previous exchange's sum at N > 1)
 
     def drain():
         while use_peer and gather.pending > 0:  # the last exchange(s): consumed inside the timed region
@@ -385,8 +386,7 @@ def main():
         torch.cuda.synchronize()
         drain()
         torch.cuda.synchronize()
-        mine = torch.stack([dloc, dlogstd]).clone() if not use_peer else \
-            gather.gather[gather.slot_of(gather.pushed), rank].view(2, A, P).clone()
+        mine = torch.stack([dloc, dlogstd]).clone() if not use_peer else gather.row(gather.pushed, rank).reshape(2, A, P).clone()
         allc = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allc, mine)
         ordered = allc[0].clone()
@@ -394,7 +394,7 @@ def main():
             ordered += allc[r]  # rank-ordered fp32 sum: what the kernel promises, bit for bit
         nccl = mine.clone()
         dist.all_reduce(nccl)
-        xcheck["exchange"] = "push (K1 finalize -> peers' gather rows) + pfpn_peer_gather_sum" if use_peer else "NCCL all_reduce"
+        xcheck["exchange"] = "push (K1 finalize -> peers' gather rows, 8-byte {value, sequence} packets), summed by the next finalize / pfpn_peer_gather_sum_packets" if use_peer else "NCCL all_reduce"
         xcheck["peer_sum_bit_equal_rank_ordered"] = bool(torch.equal(flat_small, ordered)) if use_peer else None
         xcheck["peer_sum_max_abs_vs_nccl"] = float((flat_small - nccl).abs().max())
         xcheck["peer_sum_ref_max_abs"] = float(nccl.abs().max())

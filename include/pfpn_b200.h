@@ -97,14 +97,31 @@ int pfpn_head_logprob(const pfpn_head_args* args, void* workspace, size_t worksp
  * waits for the N flags and sums the N LOCAL rows in rank order (identical on every rank).  args->dloc / dlogstd may be
  * NULL here.  Replaces (semantics) the accumulator sum of models/sync_model.py:92-96 for `samples` / `samples_std`. */
 typedef struct pfpn_head_push {
-  float* out[8];     /* out[p]: rank p's gather row for THIS rank and this call's parity, 2*A*P floats (peer-mapped)   */
-  int32_t* flags[8]; /* flags[p]: rank p's flag word for THIS rank (peer-mapped int32, zero-initialised, monotonic)    */
-  int32_t* ticket;   /* local device int32, zero-initialised (CTA-arrival counter, self-resetting)                     */
-  int32_t nranks;    /* 1..8                                                                                           */
-  int32_t value;     /* call counter, +1 per call                                                                      */
+  float* out[8];     /* out[p]: rank p's gather row for THIS rank and this call's slot (peer-mapped): 2*A*P floats         */
+                     /*         (protocol 0) or 2*A*P 8-byte packets (protocol 1)                                        */
+  int32_t* flags[8]; /* protocol 0: flags[p] = rank p's flag word for THIS rank (peer-mapped, zero-initialised, monotonic)*/
+  int32_t* ticket;   /* protocol 0: local device int32, zero-initialised (CTA-arrival counter, self-resetting)            */
+  int32_t nranks;    /* 1..8                                                                                              */
+  int32_t value;     /* exchange counter, +1 per call (>= 1)                                                              */
+  /* protocol 1 = PACKETS: every element travels as one 8-byte store {float value, int32 sequence = `value`}; an aligned
+   * 8-byte store is single-copy atomic, so the receiver validates each element by its own sequence word -- no fence, no
+   * ticket, no flag round trip behind the data (one NVLink write latency instead of three).  The same launch can also
+   * CONSUME an earlier exchange: the thread that owns element i sums packet i of the N local rows of exchange
+   * `consume_value` in rank order (spinning on the sequence words; with consume_value = value - 1 they arrived a step
+   * ago) and writes consume_out[i] -- the exchange then costs no kernel of its own.  Gather memory must start zeroed.   */
+  int32_t protocol;
+  int32_t consume_value;     /* protocol 1: 0 = consume nothing in this launch                                            */
+  const void* consume_rows;  /* protocol 1: this rank's LOCAL rows of exchange consume_value, [nranks][2*A*P] packets     */
+  float* consume_out;        /* protocol 1: [2*A*P] = consume_scale * sum over ranks                                      */
+  float consume_scale;
+  int32_t reserved;
 } pfpn_head_push;
 int pfpn_head_logprob_push(const pfpn_head_args* args, void* workspace, size_t workspace_bytes,
                            const pfpn_head_push* push, pfpn_stream_t stream);
+/* Stand-alone consumer of a protocol-1 exchange (the last one of a run, or a caller that needs the sum at once):
+ * out[i] = scale * sum over ranks (rank order) of packet i of rows[r], waiting until every sequence word == value. */
+int pfpn_peer_gather_sum_packets(const void* rows, int32_t nranks, int32_t value, size_t n, float* out, float scale,
+                                 pfpn_stream_t stream);
 /* out[n] = scale * sum_{r < nranks} gather[r*n + i] once flags[r] >= value for every r (acquire loads, system scope);
  * `gather` / `flags` are THIS rank's own buffers (the rows its peers pushed into).  n % 4 == 0. */
 int pfpn_peer_gather_sum(const float* gather, const int32_t* flags, int32_t nranks, int32_t value, size_t n, float* out,

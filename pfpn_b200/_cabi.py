@@ -50,7 +50,9 @@ class HeadArgs(C.Structure):
 class HeadPush(C.Structure):
     """Mirror of ``pfpn_head_push``."""
     _fields_ = [("out", C.c_void_p * 8), ("flags", C.c_void_p * 8), ("ticket", C.c_void_p),
-                ("nranks", C.c_int32), ("value", C.c_int32)]
+                ("nranks", C.c_int32), ("value", C.c_int32),
+                ("protocol", C.c_int32), ("consume_value", C.c_int32), ("consume_rows", C.c_void_p),
+                ("consume_out", C.c_void_p), ("consume_scale", C.c_float), ("reserved", C.c_int32)]
 
 
 class RolloutArgs(C.Structure):
@@ -222,6 +224,7 @@ pfpn_peer_allreduce_sum = _sig("pfpn_peer_allreduce_sum", C.c_int, [_vp, _vp, _i
 pfpn_head_logprob_push = _sig("pfpn_head_logprob_push", C.c_int,
                               [C.POINTER(HeadArgs), C.c_void_p, C.c_size_t, C.POINTER(HeadPush), C.c_void_p])
 pfpn_peer_gather_sum = _sig("pfpn_peer_gather_sum", C.c_int, [_vp, _vp, _i32, _i32, C.c_size_t, _vp, _f, _vp])
+pfpn_peer_gather_sum_packets = _sig("pfpn_peer_gather_sum_packets", C.c_int, [_vp, _i32, _i32, C.c_size_t, _vp, _f, _vp])
 pfpn_sync_step_scratch_bytes = _sig("pfpn_sync_step_scratch_bytes", C.c_int, [C.POINTER(C.c_size_t)])
 pfpn_sync_step = _sig("pfpn_sync_step", C.c_int, [C.POINTER(SyncArgs), C.c_void_p])
 pfpn_peer_alloc = _sig("pfpn_peer_alloc", C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p])

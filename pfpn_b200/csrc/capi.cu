@@ -26,5 +26,7 @@ static_assert(sizeof(pfpn_sample_args) == 88, "pfpn_sample_args layout changed: 
 static_assert(sizeof(pfpn_rsample_args) == 136, "pfpn_rsample_args layout changed: update _cabi.RSampleArgs");
 static_assert(sizeof(pfpn_resample_args) == 200, "pfpn_resample_args layout changed: update _cabi.ResampleArgs");
 static_assert(offsetof(pfpn_resample_args, seed) == 160 && offsetof(pfpn_resample_args, threshold) == 176, "layout");
-static_assert(sizeof(pfpn_head_push) == 144 && offsetof(pfpn_head_push, ticket) == 128 && offsetof(pfpn_head_push, value) == 140, "pfpn_head_push layout changed: update _cabi.HeadPush");
+static_assert(sizeof(pfpn_head_push) == 176 && offsetof(pfpn_head_push, ticket) == 128 && offsetof(pfpn_head_push, value) == 140 &&
+                  offsetof(pfpn_head_push, consume_rows) == 152 && offsetof(pfpn_head_push, consume_scale) == 168,
+              "pfpn_head_push layout changed: update _cabi.HeadPush");
 static_assert(sizeof(pfpn_sync_args) == 208 && offsetof(pfpn_sync_args, counters) == 128 && offsetof(pfpn_sync_args, stage) == 160 && offsetof(pfpn_sync_args, rank) == 184, "pfpn_sync_args layout changed: update _cabi.SyncArgs");

@@ -199,9 +199,51 @@ __global__ void __launch_bounds__(64) peer_gather_sum_kernel(const float* __rest
   }
 }
 
+// Consumer of a packet exchange (pfpn_head_push protocol 1): element i of every row carries its own sequence word.
+__global__ void __launch_bounds__(64) peer_gather_sum_packets_kernel(const uint2* __restrict__ rows, int nranks, int value, size_t n,
+                                                                      float* __restrict__ out, float scale) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // (orders the previous consumer of `out`)
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint2 pk[kMaxPeers];
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (r < nranks) asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(pk[r].x), "=r"(pk[r].y) : "l"(rows + r * n + i) : "memory");
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) {
+      if (r < nranks) {
+        while ((int)pk[r].y != value)
+          asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(pk[r].x), "=r"(pk[r].y) : "l"(rows + r * n + i) : "memory");
+        s += __uint_as_float(pk[r].x);  // fixed order: identical result on every rank
+      }
+    }
+    out[i] = s * scale;
+  }
+}
+
 }  // namespace pfpn
 
 using namespace pfpn;
+
+extern "C" int pfpn_peer_gather_sum_packets(const void* rows, int32_t nranks, int32_t value, size_t n, float* out, float scale,
+                                            pfpn_stream_t stream_) {
+  if (!rows || !out || nranks < 1 || nranks > kMaxPeers || n == 0 || value < 1 || (reinterpret_cast<uintptr_t>(rows) & 7))
+    return PFPN_ERR_ARG;
+  size_t grid = (n + 63) / 64;
+  if (grid > 296) grid = 296;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(64);
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream_);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  PFPN_CUDA_OK(cudaLaunchKernelEx(&cfg, peer_gather_sum_packets_kernel, reinterpret_cast<const uint2*>(rows), (int)nranks, (int)value, n,
+                                  out, scale));
+  return PFPN_OK;
+}
 
 extern "C" int pfpn_peer_gather_sum(const float* gather, const int32_t* flags, int32_t nranks, int32_t value, size_t n,
                                     float* out, float scale, pfpn_stream_t stream_) {

@@ -748,7 +748,21 @@ struct HeadPushK {
   int* ticket;     // local CTA-arrival counter (self-resetting)
   int nranks;      // 0 = no push
   int value;
+  int protocol;             // 1 = 8-byte packets {value, sequence}: see pfpn_head_push
+  int consume_value;        // packets: exchange summed by this launch (0 = none)
+  const uint2* consume_rows;
+  float* consume_out;
+  float consume_scale;
 };
+__device__ __forceinline__ void st_packet(float* row, int i, float v, int seq) {  // one single-copy-atomic 8-byte store
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint2*>(row) + i), "r"(__float_as_uint(v)), "r"(seq)
+               : "memory");
+}
+__device__ __forceinline__ uint2 ld_packet(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
 __global__ void __launch_bounds__(32 * kFinGroups) head_finalize_kernel(const float* __restrict__ part,
                                                                         const float* __restrict__ loss_part,
                                                                         const float* __restrict__ logstd, float* __restrict__ dloc,
@@ -761,6 +775,15 @@ __global__ void __launch_bounds__(32 * kFinGroups) head_finalize_kernel(const fl
   const bool col_ok = idx < 2 * AP;
   asm volatile("griddepcontrol.launch_dependents;");  // (push mode: lets pfpn_peer_gather_sum get resident and poll early)
   const float ils = (col_ok && idx < AP && grp == 0) ? expf(-logstd[idx]) : 1.f;  // (parameter, not written by the head kernel)
+  // packets: the EARLIER exchange this launch sums does not depend on the head kernel -- its loads are issued first, so
+  // their latency hides behind the partial sums (and they are not queued behind this launch's remote stores)
+  const bool consume = push.protocol == 1 && push.consume_value != 0 && grp == 0 && col_ok;
+  const uint2* crow = push.consume_rows + idx;
+  const size_t cpitch = 2 * (size_t)AP;
+  uint2 pk[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)  // first try: an L2 load (L2 is where peer writes to this GPU's memory land); re-polls are volatile
+    pk[r] = (consume && r < push.nranks) ? __ldcg(crow + r * cpitch) : make_uint2(0u, 0u);
   asm volatile("griddepcontrol.wait;" ::: "memory");  // the head kernel's partials are complete and visible
   float s = 0.f;
   if (col_ok) {
@@ -801,13 +824,28 @@ __global__ void __launch_bounds__(32 * kFinGroups) head_finalize_kernel(const fl
     } else if (dlogstd != nullptr) {
       dlogstd[idx - AP] = t;
     }
-    for (int p = 0; p < push.nranks; ++p) push.out[p][idx] = t;
+    if (push.protocol == 1) {
+      for (int p = 0; p < push.nranks; ++p) st_packet(push.out[p], idx, t, push.value);
+      if (consume) {  // the sum of an EARLIER exchange, element idx, rank order
+        float sum = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          if (r < push.nranks) {
+            while ((int)pk[r].y != push.consume_value) pk[r] = ld_packet(crow + r * cpitch);
+            sum += __uint_as_float(pk[r].x);
+          }
+        }
+        push.consume_out[idx] = sum * push.consume_scale;
+      }
+    } else {
+      for (int p = 0; p < push.nranks; ++p) push.out[p][idx] = t;
+    }
   }
   if (loss_warp) {
     for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
     if (col == 0) *loss = l;
   }
-  if (push.nranks > 0) {
+  if (push.nranks > 0 && push.protocol == 0) {
     // every CTA: my remote stores are ordered before my ticket; the last CTA of the grid raises the flags
     if (grp == 0) __threadfence_system();
     __syncthreads();
@@ -1035,15 +1073,29 @@ static int head_logprob_impl(const pfpn_head_args* args, void* workspace, size_t
   HeadPushK pk;
   memset(&pk, 0, sizeof(pk));
   if (push != nullptr) {
-    if (!bwd || push->nranks < 1 || push->nranks > 8 || !push->ticket || push->value < 1) return PFPN_ERR_ARG;
+    if (!bwd || push->nranks < 1 || push->nranks > 8 || push->value < 1) return PFPN_ERR_ARG;
+    if (push->protocol != 0 && push->protocol != 1) return PFPN_ERR_ARG;
+    const bool packets = push->protocol == 1;
+    if (!packets && !push->ticket) return PFPN_ERR_ARG;
     for (int p = 0; p < push->nranks; ++p) {
-      if (!push->out[p] || !push->flags[p]) return PFPN_ERR_ARG;
+      if (!push->out[p] || (!packets && !push->flags[p])) return PFPN_ERR_ARG;
+      if (packets && (reinterpret_cast<uintptr_t>(push->out[p]) & 7)) return PFPN_ERR_ALIGN;
       pk.out[p] = push->out[p];
       pk.flags[p] = push->flags[p];
     }
     pk.ticket = push->ticket;
     pk.nranks = push->nranks;
     pk.value = push->value;
+    pk.protocol = push->protocol;
+    if (packets && push->consume_value != 0) {
+      if (push->consume_value < 1 || push->consume_value >= push->value || !push->consume_rows || !push->consume_out ||
+          (reinterpret_cast<uintptr_t>(push->consume_rows) & 7))
+        return PFPN_ERR_ARG;
+      pk.consume_value = push->consume_value;
+      pk.consume_rows = reinterpret_cast<const uint2*>(push->consume_rows);
+      pk.consume_out = push->consume_out;
+      pk.consume_scale = push->consume_scale;
+    }
   }
   if (a.mode == PFPN_HEAD_GRAD && !a.g_lp) return PFPN_ERR_ARG;
   if (a.mode == PFPN_HEAD_PPO && (!a.adv || !a.lp_old || !a.loss)) return PFPN_ERR_ARG;

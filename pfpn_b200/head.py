@@ -67,13 +67,14 @@ def adv_stats(adv: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
 def head_call(mode: int, logits, loc, logstd, value, *, tanh=False, g_lp=None, g_ent_ba=None,
               g_ent: float = 0.0, adv=None, lp_old=None, adv_stats_t=None, eps_clip: float = 0.2,
               loss_scale: float = 0.0, want_ent_ba=False, want_dvalue=False, dlogits_out=None,
-              out: Optional[dict] = None, push=None) -> dict:
+              out: Optional[dict] = None, push=None, consume_into=None) -> dict:
     """One launch of K1.  Returns a dict of freshly written tensors.
 
     ``out`` may carry preallocated ``lp, ent, dlogits, dloc, dlogstd, loss``
     tensors (bench / CUDA-graph use) -- then nothing is allocated here.
     ``push`` (a ``pfpn_b200.peer.PeerGather``): data-parallel form -- the finalize kernel also stores dloc / dlogstd
-    into every rank's gather buffer; follow with ``push.reduce(...)``.
+    into every rank's gather buffer; follow with ``push.reduce(...)``, or pass ``consume_into`` [2*A*P] and the NEXT
+    call's launch writes the sum over ranks of this call's exchange there (one exchange late, no kernel of its own).
     """
     logits = _f32c(logits, "logits")
     B, A, P = logits.shape
@@ -140,7 +141,7 @@ def head_call(mode: int, logits, loc, logstd, value, *, tanh=False, g_lp=None, g
     ws = _ws(dev, nbytes)
     with torch.cuda.device(dev):
         if push is not None and mode != _cabi.HEAD_FWD:
-            _cabi.check(_cabi.pfpn_head_logprob_push(C.byref(a), ws.data_ptr(), ws.numel(), C.byref(push.push_args()),
+            _cabi.check(_cabi.pfpn_head_logprob_push(C.byref(a), ws.data_ptr(), ws.numel(), C.byref(push.push_args(consume_into)),
                                                      _stream_ptr()))
         else:
             _cabi.check(_cabi.pfpn_head_logprob(C.byref(a), ws.data_ptr(), ws.numel(), _stream_ptr()))

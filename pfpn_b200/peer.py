@@ -103,76 +103,94 @@ class PeerSum:
 
 
 class PeerGather:
-    """PUSH protocol for the sharded head's [2, A, P] exchange (`pfpn_head_logprob_push` + `pfpn_peer_gather_sum`): K1's
-    finalize kernel stores this rank's dloc / dlogstd into row `rank` of EVERY rank's gather buffer and raises the flags;
-    the consumer waits for the N flags and sums the N local rows in rank order.  No exchange kernel sits behind K1.
+    """PUSH protocol for the sharded head's [2, A, P] exchange (`pfpn_head_logprob_push`, protocol 1 of `pfpn_head_push`):
+    K1's finalize kernel stores this rank's dloc / dlogstd into row `rank` of EVERY rank's gather buffer as 8-byte packets
+    {value, exchange number}; an aligned 8-byte store is single-copy atomic, so the receiver validates every element by
+    its own sequence word -- no fence, ticket or flag round trip follows the data.  No exchange kernel sits behind K1.
 
-    Producer and consumer are decoupled: ``push_args()`` numbers the exchanges 1, 2, 3, ... and ``reduce()`` consumes the
-    OLDEST one not yet consumed.  A caller that consumes exchange v only after it has produced v+1 (``lag = 1``: the sum is
-    needed by the optimizer, not by the next head launch) never waits for the slowest rank inside a step -- the flags of
-    v arrived a whole step ago -- and everything stays on ONE stream.  Measured: a consumer on a second stream (events in
-    both directions every step) was SLOWER than the in-step consumer (0.1733 vs 0.1692 ms per step on 2 GPUs).
-    Buffers rotate over NBUF = 4 exchange slots: rank r's push of v+3 follows its own reduce of v+1, which needs rank p's
-    push of v+1, which follows p's reduce of v-1 -- so slot (v-1) mod 4 is consumed everywhere before v+3 overwrites it
-    (holds for lag <= 1).
+    Producer and consumer are decoupled: ``push_args()`` numbers the exchanges 1, 2, 3, ...; the sum over ranks (rank
+    order, bit-identical on every rank) of the OLDEST unconsumed exchange is produced either
 
-    Per rank: gather [NBUF][world][n] floats, flags int32[64] (word r = last exchange rank r pushed), one local ticket."""
+    * by the NEXT head launch itself (``push_args(consume_into=out)``: the finalize thread that owns element i also sums
+      element i of the previous exchange -- its packets arrived a step ago, so nothing waits and the exchange costs no
+      kernel of its own; the sum feeds the optimizer, not the next head launch, so it may lag one exchange), or
+    * by ``reduce(out)`` (`pfpn_peer_gather_sum_packets`): the last exchange of a run, or a caller that needs it at once.
+
+    Measured on 8 B200 (bench.py exchange_breakdown): K1 alone 0.1585 ms/step; rows + flags + a consumer kernel per step
+    0.1743; a consumer on a second stream was slower still (events in both directions every step).
+    Buffers rotate over NBUF = 4 exchange slots: rank r's push of v+3 follows its own consumption of v+1, which needs rank
+    p's push of v+1, which follows p's consumption of v-1 -- so slot (v-1) mod 4 is consumed everywhere before v+3
+    overwrites it (holds while at most one exchange lags).
+
+    Per rank: gather [NBUF][world][n] packets (8 bytes each), zero-initialised (sequence 0 is never valid)."""
 
     NBUF = 4
     MAX_LAG = 1
 
     def __init__(self, n: int, device: torch.device, group=None):
-        if n % 4:
-            raise ValueError("n must be a multiple of 4 floats")
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.n, self.dev = n, device
         self.pushed = 0    # exchanges produced (push_args handed out)
-        self.consumed = 0  # exchanges consumed by reduce()
+        self.consumed = 0  # exchanges whose sum was produced
         with torch.cuda.device(device):
-            gather = _alloc(self.NBUF * self.world * n * 4)
-            flag = _alloc(64 * 4)
-            self._gather_ptr, self._flag_ptr = gather[0], flag[0]
-            self._gather_ptrs, self._flag_ptrs = _share([gather, flag], device, group)
-        self.gather = torch.as_tensor(_CudaArray(self._gather_ptr, self.NBUF * self.world * n, "<f4"),
-                                      device=device).view(self.NBUF, self.world, n)
-        self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
+            gather = _alloc(self.NBUF * self.world * n * 8)
+            self._gather_ptr = gather[0]
+            (self._gather_ptrs,) = _share([gather], device, group)
+        # [NBUF][world][n][2] float32 view: [..., 0] = value, [..., 1] = sequence word (as float bits)
+        self.gather = torch.as_tensor(_CudaArray(self._gather_ptr, self.NBUF * self.world * n * 2, "<f4"),
+                                      device=device).view(self.NBUF, self.world, n, 2)
         self._push = [self._make_push(slot) for slot in range(self.NBUF)]
 
     @property
     def calls(self) -> int:
         return self.pushed
 
+    def _rows_ptr(self, slot: int) -> int:
+        return self._gather_ptr + slot * self.world * self.n * 8
+
     def _make_push(self, slot: int):
         p = _cabi.HeadPush()
         for r in range(self.world):
-            p.out[r] = self._gather_ptrs[r] + ((slot * self.world + self.rank) * self.n) * 4
-            p.flags[r] = self._flag_ptrs[r] + 4 * self.rank
-        p.ticket = self.ticket.data_ptr()
+            p.out[r] = self._gather_ptrs[r] + ((slot * self.world + self.rank) * self.n) * 8
         p.nranks = self.world
+        p.protocol = 1
         return p
 
     def slot_of(self, call: int) -> int:
         return call % self.NBUF
 
-    def push_args(self):
-        """The `pfpn_head_push` of the next exchange: pass it to pfpn_head_logprob_push (head_call(push=self))."""
-        if self.pushed - self.consumed > self.MAX_LAG:
-            raise RuntimeError("consume the pending exchanges first (reduce()): at most one exchange may lag")
-        self.pushed += 1
-        p = self._push[self.slot_of(self.pushed)]
-        p.value = self.pushed
-        return p
+    def row(self, call: int, rank: int) -> torch.Tensor:
+        """Values rank `rank` pushed in exchange `call` (this rank's local copy)."""
+        return self.gather[self.slot_of(call), rank, :, 0]
 
     @property
     def pending(self) -> int:
         return self.pushed - self.consumed
+
+    def push_args(self, consume_into: torch.Tensor = None, scale: float = 1.0):
+        """The `pfpn_head_push` of the next exchange (head_call(push=...)).  With ``consume_into`` [n] the same launch also
+        writes scale * (sum over ranks of the oldest unconsumed exchange) there, if one is pending."""
+        if self.pending > self.MAX_LAG:
+            raise RuntimeError("consume the pending exchange first (reduce()): at most one exchange may lag")
+        self.pushed += 1
+        p = self._push[self.slot_of(self.pushed)]
+        p.value = self.pushed
+        p.consume_value = 0
+        if consume_into is not None and self.pending > 1:
+            if consume_into.numel() != self.n or consume_into.dtype != torch.float32 or not consume_into.is_contiguous():
+                raise ValueError("consume_into must be a contiguous float32 tensor of n elements")
+            self.consumed += 1
+            p.consume_value = self.consumed
+            p.consume_rows = self._rows_ptr(self.slot_of(self.consumed))
+            p.consume_out = consume_into.data_ptr()
+            p.consume_scale = scale
+        return p
 
     def reduce(self, out: torch.Tensor, scale: float = 1.0, stream_ptr: int = 0):
         """out[n] = scale * sum over ranks (rank order) of the OLDEST unconsumed exchange, on the producer's stream."""
         if self.consumed >= self.pushed:
             raise RuntimeError("nothing to consume: no exchange was pushed")
         self.consumed += 1
-        slot = self.slot_of(self.consumed)
-        _cabi.check(_cabi.pfpn_peer_gather_sum(self._gather_ptr + slot * self.world * self.n * 4, self._flag_ptr, self.world,
-                                               self.consumed, self.n, out.data_ptr(), scale, stream_ptr))
+        _cabi.check(_cabi.pfpn_peer_gather_sum_packets(self._rows_ptr(self.slot_of(self.consumed)), self.world, self.consumed,
+                                                       self.n, out.data_ptr(), scale, stream_ptr))
         return out

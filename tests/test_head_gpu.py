@@ -186,12 +186,14 @@ def test_full_size_shard_linearity(cuda_dev):
 
 
 def test_push_form_single_rank_equals_plain_call(cuda_dev):
-    """pfpn_head_logprob_push + pfpn_peer_gather_sum (the data-parallel form of K1's [2,A,P] output) on a world of one
-    rank: the finalize kernel's push / ticket / flag protocol and the gather-sum consumer, over several calls (both
-    buffer parities), must reproduce the plain call's dloc / dlogstd bit for bit."""
+    """pfpn_head_logprob_push (the data-parallel form of K1's [2,A,P] output) on a world of one rank, both protocols:
+    packets {value, sequence} consumed at once (pfpn_peer_gather_sum_packets), consumed ONE exchange late by the next
+    launch's finalize kernel (consume_into) across all rotating slots, and rows + ticket + flags with
+    pfpn_peer_gather_sum.  Each must reproduce the plain call's dloc / dlogstd bit for bit."""
+    import ctypes as C
     import socket
     import torch.distributed as dist
-    from pfpn_b200.head import _stream_ptr
+    from pfpn_b200.head import _stream_ptr, _ws, head_workspace_bytes
     from pfpn_b200.peer import PeerGather
     created = False
     if not dist.is_initialized():
@@ -202,18 +204,59 @@ def test_push_form_single_rank_equals_plain_call(cuda_dev):
         created = True
     try:
         B, A, P = 1000, 36, 35
+        n = 2 * A * P
         d = {k: (v.to(cuda_dev) if torch.is_tensor(v) else v) for k, v in synth.head_inputs(B, A, P, seed=9).items()}
-        pg = PeerGather(2 * A * P, cuda_dev)
-        out = torch.empty(2 * A * P, device=cuda_dev)
-        for it in range(5):
+        cat = lambda r: torch.cat([r["dloc"].reshape(-1), r["dlogstd"].reshape(-1)])
+        pg = PeerGather(n, cuda_dev)
+        out = torch.empty(n, device=cuda_dev)
+        for it in range(5):  # packets, consumed at once
             g_lp = torch.randn(B, device=cuda_dev) / B
             ref = head.head_call(_cabi.HEAD_GRAD, d["logits"], d["loc"], d["logstd"], d["value"], g_lp=g_lp)
             o = head.head_call(_cabi.HEAD_GRAD, d["logits"], d["loc"], d["logstd"], d["value"], g_lp=g_lp, push=pg)
             pg.reduce(out, 1.0, _stream_ptr())
             torch.cuda.synchronize()
             assert torch.equal(o["dloc"], ref["dloc"]) and torch.equal(o["dlogstd"], ref["dlogstd"])
-            assert torch.equal(out[:A * P].view(A, P), ref["dloc"]) and torch.equal(out[A * P:].view(A, P), ref["dlogstd"])
-            assert int(pg.ticket.item()) == 0  # self-resetting CTA counter
+            assert torch.equal(out, cat(ref))
+            assert torch.equal(pg.row(pg.pushed, 0), cat(ref))
+        refs, outs = [], [torch.full((n,), float("nan"), device=cuda_dev) for _ in range(9)]
+        for it in range(9):  # packets, each exchange summed by the NEXT launch (lag 1), scale 0.5
+            g_lp = torch.randn(B, device=cuda_dev) / B
+            refs.append(cat(head.head_call(_cabi.HEAD_GRAD, d["logits"], d["loc"], d["logstd"], d["value"], g_lp=g_lp)))
+            if it == 0:
+                head.head_call(_cabi.HEAD_GRAD, d["logits"], d["loc"], d["logstd"], d["value"], g_lp=g_lp, push=pg)
+            else:
+                with torch.cuda.device(cuda_dev):
+                    o = head.head_call(_cabi.HEAD_GRAD, d["logits"], d["loc"], d["logstd"], d["value"], g_lp=g_lp, push=pg,
+                                       consume_into=outs[it - 1])
+            assert pg.pending == 1
+        pg.reduce(outs[8], 1.0, _stream_ptr())
+        torch.cuda.synchronize()
+        assert pg.pending == 0
+        for it in range(9):
+            assert torch.equal(outs[it], refs[it]), it
+        with pytest.raises(RuntimeError):
+            pg.reduce(out)  # nothing pending
+
+        # protocol 0: rows + CTA ticket + flags, raw structure over local buffers
+        rows = torch.zeros(2, n, device=cuda_dev)
+        flags = torch.zeros(64, dtype=torch.int32, device=cuda_dev)
+        ticket = torch.zeros(1, dtype=torch.int32, device=cuda_dev)
+        for it in range(1, 5):
+            g_lp = torch.randn(B, device=cuda_dev) / B
+            ref = head.head_call(_cabi.HEAD_GRAD, d["logits"], d["loc"], d["logstd"], d["value"], g_lp=g_lp)
+            hp = _cabi.HeadPush()
+            hp.out[0], hp.flags[0], hp.ticket = rows[it & 1].data_ptr(), flags.data_ptr(), ticket.data_ptr()
+            hp.nranks, hp.value = 1, it
+
+            class _Raw:
+                def push_args(self, consume_into=None):
+                    return hp
+            o = head.head_call(_cabi.HEAD_GRAD, d["logits"], d["loc"], d["logstd"], d["value"], g_lp=g_lp, push=_Raw())
+            _cabi.check(_cabi.pfpn_peer_gather_sum(rows[it & 1].data_ptr(), flags.data_ptr(), 1, it, n, out.data_ptr(), 1.0,
+                                                   _stream_ptr()))
+            torch.cuda.synchronize()
+            assert torch.equal(out, cat(ref)) and torch.equal(cat(o), cat(ref))
+            assert int(ticket.item()) == 0 and int(flags[0].item()) == it  # self-resetting CTA counter; monotonic flag
     finally:
         if created:
             dist.destroy_process_group()

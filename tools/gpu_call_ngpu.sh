@@ -4,9 +4,12 @@ N=${1:-2}
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-timeout 900 python -m pytest tests/test_peer_multi_gpu.py -m gpu -x -q > gpurun_out/pytest_ngpu_$N.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_ngpu_$N.log
+timeout 300 python -m pytest tests/test_head_gpu.py -m gpu -x -q -k push > gpurun_out/pytest_push_$N.log 2>&1; rc=$?; tail -5 gpurun_out/pytest_push_$N.log
+if [ $rc -ne 0 ]; then echo "push test failed rc=$rc"; exit 1; fi
+timeout 900 python -m pytest tests/test_peer_multi_gpu.py -m gpu -x -q > gpurun_out/pytest_ngpu_$N.log 2>&1; rc=$?; echo "pytest rc=$rc" >> gpurun_out/pytest_ngpu_$N.log
 tail -25 gpurun_out/pytest_ngpu_$N.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29731 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench rc=$?"
+if [ $rc -ne 0 ]; then exit 1; fi
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29731 bench.py --gpus $N --steps 200 --warmup 20 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench rc=$?"
 python - <<PY
 import json
 try:

@@ -105,17 +105,14 @@ for it in range(5):
     for r in range(1, world):
         ordered += allc[r]
     ok_push = ok_push and bool(torch.equal(outg, ordered))  # bit-equal to the rank-ordered sum, on every rank
-# the same consumed ONE exchange late (lag 1: produce v+1, then consume v), 4 rotating slots
+# the same, each exchange summed ONE exchange late by the next launch's finalize kernel (consume_into), 4 rotating slots
 ok_async, outs = True, [torch.empty(n, device=dev) for _ in range(8)]
-exp, nxt = [], 0
+exp = []
 for it in range(8):
     glp2 = glp * (1.0 + 0.05 * it)
-    o2 = head.head_call(_cabi.HEAD_GRAD, lg, locp, lsp, val, g_lp=glp2, push=pg)
+    o2 = head.head_call(_cabi.HEAD_GRAD, lg, locp, lsp, val, g_lp=glp2, push=pg, consume_into=outs[it - 1] if it else None)
     exp.append(torch.cat([o2["dloc"].reshape(-1), o2["dlogstd"].reshape(-1)]))
-    if pg.pending > 1:
-        pg.reduce(outs[nxt], 1.0, _stream_ptr()); nxt += 1
-while pg.pending > 0:
-    pg.reduce(outs[nxt], 1.0, _stream_ptr()); nxt += 1
+pg.reduce(outs[7], 1.0, _stream_ptr())
 torch.cuda.synchronize()
 for it in range(8):
     allc = [torch.empty_like(exp[it]) for _ in range(world)]
@@ -128,12 +125,13 @@ out.update(push_async_ok=ok_async)
 torch.cuda.synchronize(); dist.barrier()
 e0.record()
 for _ in range(30):
-    head.head_call(_cabi.HEAD_GRAD, lg, locp, lsp, val, g_lp=glp, push=pg, out=o); pg.reduce(outg, 1.0, _stream_ptr())
+    head.head_call(_cabi.HEAD_GRAD, lg, locp, lsp, val, g_lp=glp, push=pg, out=o, consume_into=outg)
+pg.reduce(outg, 1.0, _stream_ptr())
 e1.record(); torch.cuda.synchronize(); t_push = e0.elapsed_time(e1) / 30
 e0.record()
 for _ in range(30):
     head.head_call(_cabi.HEAD_GRAD, lg, locp, lsp, val, g_lp=glp, out=o)
 e1.record(); torch.cuda.synchronize(); t_nopush = e0.elapsed_time(e1) / 30
 out.update(push_sum_ok=ok_push, ms_head_with_push_exchange=round(t_push, 4), ms_head_alone=round(t_nopush, 4))
-print(json.dumps(out), flush=True)
+os.write(1, (json.dumps(out) + "\n").encode())  # one write: the ranks' lines never interleave
 dist.barrier(); dist.destroy_process_group()

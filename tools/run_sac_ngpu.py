@@ -25,7 +25,7 @@ torch.cuda.synchronize()
 ref = net.params.clone(); dist.broadcast(ref, 0)
 reft = net.target_params.clone(); dist.broadcast(reft, 0)
 refm = net.state_mean.clone(); dist.broadcast(refm, 0)
-print(json.dumps({"rank": rank, "world": world, "params_equal": bool(torch.equal(ref, net.params)),
+os.write(1, (json.dumps({"rank": rank, "world": world, "params_equal": bool(torch.equal(ref, net.params)),
                   "target_equal": bool(torch.equal(reft, net.target_params)), "state_mean_equal": bool(torch.equal(refm, net.state_mean)),
-                  "finite": bool(torch.isfinite(net.params).all()), "loc_row0": [round(float(v), 4) for v in net.loc[0, :4]], "log_alpha": float(net.log_alpha)}), flush=True)
+                  "finite": bool(torch.isfinite(net.params).all()), "loc_row0": [round(float(v), 4) for v in net.loc[0, :4]], "log_alpha": float(net.log_alpha)}) + "\n").encode())
 dist.barrier(); dist.destroy_process_group()
