@@ -267,6 +267,11 @@ def main():
     from pfpn_b200 import _cabi, head, synth
     from pfpn_b200.host import HostHeadPipeline
 
+    host_binding, all_cpus = None, os.sched_getaffinity(0)
+    if os.environ.get("PFPN_BIND_NUMA", "1") != "0":
+        from pfpn_b200.host import bind_host_to_gpu
+        host_binding = bind_host_to_gpu(local_rank)  # before any pinned allocation: first touch decides the NUMA node
+
     def maxr(x: float) -> float:
         t = torch.tensor([x], device=dev, dtype=torch.float64)
         if world > 1:
@@ -434,6 +439,7 @@ def main():
     # sanity: the host path and the resident path agree
     assert torch.allclose(out["lp"], lp.cpu(), rtol=0, atol=0), "host pipeline lp mismatch"
     e2e_step_s = e2e_ms_local * 1e-3 / args.e2e_steps
+    os.sched_setaffinity(0, all_cpus)  # (the CPU baseline below uses every core the process was given)
 
     # ---- the DPPO minibatch update around the head (BASELINE c4): B_total = 65536 sharded ------
     dppo = None
@@ -558,7 +564,7 @@ def main():
                     "api": "pfpn_b200.host.HostHeadPipeline.run (pinned host buffers, 3-stream chunked)",
                     "rank0_h2d_GBps": pipe.h2d_bytes / e2e_step_s / 1e9, "rank0_d2h_GBps": pipe.d2h_bytes / e2e_step_s / 1e9,
                     "bound": "PCIe: both directions stream concurrently for the whole step; the 0.17 ms kernel is ~2 % of it",
-                    "rank0_host_affinity": numa_note(local_rank)},
+                    "rank0_host_affinity": numa_note(local_rank), "rank0_host_binding": host_binding},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -695,6 +701,33 @@ def run_extra(dev, rank, world, stream, maxr):
     out["c5_sac_head"] = c5
     del logits5, buf5
     torch.cuda.empty_cache()
+    # ---- K6: the trunk's tensor-core GEMM at the headline batch, against the MEASURED tensor peak -------------------
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            mp = json.load(f)
+        bf16_burst, bf16_sust = float(mp["bf16_tflops"]), float(mp.get("bf16_tflops_sustained", mp["bf16_tflops"]))
+        peak_src = "MEASURED_PEAKS.json: cuBLAS bf16 / 2 (tf32 runs at half the bf16 rate)"
+    except Exception:  # noqa: BLE001
+        bf16_burst, bf16_sust, peak_src = 2250.0, 2250.0, "fallback: nominal 2.25 PFLOP/s bf16 / 2"
+    Mg, Ng, Kg = B_PER_GPU, 512, 1024
+    Ag = torch.randn(Mg, Kg, device=dev, generator=gr)
+    Wg = torch.randn(Kg, Ng, device=dev, generator=gr) * 0.05
+    Wlo = torch.empty_like(Wg)
+    bg = torch.zeros(Ng, device=dev)
+    Cg = torch.empty(Mg, Ng, device=dev)
+    _cabi.check(_cabi.pfpn_split_lo(Wg.data_ptr(), Wlo.data_ptr(), Wg.numel(), stream.cuda_stream))
+    t_g, _ = timed(lambda: _cabi.check(_cabi.pfpn_tc_gemm_nn_lo(Ag.data_ptr(), Kg, Wg.data_ptr(), Wlo.data_ptr(), Ng, Cg.data_ptr(), Ng,
+                                                                  bg.data_ptr(), None, Ng, Mg, Ng, Kg, 2, stream.cuda_stream)), 20, stream)
+    t_g = maxr(t_g)
+    fp32_tf = 2.0 * Mg * Ng * Kg / (t_g * 1e-3) / 1e12
+    out["k6_trunk_gemm"] = {"shape": f"M={Mg} (per GPU), N={Ng}, K={Kg}, bias+relu6 (layer 2 forward)", "ms": t_g,
+                            "fp32_equivalent_TFLOPs": fp32_tf, "tf32_mma_TFLOPs": 3.0 * fp32_tf,
+                            "tf32_peak_burst": bf16_burst / 2, "tf32_peak_sustained": bf16_sust / 2,
+                            "frac_of_burst_peak": 3.0 * fp32_tf / (bf16_burst / 2), "frac_of_sustained_peak": 3.0 * fp32_tf / (bf16_sust / 2),
+                            "peak_source": peak_src,
+                            "note": "3xTF32 error-compensated: three tcgen05.mma (kind::tf32, cta_group::2) per fp32 product; "
+                                    "bound = tensor pipe under the power cap"}
+    del Ag, Wg, Wlo, Cg
     return out
 
 

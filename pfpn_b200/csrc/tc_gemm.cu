@@ -726,6 +726,347 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persist_kernel(const _
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-PAIR form (round 2, K-major A only: forward and input gradient): two CTAs of one cluster -- the two SMs of a TPC --
+// compute a 256 x 128 output tile with tcgen05.mma.cta_group::2.  CTA r of the pair owns rows [m0 + 128 r, + 128): its
+// own A tile feeds the hi products straight from shared memory and, through its own splitter warps, the lo products from
+// its OWN tensor memory; its accumulators (128 lanes x 384 columns) live in its own tensor memory, and its shared memory
+// holds only HALF of the B tile (64 of the 128 N-rows, hi and lo).
+// The one-CTA kernel is bound by shared-memory bandwidth, not by the tensor pipe: per 32-wide k-block an SM absorbs
+// 48 KB of TMA writes, 16 KB of splitter reads and 12 x 4 KB of B-operand reads by the MMAs = 112 KB against 128 B/clk,
+// i.e. >= 875 clk where the 12 MMAs need ~800.  The pair halves the B traffic per SM (72 KB, ~560 clk).
+// Only the leader (cluster rank 0) issues MMAs.  Barriers: full / empty / acc_full / stage_* are per CTA (empty and
+// acc_full are signalled in BOTH CTAs by one multicast tcgen05.commit); conv and acc_free live in the LEADER and count
+// the 2 x 128 splitter threads of both CTAs (remote arrive, release / acquire at cluster scope).
+// ------------------------------------------------------------------------------------------------
+constexpr int TP_STAGES = 4;
+static_assert(TP_STAGES * 32 <= 512 - (int)TC_TMEM_A, "one 32-column a_lo slot per ring stage next to the three accumulators");
+constexpr int TP_HALF_BYTES = TC_TILE_BYTES / 2;                       // 64 N-rows x 32 floats
+constexpr int TP_STAGE_BYTES = TC_TILE_BYTES + 2 * TP_HALF_BYTES;      // A, B_hi half, B_lo half
+constexpr int TP_RING_BYTES = TP_STAGES * TP_STAGE_BYTES;
+constexpr int TP_SMEM_BYTES = TP_RING_BYTES + TCP_STAGING_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// Remote arrive with the DEFAULT semantics (release at CTA scope), as CUTLASS's ClusterBarrier does.  What the leader's
+// MMAs read from the peer is (a) tensor memory written by tcgen05.st -- ordered by tcgen05.wait::st +
+// tcgen05.fence::before_thread_sync on this side and fence::after_thread_sync on the leader's -- and (b) shared memory
+// written by TMA, complete (complete_tx on this CTA's `full` barrier) before this thread arrives; neither sits behind a
+// cache.  A `.release.cluster` arrive compiles to MEMBAR.ALL.GPU + ERRBAR per thread per k-block: 13 % of all stall
+// samples of the first pair profile, on the critical splitter -> MMA path (1972 instead of ~1000 clk per k-block).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// M = 256 over the pair: A rows [0,128) from the leader's tensor memory, [128,256) from the peer's (same address),
+// B = N x 8 with N/2 rows from each CTA's shared memory (same offset), D rows likewise split over the two tensor memories
+__device__ __forceinline__ void umma_tf32_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on `bar` (same offset) in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+// both operands from shared memory: A = this CTA's 128 rows (K-major tile as TMA landed it), B as above
+__device__ __forceinline__ void umma_tf32_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+      : "memory");
+}
+
+template <bool B_MN>
+__global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                      const __grid_constant__ CUtensorMap mapB,
+                                                                      const __grid_constant__ CUtensorMap mapBlo, const TcParams p,
+                                                                      const int tiles_n, const int num_tiles) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // (the dynamic segment starts at the same offset in both CTAs)
+  unsigned char* gbase = smem_dyn + (base - raw);
+  unsigned char* staging = gbase + TP_RING_BYTES;
+  const uint32_t bar0 = base + TP_RING_BYTES + TCP_STAGING_BYTES;
+  auto full = [&](int s) { return bar0 + 8 * s; };
+  auto conv = [&](int s) { return bar0 + 8 * (TP_STAGES + s); };
+  auto empty = [&](int s) { return bar0 + 8 * (2 * TP_STAGES + s); };
+  const uint32_t acc_full = bar0 + 8 * 3 * TP_STAGES, acc_free = acc_full + 8, stage_full = acc_full + 16,
+                 stage_free = acc_full + 24;
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(gbase + TP_RING_BYTES + TCP_STAGING_BYTES + 8 * (3 * TP_STAGES + 4));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TP_STAGES; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(conv(s), 256);  // (used in the leader only)
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_free, 256);   // (leader only)
+    mbar_init(stage_full, 128);
+    mbar_init(stage_free, 128);
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+    if (p.b_lo_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBlo)) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  auto decode = [&](int t, int& m0, int& n0) {
+    const int mb = t / tiles_n;
+    m0 = mb * 2 * TC_BM + (int)crank * TC_BM;  // this CTA's 128 rows
+    n0 = (t - mb * tiles_n) * TC_BN;
+  };
+  const int nkb = (p.K + TC_BK - 1) / TC_BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int g = 0;
+      for (int t = pair; t < num_tiles; t += npairs) {
+        int m0, n0;
+        decode(t, m0, n0);
+        const int nh = n0 + (int)crank * (TC_BN / 2);  // this CTA's half of the B tile
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int s = g % TP_STAGES;
+          mbar_wait_sleep(empty(s), (uint32_t)(((g / TP_STAGES) & 1) ^ 1), p.wait_ns);
+          mbar_expect_tx(full(s), TC_TILE_BYTES + (p.b_lo_tma ? 2 : 1) * TP_HALF_BYTES);
+          const uint32_t a_dst = base + s * TP_STAGE_BYTES, b_dst = a_dst + TC_TILE_BYTES, l_dst = b_dst + TP_HALF_BYTES;
+          const int k0 = kb * TC_BK;
+          tma_load_2d(a_dst, &mapA, k0, m0, full(s));
+          if (B_MN) {
+#pragma unroll
+            for (int q = 0; q < TC_BN / 64; ++q) tma_load_2d(b_dst + q * 4096, &mapB, nh + 32 * q, k0, full(s));
+          } else {
+            tma_load_2d(b_dst, &mapB, k0, nh, full(s));  // (box of 64 rows)
+          }
+          if (p.b_lo_tma) {
+            if (B_MN) {
+#pragma unroll
+              for (int q = 0; q < TC_BN / 64; ++q) tma_load_2d(l_dst + q * 4096, &mapBlo, nh + 32 * q, k0, full(s));
+            } else {
+              tma_load_2d(l_dst, &mapBlo, k0, nh, full(s));
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && crank == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(TC_BN >> 3) << 17) |
+                             ((uint32_t)((2 * TC_BM) >> 4) << 24);
+      int g = 0, ti = 0;
+      for (int t = pair; t < num_tiles; t += npairs, ++ti) {
+        if (ti > 0) mbar_wait(acc_free, (uint32_t)((ti - 1) & 1));  // both CTAs read the previous accumulators out
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int s = g % TP_STAGES;
+          mbar_wait(conv(s), (uint32_t)((g / TP_STAGES) & 1));  // both A tiles are in tensor memory, both B halves landed
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_sm = base + s * TP_STAGE_BYTES, b_hi = a_sm + TC_TILE_BYTES, b_lo = b_hi + TP_HALF_BYTES;
+          const uint32_t a_lo = tmem + TC_TMEM_A + (uint32_t)(s * 32);
+#pragma unroll
+          for (int ks = 0; ks < TC_BK / 8; ++ks) {
+            // a_hi is the raw A tile where TMA put it (the tensor core drops the low 13 mantissa bits itself); only a_lo
+            // goes through the splitter into tensor memory -- one 32-column slot PER RING STAGE, so the splitter runs up to
+            // TP_STAGES - 1 k-blocks ahead of the MMAs.  (With hi AND lo in tensor memory only two slots fit next to the
+            // three accumulators, and the commit -> tcgen05.st -> arrive -> issue round trip, ~1500 clk, bounded the
+            // k-block period at (800 + 1500) / 2 clk in both the one-CTA and the first pair kernel.)
+            const uint64_t da_hi = umma_desc(a_sm + ks * 32);
+            const uint64_t db_hi = B_MN ? umma_desc_mn(b_hi + ks * 1024) : umma_desc(b_hi + ks * 32);
+            const uint64_t db_lo = B_MN ? umma_desc_mn(b_lo + ks * 1024) : umma_desc(b_lo + ks * 32);
+            const uint32_t dmain = tmem + (uint32_t)((kb & 1) * TC_BN);
+            umma_tf32_ss_pair(dmain, da_hi, db_hi, idesc, (kb >= 2 || ks != 0) ? 1u : 0u);
+            umma_tf32_ts_pair(tmem + 2 * TC_BN, a_lo + ks * 8, db_hi, idesc, (kb | ks) != 0);
+            umma_tf32_ss_pair(tmem + 2 * TC_BN, da_hi, db_lo, idesc, 1u);
+          }
+          umma_commit_pair(empty(s));
+        }
+        umma_commit_pair(acc_full);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int t128 = threadIdx.x - 128;
+    const int wq = warp & 3;
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    const uint32_t conv_leader0 = mapa_cluster(conv(0), 0), acc_free_leader = mapa_cluster(acc_free, 0);
+    int g = 0, ti = 0;
+    for (int t = pair; t < num_tiles; t += npairs, ++ti) {
+      for (int kb = 0; kb < nkb; ++kb, ++g) {
+        const int s = g % TP_STAGES;
+        mbar_wait(full(s), (uint32_t)((g / TP_STAGES) & 1));
+        const unsigned char* sa = gbase + (size_t)s * TP_STAGE_BYTES;
+        uint32_t xl[32];
+        const unsigned char* pa = sa + t128 * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 v = *reinterpret_cast<const uint4*>(pa + ((c ^ (t128 & 7)) << 4));
+          xl[4 * c] = v.x; xl[4 * c + 1] = v.y; xl[4 * c + 2] = v.z; xl[4 * c + 3] = v.w;
+        }
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          xl[r] = __float_as_uint(__uint_as_float(xl[r]) - __uint_as_float(xl[r] & 0xffffe000u));
+        if (!p.b_lo_tma) {  // this CTA's half of B_lo, elementwise in the landed (swizzled) layout
+          const float4* hi = reinterpret_cast<const float4*>(sa + TC_TILE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(const_cast<unsigned char*>(sa) + TC_TILE_BYTES + TP_HALF_BYTES);
+#pragma unroll
+          for (int j = 0; j < TP_HALF_BYTES / 16 / 128; ++j) {
+            const int i = t128 + 128 * j;
+            const float4 x = hi[i];
+            float4 l;
+            l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+            l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+            l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+            l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+            lo[i] = l;
+          }
+        }
+        // (slot s was last read by the MMAs of k-block g - TP_STAGES; the TMA warp waited for their commit before it
+        //  refilled stage s, and this thread saw that refill complete on full(s))
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem_st32(tmem + lane_base + TC_TMEM_A + (uint32_t)(s * 32), xl);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (!p.b_lo_tma) fence_async_smem();  // (the B_lo half written above is read by the MMAs through the async proxy)
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive_cluster(conv_leader0 + 8 * s);
+      }
+      // ---- epilogue, first half: own rows TMEM -> staging; then the accumulators are free again -------------------
+      mbar_wait(acc_full, (uint32_t)(ti & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (ti > 0) mbar_wait(stage_free, (uint32_t)((ti - 1) & 1));  // the store warps are done with the previous tile
+#pragma unroll 1
+      for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+        uint32_t r[32], q[32], o[32];
+        const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+              "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]),
+              "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]),
+              "=r"(q[25]), "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+            : "r"(taddr + (uint32_t)(2 * TC_BN)));
+        if (nkb > 1) {
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]), "=r"(o[8]),
+                "=r"(o[9]), "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15]), "=r"(o[16]),
+                "=r"(o[17]), "=r"(o[18]), "=r"(o[19]), "=r"(o[20]), "=r"(o[21]), "=r"(o[22]), "=r"(o[23]), "=r"(o[24]),
+                "=r"(o[25]), "=r"(o[26]), "=r"(o[27]), "=r"(o[28]), "=r"(o[29]), "=r"(o[30]), "=r"(o[31])
+              : "r"(taddr + (uint32_t)TC_BN));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = 0u;
+        }
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        unsigned char* srow = staging + (size_t)(c0 >> 5) * TC_TILE_BYTES + (size_t)(wq * 32 + lane) * 128;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 v = make_float4((__uint_as_float(r[j]) + __uint_as_float(o[j])) + __uint_as_float(q[j]),
+                                       (__uint_as_float(r[j + 1]) + __uint_as_float(o[j + 1])) + __uint_as_float(q[j + 1]),
+                                       (__uint_as_float(r[j + 2]) + __uint_as_float(o[j + 2])) + __uint_as_float(q[j + 2]),
+                                       (__uint_as_float(r[j + 3]) + __uint_as_float(o[j + 3])) + __uint_as_float(q[j + 3]));
+          *reinterpret_cast<float4*>(srow + ((((j >> 2) ^ (lane & 7))) << 4)) = v;
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive_cluster(acc_free_leader);  // this CTA's accumulators may be overwritten by the next tile
+      mbar_arrive(stage_full);               // (release: the staging writes above are visible to the store warps)
+    }
+  } else if (warp >= 8) {
+    // ---- epilogue, second half: staging -> bias / relu6 / mask -> global, overlapping the next tile's main loop ----
+    const int w8 = warp - 8;
+    int ti = 0;
+    for (int t = pair; t < num_tiles; t += npairs, ++ti) {
+      int m0, n0;
+      decode(t, m0, n0);
+      mbar_wait_sleep(stage_full, (uint32_t)(ti & 1), p.wait_ns);
+      const int n = n0 + lane * 4;
+      const bool n_ok = n < p.N;  // N % 4 == 0
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n_ok && (p.epi == TC_EPI_BIAS || p.epi == TC_EPI_BIAS_RELU6)) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+      const unsigned char* sbuf = staging + (size_t)(lane >> 3) * TC_TILE_BYTES;
+      const int rows_here = min(TC_BM, p.M - m0);  // (<= 0 for the peer CTA of a ragged last row block)
+      if (n_ok && rows_here > 0) {
+        float* crow = p.C + (size_t)m0 * p.ldc + n;
+#pragma unroll 1
+        for (int r0 = w8; r0 < rows_here; r0 += 32) {
+          float4 h[8];
+          if (p.epi == TC_EPI_MASK6) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int row = r0 + 4 * u;
+              h[u] = row < rows_here ? __ldg(reinterpret_cast<const float4*>(p.Hm + (size_t)(m0 + row) * p.ldh + n))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int row = r0 + 4 * u;
+            if (row >= rows_here) break;
+            float4 v = *reinterpret_cast<const float4*>(sbuf + (size_t)row * 128 + ((((lane & 7) ^ (row & 7))) << 4));
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            if (p.epi == TC_EPI_BIAS_RELU6) {
+              v.x = fminf(fmaxf(v.x, 0.f), 6.f); v.y = fminf(fmaxf(v.y, 0.f), 6.f);
+              v.z = fminf(fmaxf(v.z, 0.f), 6.f); v.w = fminf(fmaxf(v.w, 0.f), 6.f);
+            }
+            if (p.epi == TC_EPI_MASK6) {
+              v.x = (h[u].x > 0.f && h[u].x < 6.f) ? v.x : 0.f; v.y = (h[u].y > 0.f && h[u].y < 6.f) ? v.y : 0.f;
+              v.z = (h[u].z > 0.f && h[u].z < 6.f) ? v.z : 0.f; v.w = (h[u].w > 0.f && h[u].w < 6.f) ? v.w : 0.f;
+            }
+            *reinterpret_cast<float4*>(crow + (size_t)row * p.ldc) = v;
+          }
+        }
+      }
+      mbar_arrive(stage_free);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();  // the leader's MMAs read the peer's shared and tensor memory: nobody leaves before both are done
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -796,6 +1137,43 @@ static int tc_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUt
   return PFPN_OK;
 }
 
+// CTA-pair launch (K-major A): clusters of two CTAs, as many pairs as the device keeps resident at once (<= SMs / 2)
+template <bool B_MN>
+static int tc_launch_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBlo, const TcParams& p, int tiles_n,
+                          int num_tiles, cudaStream_t st) {
+  static int attr_dev = -1, max_pairs = 0;
+  int dev = 0;
+  PFPN_CUDA_OK(cudaGetDevice(&dev));
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cfg.blockDim = dim3(TCP_THREADS);
+  cfg.dynamicSmemBytes = TP_SMEM_BYTES;
+  cfg.stream = st;
+  if (dev != attr_dev) {
+    PFPN_CUDA_OK(cudaFuncSetAttribute((const void*)tc_gemm_pair_kernel<B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM_BYTES));
+    int sms = 0;
+    PFPN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cfg.gridDim = dim3((unsigned)(sms & ~1));
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, (const void*)tc_gemm_pair_kernel<B_MN>, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = sms / 2;
+    }
+    max_pairs = n < sms / 2 ? n : sms / 2;
+    attr_dev = dev;
+  }
+  const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  PFPN_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_gemm_pair_kernel<B_MN>, mapA, mapB, mapBlo, p, tiles_n, num_tiles));
+  return PFPN_OK;
+}
+
 static int tc_gemm_common(const float* A, int lda, const float* Bm, const float* Blo, int ldb, bool b_mn, float* Cout, int ldc,
                           const float* bias, const float* Hm, int ldh, int M, int N, int K, int epi, cudaStream_t st) {
   if (!A || !Bm || !Cout || M < 0 || N <= 0 || K <= 0 || epi < 0 || epi > 3) return PFPN_ERR_ARG;
@@ -805,14 +1183,25 @@ static int tc_gemm_common(const float* A, int lda, const float* Bm, const float*
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   if ((lda & 3) || (ldb & 3) || (ldc & 3) || (N & 3) || (K & 3) || !al16(A) || !al16(Bm) || !al16(Cout) || !al16(Blo))
     return PFPN_ERR_ALIGN;
+  // PFPN_TC_PAIR (default 1): two-SM MMAs (tcgen05 cta_group::2) once there are at least two row blocks
+  static const int pair_on = []() {
+    const char* e = getenv("PFPN_TC_PAIR");
+    return e ? atoi(e) : 1;
+  }();
+  const bool use_pair = pair_on && M > TC_BM;
   CUtensorMap mapA, mapB, mapBlo;
   int rc = make_map(&mapA, A, M, K, lda, TC_BM);
   if (rc != PFPN_OK) return rc;
-  rc = make_map(&mapB, Bm, N, K, ldb, TC_BN, b_mn);
+  rc = make_map(&mapB, Bm, N, K, ldb, use_pair ? TC_BN / 2 : TC_BN, b_mn);
   if (rc != PFPN_OK) return rc;
-  rc = make_map(&mapBlo, Blo ? Blo : Bm, N, K, ldb, TC_BN, b_mn);
+  rc = make_map(&mapBlo, Blo ? Blo : Bm, N, K, ldb, use_pair ? TC_BN / 2 : TC_BN, b_mn);
   if (rc != PFPN_OK) return rc;
   TcParams p{Cout, bias, Hm, M, N, K, ldc, ldh, epi, (K + TC_BK - 1) / TC_BK * TC_BK, nullptr, pfpn_wait_ns(64u), Blo ? 1 : 0};
+  if (use_pair) {
+    const int tiles_n = (N + TC_BN - 1) / TC_BN, tiles_m2 = (M + 2 * TC_BM - 1) / (2 * TC_BM);
+    return b_mn ? tc_launch_pair<true>(mapA, mapB, mapBlo, p, tiles_n, tiles_n * tiles_m2, st)
+                : tc_launch_pair<false>(mapA, mapB, mapBlo, p, tiles_n, tiles_n * tiles_m2, st);
+  }
   dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
   return b_mn ? tc_launch<false, true>(mapA, mapB, mapBlo, p, grid, st) : tc_launch<false, false>(mapA, mapB, mapBlo, p, grid, st);
 }

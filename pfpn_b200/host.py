@@ -9,12 +9,39 @@ is either a cudaMemcpyAsync or one of our kernels.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
 
 from . import _cabi
 from . import head as _head
+
+
+def bind_host_to_gpu(device_index: int) -> Optional[str]:
+    """Pin this process to the CPUs next to GPU `device_index` (NVML's ideal CPU set, cut to what the process may use),
+    so that the pinned host buffers allocated afterwards land on the GPU's own NUMA node.  With one process per GPU on a
+    multi-socket host this decides whether the host<->device copies cross the socket interconnect.  Returns the CPU list
+    as a string, or None when NVML / the affinity call is unavailable (nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(device_index)
+        try:
+            bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:  # noqa: BLE001 -- older torch: fall back to the NVML index
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        ideal = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        cpus = sorted(ideal & os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"{cpus[0]}-{cpus[-1]} ({len(cpus)} cpus)"
+    except Exception:  # noqa: BLE001 -- binding is an optimisation, never a requirement
+        return None
 
 
 class HostHeadPipeline:

@@ -112,3 +112,42 @@ def test_presplit_weight_operand_is_bit_identical(cuda_dev, M, N, K):
     _cabi.check(_cabi.pfpn_tc_gemm_nt_lo(dY.data_ptr(), N, W.data_ptr(), Wlo.data_ptr(), N, D1.data_ptr(), K, None, X.data_ptr(), K,
                                          M, K, N, 3, st))
     assert torch.equal(D0, D1)
+
+
+_FORMS = r"""
+import hashlib, sys, torch
+from pfpn_b200 import _cabi
+from pfpn_b200.head import _stream_ptr
+dev = torch.device("cuda:0"); st = _stream_ptr(); h = hashlib.sha256()
+for (M, N, K) in [(256, 128, 32), (1000, 1260, 512), (4100, 512, 1024), (8192, 1024, 200), (129, 132, 36)]:
+    g = torch.Generator().manual_seed(M + N)
+    X = torch.randn(M, K, generator=g).to(dev); W = (torch.randn(K, N, generator=g) * 0.05).to(dev)
+    b = torch.randn(N, generator=g).to(dev); dY = torch.randn(M, N, generator=g).to(dev)
+    Wlo = torch.empty_like(W); _cabi.check(_cabi.pfpn_split_lo(W.data_ptr(), Wlo.data_ptr(), W.numel(), st))
+    Y = torch.empty(M, N, device=dev); D = torch.empty(M, K, device=dev); D2 = torch.empty(M, K, device=dev)
+    _cabi.check(_cabi.pfpn_tc_gemm_nn_lo(X.data_ptr(), K, W.data_ptr(), Wlo.data_ptr(), N, Y.data_ptr(), N, b.data_ptr(), None, 0, M, N, K, 2, st))
+    _cabi.check(_cabi.pfpn_tc_gemm_nt_lo(dY.data_ptr(), N, W.data_ptr(), Wlo.data_ptr(), N, D.data_ptr(), K, None, X.data_ptr(), K, M, K, N, 3, st))
+    _cabi.check(_cabi.pfpn_tc_gemm_nt(dY.data_ptr(), N, W.data_ptr(), N, D2.data_ptr(), K, None, X.data_ptr(), K, M, K, N, 0, st))
+    torch.cuda.synchronize()
+    for t in (Y, D, D2):
+        h.update(t.cpu().numpy().tobytes())
+print("HASH", h.hexdigest())
+"""
+
+
+def test_cta_pair_form_is_bit_identical_to_the_one_cta_forms(cuda_dev):
+    """The cta_group::2 kernel (default for M > 128) against the persistent one-CTA kernel and the one-tile kernel: the same
+    products reach the same accumulators in the same order, so every output bit must agree (ragged M, N, K included).
+    The form is chosen once per process (PFPN_TC_PAIR / PFPN_TC_PERSISTENT), hence three child processes."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hashes = []
+    for env in ({"PFPN_TC_PAIR": "1"}, {"PFPN_TC_PAIR": "0"}, {"PFPN_TC_PAIR": "0", "PFPN_TC_PERSISTENT": "0"}):
+        e = dict(os.environ, **env)
+        e["PYTHONPATH"] = root + os.pathsep + e.get("PYTHONPATH", "")
+        r = subprocess.run([sys.executable, "-c", _FORMS], capture_output=True, text=True, timeout=300, env=e, cwd=root)
+        assert r.returncode == 0, r.stderr[-2000:]
+        hashes.append([l for l in r.stdout.splitlines() if l.startswith("HASH")][-1])
+    assert hashes[0] == hashes[1] == hashes[2], hashes

@@ -17,7 +17,9 @@ for (N, K) in [(1024, 200), (512, 1024), (1260, 512), (1024, 512), (512, 1260)]:
     A = torch.randn(M, K, device=dev); Bt = torch.randn(N, K, device=dev) * 0.05; W = Bt.t().contiguous()
     b = torch.randn(N, device=dev); C = torch.empty(M, N, device=dev); C2 = torch.empty(M, N, device=dev)
     st = _stream_ptr()
-    tc = lambda: _cabi.check(_cabi.pfpn_tc_gemm_nt(A.data_ptr(), K, Bt.data_ptr(), K, C.data_ptr(), N, b.data_ptr(), None, 0, M, N, K, 2, st))
+    Blo = torch.empty_like(Bt); _cabi.check(_cabi.pfpn_split_lo(Bt.data_ptr(), Blo.data_ptr(), Bt.numel(), st))
+    # the production form: weight low halves pre-split once per optimizer step, persistent kernel
+    tc = lambda: _cabi.check(_cabi.pfpn_tc_gemm_nt_lo(A.data_ptr(), K, Bt.data_ptr(), Blo.data_ptr(), K, C.data_ptr(), N, b.data_ptr(), None, 0, M, N, K, 2, st))
     ff = lambda: _cabi.check(_cabi.pfpn_mlp_linear_fwd(A.data_ptr(), K, W.data_ptr(), b.data_ptr(), C2.data_ptr(), N, M, K, N, 1, st))
     ms_tc, ms_ff = t(tc), t(ff)
     ref = (A.double() @ Bt.double().t() + b.double()).clamp(0, 6)
