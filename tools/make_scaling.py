@@ -15,7 +15,7 @@ json.dump(lines, open(os.path.join(ROOT, "profiles", f"{rnd}_bench_lines.json"),
 base = lines.get(1)
 out = [f"# {rnd}: scaling of `bench.py` over 1 / 2 / 4 / 8 B200 (builder-run; the driver's SCALE record is the judged one)\n",
        "Head step = adv-stats + fused head fwd+bwd (PPO) over 65536 states PER GPU (weak scaling); the `[2,A,P]` exchange is pushed by "
-       "K1's finalize kernel and consumed on a second stream.  DPPO update = c4, 65536 states in total sharded over the GPUs "
+       "K1's finalize kernel as {value, sequence} packets and summed by the next step's finalize kernel.  DPPO update = c4, 65536 states in total sharded over the GPUs "
        "(strong scaling).  c5 = fused SAC head, 10^6 states in total.\n",
        "| N | head ms/step | head samples/s | weak eff. | K1 roofline frac | DPPO ms/update | strong eff. | c5 fused M states/s | c5 frac of 8(d) roofline | e2e samples/s | xcheck |",
        "|---|---|---|---|---|---|---|---|---|---|---|"]
