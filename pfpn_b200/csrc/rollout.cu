@@ -224,40 +224,48 @@ __global__ void __launch_bounds__(SLOTS * 72 + 32, 2) rollout_kernel(const Rollo
       const float total = c34;
       Hs += __shfl_xor_sync(0xffffffffu, Hs, 1);
       // ---- the draw ---------------------------------------------------------------------------------------------
+      // (lane 0 of the row generates the uniform's Philox block, lane 1 the normal's -- the same instructions, different
+      //  counters -- and they swap through two shuffles: one block per lane instead of two)
       double u;
+      uint32_t qnx = 0u, qny = 0u;
       if (kp.a.ext_uniform != nullptr) {
         u = kp.a.ext_uniform[r];
       } else {
-        const uint4 q = rng(kp.a.offset, (uint64_t)r);
-        u = u64_to_unit_double(q.x, q.y);
+        const uint4 q = rng(kp.a.offset + (uint64_t)c, (uint64_t)r);
+        const uint32_t ox = __shfl_xor_sync(0xffffffffu, q.x, 1), oy = __shfl_xor_sync(0xffffffffu, q.y, 1);
+        u = c == 0 ? u64_to_unit_double(q.x, q.y) : u64_to_unit_double(ox, oy);
+        qnx = c == 0 ? ox : q.x;
+        qny = c == 0 ? oy : q.y;
       }
       const float to_find = (float)(u * (double)total);
       const float margin = 2.f * delta * total + 1.2e-7f * total;
-      int cnt = 0;
-      bool near = false;
-      float run = 0.f;  // (the same additions, in the same order, as T above)
+      // d_k = cdf_k - to_find, accumulated directly (run starts at base - to_find: one add per particle); the index is the
+      // number of d_k < 0 -- the sign bits -- and the row is uncertain iff min |d_k| <= margin (d_k == 0 included, so the
+      // difference between "< 0" and TF's "<= to_find" is always decided by the exact path).  Three instructions per particle.
+      unsigned cnt = 0u;
+      float dmin = 3.402823466e38f;
+      float run = base - to_find;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         run += e1[i];
-        const float cv = base + run;
-        cnt += cv <= to_find ? 1 : 0;
-        near = near || fabsf(cv - to_find) <= margin;
+        cnt += __float_as_uint(run) >> 31;
+        dmin = fminf(dmin, fabsf(run));
       }
       {  // the three tail values: lane 0 counts particles 32 and 34, lane 1 particle 33
-        const float ca = c == 0 ? c32 : c33;
-        cnt += ca <= to_find ? 1 : 0;
-        near = near || fabsf(ca - to_find) <= margin;
-        if (c == 0) {
-          cnt += c34 <= to_find ? 1 : 0;
-          near = near || fabsf(c34 - to_find) <= margin;
-        }
+        const float da = (c == 0 ? c32 : c33) - to_find;
+        cnt += __float_as_uint(da) >> 31;
+        dmin = fminf(dmin, fabsf(da));
+        const float db = c == 0 ? c34 - to_find : 1.f;  // (lane 1: a positive dummy that cannot be the minimum... of interest)
+        cnt += c == 0 ? __float_as_uint(db) >> 31 : 0u;
+        dmin = c == 0 ? fminf(dmin, fabsf(db)) : dmin;
       }
+      bool near = !(dmin > margin);  // (NaN -> near)
       cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
       {  // (no short-circuit around the shuffle: every lane must execute it)
         const int near_o = __shfl_xor_sync(0xffffffffu, (int)near, 1);
         near = near || near_o != 0;
       }
-      int idx = cnt;
+      int idx = (int)cnt;
       const bool fallback = near || idx >= P || !(total > 0.f) || !isfinite(total) || degenerate;
       // rows that need the literal fp64 algorithm (~0.1 %): one at a time, by the whole warp, in warp-uniform control flow
       unsigned fb_mask = __ballot_sync(0xffffffffu, fallback && c == 0);
@@ -276,22 +284,22 @@ __global__ void __launch_bounds__(SLOTS * 72 + 32, 2) rollout_kernel(const Rollo
       if (kp.a.ext_normal != nullptr) {
         eps = __ldg(&kp.a.ext_normal[r * P + idx]);
       } else {
-        const uint4 q = rng(kp.a.offset + 1, (uint64_t)r);
-        eps = __fsqrt_rn(-2.f * logf(u32_to_unit_open(q.x))) * cospif(2.f * u32_to_unit_open(q.y));  // (= K2's sqrtf)
+        eps = __fsqrt_rn(-2.f * logf(u32_to_unit_open(qnx))) * cospif(2.f * u32_to_unit_open(qny));  // (= K2's sqrtf)
       }
       const float mu_s = __ldg(&kp.a.loc[a * P + idx]), sd_s = expf(__ldg(&kp.a.logstd[a * P + idx]));
       const float v = __fadd_rn(__fmul_rn(eps, sd_s), mu_s);
       // ---- log_prob of the action (utils.py:108-134, plain variant), entropy (:146-151), statistics (a2c.py:346-365) ---
       const float is1 = rcpf(total);
+      const float is1s = row_ok ? is1 : 0.f;  // (a masked row adds probability 0: max(vmax, 0) = vmax, vsum + 0)
       float S2 = 0.f;
 #pragma unroll
       for (int i = 0; i < EPL; ++i) {
         const float z = fmaf(v, csp[(i * 3 + 0) * TPS], csp[(i * 3 + 1) * TPS]);
         const float n = ex2f(fmaf(z * z, -0.5f * kLog2e, csp[(i * 3 + 2) * TPS]));
         S2 = fmaf(e1[i], n, S2);  // (e1 == 0 for "not a particle")
-        const float pr = e1[i] * is1;
-        vmax[i] = row_ok ? fmaxf(vmax[i], pr) : vmax[i];
-        vsum[i] += row_ok ? pr : 0.f;
+        const float pr = e1[i] * is1s;
+        vmax[i] = fmaxf(vmax[i], pr);
+        vsum[i] += pr;
       }
       __syncwarp();
       S2 += __shfl_xor_sync(0xffffffffu, S2, 1);
