@@ -27,6 +27,10 @@
 namespace pfpn {
 
 constexpr int kRoMaxCtas = 148 * 2;
+// value a non-finite logit (and the unused 36th half-slot) is replaced by: far below any logit that can matter, yet
+// d = kRoExcluded - max stays finite, so no clamp is needed before 0 * d (rows whose maximum is not above it take the
+// literal fp64 path, which reads the raw logits)
+constexpr float kRoExcluded = -1e30f;
 
 struct RolloutK {
   pfpn_rollout_args a;
@@ -85,8 +89,9 @@ __global__ void __launch_bounds__(SLOTS * 72 + 32, 2) rollout_kernel(const Rollo
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* done_bar = full_bar + NSTAGE;
   float2* rowbuf = reinterpret_cast<float2*>(tail + 16 * NSTAGE);  // [NSTAGE][SLOTS * A] per-row (log p, H)
-  float* cs = reinterpret_cast<float*>(rowbuf + NSTAGE * SLOTS * A);  // [EPL * 3][A * LPR] per-thread-column constants
-  double* fb_s = reinterpret_cast<double*>(cs + EPL * 3 * A * LPR);  // [compute warps][40] fp64 fallback scratch
+  float4* cs = reinterpret_cast<float4*>(rowbuf + NSTAGE * SLOTS * A);  // [EPL][A * LPR] per-thread-column constants (one LDS.128)
+  float2* musd = reinterpret_cast<float2*>(cs + EPL * A * LPR);         // [AP] {loc, exp(logstd)} of the sampled particle
+  double* fb_s = reinterpret_cast<double*>(musd + AP);                  // [compute warps][40] fp64 fallback scratch
   float* red = reinterpret_cast<float*>(smem_raw);  // [SLOTS][2][AP] end-of-kernel combine, aliases the (then idle) stages
   static_assert(SLOTS * 2 * AP * 4 <= NSTAGE * STAGE_BYTES, "the combine tables reuse the stage ring");
 
@@ -151,7 +156,7 @@ __global__ void __launch_bounds__(SLOTS * 72 + 32, 2) rollout_kernel(const Rollo
     auto kof = [&](int i) -> int { return i < 16 ? 16 * c + i : (i == 16 ? 32 + c : 34); };
     // per-(a,k) constants {1/sigma, -mu/sigma, -(logstd + ln sqrt(2 pi)) log2 e} in shared memory, one column per thread
     // of a state slot (conflict-free); the statistics accumulators stay in registers
-    float* csp = cs + rem;
+    float4* csp = cs + rem;
     constexpr int TPS = A * LPR;
     float vmax[EPL], vsum[EPL];
 #pragma unroll
@@ -161,9 +166,8 @@ __global__ void __launch_bounds__(SLOTS * 72 + 32, 2) rollout_kernel(const Rollo
       const float ls = __ldg(&kp.a.logstd[a * P + k]), mu = __ldg(&kp.a.loc[a * P + k]);
       const float is_ = ok ? expf(-ls) : 0.f;
       if (slot == 0) {
-        csp[(i * 3 + 0) * TPS] = is_;
-        csp[(i * 3 + 1) * TPS] = ok ? -mu * is_ : 0.f;
-        csp[(i * 3 + 2) * TPS] = ok ? -(ls + kHalfLog2Pi) * kLog2e : 0.f;
+        csp[i * TPS] = make_float4(is_, ok ? -mu * is_ : 0.f, ok ? -(ls + kHalfLog2Pi) * kLog2e : 0.f, 0.f);
+        if (ok) musd[a * P + k] = make_float2(mu, expf(ls));  // (expf as K2 evaluates it: the same action bits)
       }
       vmax[i] = 0.f;
       vsum[i] = 0.f;
@@ -200,15 +204,15 @@ __global__ void __launch_bounds__(SLOTS * 72 + 32, 2) rollout_kernel(const Rollo
       for (int i = 0; i < EPL; ++i) {
         const bool ok = i < 17 || c == 0;
         const float x = ok ? lg[kof(i)] : -3.402823466e38f;
-        e1[i] = fabsf(x) <= 3.402823466e38f ? x : -3.402823466e38f;
+        e1[i] = (fabsf(x) <= 3.402823466e38f && ok) ? x : kRoExcluded;
         m = fmaxf(m, e1[i]);
       }
       m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-      const bool degenerate = !(m > -3.402823466e38f);  // no finite logit at all: the literal algorithm decides
+      const bool degenerate = !(m > kRoExcluded);  // no usable logit at all (or all below -1e30): the literal algorithm decides
       float T = 0.f, Hs = 0.f;  // block total (slots < 16); sum e (l - m) for the entropy
 #pragma unroll
       for (int i = 0; i < EPL; ++i) {
-        const float d = fmaxf(e1[i] - m, -1e30f);  // (finite: 0 * d below stays 0)
+        const float d = e1[i] - m;  // (an excluded slot: -1e30 - m, finite, its term 2^(d log2 e) exactly 0 and 0 * d = -0)
         const float e = ex2f(d * kLog2e);
         Hs = fmaf(e, d, Hs);
         e1[i] = e;
@@ -286,16 +290,17 @@ __global__ void __launch_bounds__(SLOTS * 72 + 32, 2) rollout_kernel(const Rollo
       } else {
         eps = __fsqrt_rn(-2.f * logf(u32_to_unit_open(qnx))) * cospif(2.f * u32_to_unit_open(qny));  // (= K2's sqrtf)
       }
-      const float mu_s = __ldg(&kp.a.loc[a * P + idx]), sd_s = expf(__ldg(&kp.a.logstd[a * P + idx]));
-      const float v = __fadd_rn(__fmul_rn(eps, sd_s), mu_s);
+      const float2 ms_ = musd[a * P + idx];  // (shared-memory table: a dependent global load here was 5 % of all stall samples)
+      const float v = __fadd_rn(__fmul_rn(eps, ms_.y), ms_.x);
       // ---- log_prob of the action (utils.py:108-134, plain variant), entropy (:146-151), statistics (a2c.py:346-365) ---
       const float is1 = rcpf(total);
       const float is1s = row_ok ? is1 : 0.f;  // (a masked row adds probability 0: max(vmax, 0) = vmax, vsum + 0)
       float S2 = 0.f;
 #pragma unroll
       for (int i = 0; i < EPL; ++i) {
-        const float z = fmaf(v, csp[(i * 3 + 0) * TPS], csp[(i * 3 + 1) * TPS]);
-        const float n = ex2f(fmaf(z * z, -0.5f * kLog2e, csp[(i * 3 + 2) * TPS]));
+        const float4 q4 = csp[i * TPS];
+        const float z = fmaf(v, q4.x, q4.y);
+        const float n = ex2f(fmaf(z * z, -0.5f * kLog2e, q4.z));
         S2 = fmaf(e1[i], n, S2);  // (e1 == 0 for "not a particle")
         const float pr = e1[i] * is1s;
         vmax[i] = fmaxf(vmax[i], pr);
@@ -303,8 +308,9 @@ __global__ void __launch_bounds__(SLOTS * 72 + 32, 2) rollout_kernel(const Rollo
       }
       __syncwarp();
       S2 += __shfl_xor_sync(0xffffffffu, S2, 1);
-      const float lnp = kLn2 * (lg2f(S2) - lg2f(total));  // -inf when every term underflowed (p == 0)
-      const float Hval = logf(total) - Hs * is1;            // sum_k p_k (ln s1 - (l_k - m))
+      const float l2t = lg2f(total);
+      const float lnp = kLn2 * (lg2f(S2) - l2t);  // -inf when every term underflowed (p == 0)
+      const float Hval = fmaf(kLn2, l2t, -Hs * is1);  // sum_k p_k (ln s1 - (l_k - m))
       if (c == 0) {
         rowbuf[st * SLOTS * A + slot * A + a] = row_ok ? make_float2(lnp, Hval) : make_float2(0.f, 0.f);
         if (row_ok) {
@@ -389,9 +395,9 @@ extern "C" int pfpn_head_rollout(const pfpn_rollout_args* args, void* workspace,
   size_t need;
   pfpn_rollout_workspace_bytes(a.A, a.P, &need);
   if (stats && (!workspace || workspace_bytes < need)) return PFPN_ERR_WORKSPACE;
-  constexpr int SLOTS = 4, NSTAGE = 4, AP = 36 * 35;
+  constexpr int SLOTS = 4, NSTAGE = 3, AP = 36 * 35;  // (3 stages x 2 CTAs per SM = 120 KB of loads in flight per SM)
   constexpr int stage_bytes = (SLOTS * AP * 4 + 127) & ~127;
-  constexpr int smem = NSTAGE * stage_bytes + 16 * NSTAGE + NSTAGE * SLOTS * 36 * 8 + 18 * 3 * 72 * 4 + 9 * 40 * 8 + 128;
+  constexpr int smem = NSTAGE * stage_bytes + 16 * NSTAGE + NSTAGE * SLOTS * 36 * 8 + 18 * 72 * 16 + AP * 8 + 9 * 40 * 8 + 128;
   int dev = 0, sms = 0;
   PFPN_CUDA_OK(cudaGetDevice(&dev));
   PFPN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
