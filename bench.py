@@ -334,7 +334,8 @@ def main():
                 flat_small[0].copy_(dloc)
                 flat_small[1].copy_(dlogstd)
                 dist.all_reduce(flat_small)
-    launches_per_step = 3  # adv_stats, K1, K1 finalize (+ push + the previous exchange's sum at N > 1)
+    # adv_stats, K1, K1 finalize (which also pushes and sums the previous exchange at N > 1); NCCL fallback: + 2 copies + all-reduce
+    launches_per_step = 3 if (use_peer or world == 1) else 6
 
     def drain():
         while use_peer and gather.pending > 0:  # the last exchange(s): consumed inside the timed region

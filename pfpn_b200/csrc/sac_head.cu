@@ -188,6 +188,10 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
     const int kb0 = 16 * (c >> 2) + (c & 3);
     const int pb0 = 8 * (c >> 2) + (c & 3);  // this lane's offset inside a permuted 32-block of the float2 tables
     const bool tail_ok = c < P - 96;  // slot (u = 0, j = 3): particle 96 + kb0
+    // (opaque copies: under the 96-register cap the compiler otherwise re-derives slot / a / c / kb0 / pb0 from
+    //  threadIdx.x at every use inside the tile loop -- 5 % of the executed instructions in the first profile)
+    int kb0_p = kb0, pb0_p = pb0, rowoff_p = slot * AP + a * P, sa_p = slot * A + a;
+    asm volatile("" : "+r"(kb0_p), "+r"(pb0_p), "+r"(rowoff_p), "+r"(sa_p));
     const float2* ms_r = ms_s + a * P;
     const float2* mi_r = mi_s + a * P;
     const float* cst_r = cst_s + a * P;
@@ -196,14 +200,14 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
 #pragma unroll
     for (int i = 0; i < NP; ++i) acc1[i] = acc2[i] = make_float2(0.f, 0.f);
 
-    for (int it = 0; it < my_tiles; ++it) {
-      const int st = it % NSTAGE;
-      const int tile = first_tile + it * tile_step;
+    int st = 0;
+    uint32_t ph = 0u;
+    for (int it = 0, tile = first_tile; it < my_tiles; ++it, tile += tile_step, ph ^= (st == NSTAGE - 1), st = (st == NSTAGE - 1) ? 0 : st + 1) {
       float* sbuf = reinterpret_cast<float*>(stage0 + (size_t)st * STAGE_BYTES);
       const bool is_tail = tail_exists && tile == tail_tile;
       const int b0 = tile * SLOTS;
       if (!is_tail) {
-        mbar_wait(smem_u32(&full_bar[st]), (uint32_t)((it / NSTAGE) & 1));
+        mbar_wait(smem_u32(&full_bar[st]), ph);
       } else {
         const int nvalid = (B - b0) * AP;
         for (int i = tid; i < nvalid; i += NTHR) sbuf[i] = __ldg(&g_logits[(size_t)b0 * AP + i]);
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
       const int b = b0 + slot;
       const bool row_ok = b < B;
       const long long r = (long long)(row_ok ? b : b0) * A + a;  // (masked rows recompute state b0, results discarded)
-      float* lg = sbuf + (row_ok ? slot : 0) * AP + a * P;
+      float* lg = sbuf + (row_ok ? rowoff_p : a * P);
 
       // ---- step 1: draws, noisy logits (log2 domain), locations -----------------------------------------------
       // Slots are kept as register PAIRS (slot e -> pair e / 2, half e % 2) so that steps 3 / 4 run on packed fp32x2
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
       int kmax = 0;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int kb = 4 * u + kb0;
+        const int kb = 4 * u + kb0_p;
         const int nj = u == 0 ? 4 : 3;  // particles >= 100: only slot (0, 3) exists
         float n4[4], nl4[4], ya4[4];
         if (FAST) {
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
           const int k = kb + 32 * j;
           const bool ok = j < 3 || tail_ok;
           const float x = ok ? lg[k] : 0.f;
-          const float2 ms = ms_r[ok ? 32 * j + 16 * (u >> 1) + 4 * (u & 1) + pb0 : 0];  // {mu, sigma}, permuted table
+          const float2 ms = ms_r[ok ? 32 * j + 16 * (u >> 1) + 4 * (u & 1) + pb0_p : 0];  // {mu, sigma}, permuted table
           const float yf = ok ? fmaf(x, kLog2e, -(FAST ? lg2f(nl4[j]) : log2f(nl4[j]))) : -3.402823466e38f;
           const float ycmp = FAST ? yf : (ok ? x + ya4[j] : -3.402823466e38f);  // (G + logits) / T, T = 1
           const float pk = FAST ? fmaf(n4[j], ms.y, ms.x) : __fadd_rn(__fmul_rn(n4[j], ms.y), ms.x);
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
           const bool take = FAST ? (ycmp > ymax) : (ycmp > ymax || (ycmp == ymax && k < kmax));  // ties -> smallest index (tf.argmax)
           if (take) {
             ymax = ycmp;
-            yfm = yf;
+            if (!FAST) yfm = yf;  // (FAST: the comparison key IS yf)
             kmax = k;
             pmax = pk;
           }
@@ -280,13 +284,13 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
       // ---- step 2: row argmax over the 8 lanes, carrying the winner's location --------------------------------
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) {
-        const float oy = __shfl_xor_sync(0xffffffffu, ymax, o), of = __shfl_xor_sync(0xffffffffu, yfm, o);
+        const float oy = __shfl_xor_sync(0xffffffffu, ymax, o), of = FAST ? 0.f : __shfl_xor_sync(0xffffffffu, yfm, o);
         const float op = __shfl_xor_sync(0xffffffffu, pmax, o);
         const int ok_ = __shfl_xor_sync(0xffffffffu, kmax, o);
         const bool take = oy > ymax || (oy == ymax && ok_ < kmax);
         if (take) {
           ymax = oy;
-          yfm = of;
+          if (!FAST) yfm = of;
           kmax = ok_;
           pmax = op;
         }
@@ -302,14 +306,15 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
       // slot e of this lane <-> particle k = 4 u + kb0 + 32 j, (u, j) = (e / 3, e % 3) for e < 12, (0, 3) for e = 12
       auto slot_k = [&](int e) -> int {
         const int u = e < 12 ? e / 3 : 0, j = e < 12 ? e % 3 : 3;
-        const int k = 4 * u + kb0 + 32 * j;
+        const int k = 4 * u + kb0_p + 32 * j;
         return (e < 12 || (e == 12 && tail_ok)) ? k : 0;  // masked half-slots read entry 0 (their terms are exactly 0)
       };
       auto slot_p = [&](int e) -> int {  // position of slot e's particle in the permuted float2 tables
         const int u = e < 12 ? e / 3 : 0, j = e < 12 ? e % 3 : 3;
-        const int q = 32 * j + 16 * (u >> 1) + 4 * (u & 1) + pb0;
+        const int q = 32 * j + 16 * (u >> 1) + 4 * (u & 1) + pb0_p;
         return (e < 12 || (e == 12 && tail_ok)) ? q : 0;
       };
+      if (FAST) yfm = ymax;
       const float2 uu2 = splat2(uu), nyf2 = splat2(-yfm), one2 = splat2(1.f), mtwo2 = splat2(-2.f);
       const float2 tl2 = splat2(2.f * kLog2e), nhl2 = splat2(-0.5f * kLog2e);
       float2 S1v = splat2(0.f), S2v = S1v, Tv = S1v, Swv = S1v, Swtv = S1v;
@@ -355,7 +360,7 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
       const float g = row_ok ? __ldg(&kp.a.g_lp[b]) : 0.f;
       const float g_row = p_ok ? g : 0.f;                       // guard of utils.py:109-117
       const float gs2 = p_ok ? g_row * rcpf(S2) : 0.f;
-      const float ga = row_ok ? sbuf[TILE_F + slot * A + a] : 0.f;
+      const float ga = row_ok ? sbuf[TILE_F + sa_p] : 0.f;
       const float gu = fmaf(g_row, 2.f * t, -T * gs2);          // dL/du through log_prob: g (-sum r z / sigma + 2 tanh u)
       const float coef = fmaf(gu, rcpf(fmaxf(1e-6f, omt2)), ga);  // mask + mask2 (utils.py:164-183)
       const float iw = rcpf(Sw);
@@ -393,7 +398,7 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
         kp.a.s_pre[o] = uu;
         kp.a.idx[o] = arg;
       }
-      if (c == 0) rowbuf[st * SLOTS * A + slot * A + a] = row_ok ? lnp : 0.f;
+      if (c == 0) rowbuf[st * SLOTS * A + sa_p] = row_ok ? lnp : 0.f;
       if (is_tail) {  // ragged last tile: plain stores of the valid part
         asm volatile("bar.sync 1, %0;" ::"r"(NTHR) : "memory");
         const int nvalid = (B - b0) * AP;
