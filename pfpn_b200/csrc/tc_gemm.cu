@@ -1126,7 +1126,8 @@ static int tc_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUt
       PFPN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
       attr_dev_p = dev;
     }
-    const int ctas = num_tiles < sms ? num_tiles : sms;
+    const int per_cta = (num_tiles + sms - 1) / sms;
+    const int ctas = (num_tiles + per_cta - 1) / per_cta;  // (balanced: see tc_launch_pair)
     tc_gemm_persist_kernel<A_MN, B_MN><<<ctas, TCP_THREADS, TCP_SMEM_BYTES, st>>>(mapA, mapB, mapBlo, p, (int)grid.y, (int)grid.x,
                                                                                   num_tiles);
     PFPN_CUDA_OK(cudaGetLastError());
@@ -1168,7 +1169,11 @@ static int tc_launch_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, cons
     max_pairs = n < sms / 2 ? n : sms / 2;
     attr_dev = dev;
   }
-  const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
+  // balanced grid: every pair walks the same number of tiles (ceil), and no more pairs are launched than that needs --
+  // the SMs left over serve the kernels of the other streams (critic branch, weight gradients) instead of idling through
+  // a ragged last wave (8192 rows x N=1024: 256 tiles = 64 pairs x 4, not 74 pairs x 3.46)
+  const int per_pair = (num_tiles + max_pairs - 1) / max_pairs;
+  const int pairs = (num_tiles + per_pair - 1) / per_pair;
   cfg.gridDim = dim3((unsigned)(2 * pairs));
   PFPN_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_gemm_pair_kernel<B_MN>, mapA, mapB, mapBlo, p, tiles_n, num_tiles));
   return PFPN_OK;

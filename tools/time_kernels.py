@@ -1,4 +1,4 @@
-"""Time K3f, K2f and the DPPO update for one setting of PFPN_WAIT_NS (producer back-off); one JSON line."""
+"""Time K3f, K2f and the DPPO update (optionally under one setting of PFPN_WAIT_NS, the producers' back-off); one JSON line."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
