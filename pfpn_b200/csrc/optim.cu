@@ -99,9 +99,21 @@ __global__ void normalizer_finalize_kernel(const double* __restrict__ part, int 
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= S) return;
   double s = 0.0, q = 0.0;
-  for (int i = 0; i < nblk; ++i) {
-    s += part[((size_t)i * 2 + 0) * S + k];
-    q += part[((size_t)i * 2 + 1) * S + k];
+  for (int i0 = 0; i0 < nblk; i0 += 8) {  // loads batched eight partial pairs deep, additions in the same fixed order
+    double xs[8], xq[8];                   // (one dependent L2 round trip per partial made this 34 us at 296 partials)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const bool ok = i0 + u < nblk;
+      xs[u] = ok ? __ldcg(&part[((size_t)(i0 + u) * 2 + 0) * S + k]) : 0.0;
+      xq[u] = ok ? __ldcg(&part[((size_t)(i0 + u) * 2 + 1) * S + k]) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (i0 + u < nblk) {
+        s += xs[u];
+        q += xq[u];
+      }
+    }
   }
   const double mean = s / B;
   double var = q / B - mean * mean;

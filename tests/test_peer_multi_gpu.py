@@ -8,13 +8,20 @@ import sys
 import pytest
 import torch
 
+
+def _free_port() -> int:
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_fused_peer_allreduce_adam_matches_nccl():
-    port = 29600 + os.getpid() % 300
+    port = _free_port()
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "run_peer_ngpu.py")],
                        capture_output=True, text=True, timeout=600)
@@ -30,7 +37,7 @@ def test_fused_peer_allreduce_adam_matches_nccl():
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_sac_learner_replicas_stay_identical_across_a_resample_tick():
-    port = 29300 + os.getpid() % 300
+    port = _free_port()
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "run_sac_ngpu.py")],
                        capture_output=True, text=True, timeout=600)
