@@ -97,7 +97,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "10"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -360,6 +360,7 @@ def main():
         evs[i + 1].record(stream)
     barrier()
     per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
+    clocks = sampler.stop() if sampler else None  # (sampled during the timed region only: the poller must not run under the other legs)
     local_ms = evs[0].elapsed_time(evs[-1])
     total_ms = maxr(local_ms)
     rank_ms, breakdown = None, None
@@ -529,8 +530,6 @@ def main():
                     d_ = (p_ - ref_p).abs().max() / (ref_p - snap_n["params"]).abs().max().clamp_min(1e-30)
                     xcheck[f"{name}_vs_nccl_rel_update_diff"] = float(d_)
                     xcheck[f"{name}_vs_nccl_state_mean_max_abs"] = float((sm_ - results["nccl"][3]).abs().max())
-    clocks = sampler.stop() if sampler else None
-
     # ---- BASELINE c2 / c3 / c5 at this run's N ---------------------------------------------------------------------
     extra = None
     if not args.no_extra:
