@@ -283,3 +283,28 @@ def test_autograd_wrapper_entropy_before_log_prob_and_entropy_only(cuda_dev):
             (0.02 * ent.sum()).backward()
             only = oh.head_fwd_bwd(d["logits"], d["loc"], d["logstd"], d["value"], torch.zeros(B), torch.full((B,), 0.02))
             assert rel(lg.grad, only["dlogits"]) < TOL
+
+
+@pytest.mark.parametrize("B", [5000, 40000])
+def test_host_pipeline_equals_resident_call(cuda_dev, B):
+    """pfpn_b200.host.HostHeadPipeline (pinned host buffers, ramped chunk schedule over three streams) against one resident
+    K1 call on the same minibatch: per-state outputs and the logits gradient bit for bit (the advantage statistics are
+    whole-batch in both), the [A,P] sums and the loss up to the chunked summation order."""
+    from pfpn_b200.host import HostHeadPipeline
+    A, P = 36, 35
+    d = synth.head_inputs(B, A, P, seed=21)
+    dd = {k: (v.to(cuda_dev) if torch.is_tensor(v) else v) for k, v in d.items()}
+    fwd = head.head_call(_cabi.HEAD_FWD, dd["logits"], dd["loc"], dd["logstd"], dd["value"])
+    lp_old = (fwd["lp"] + dd["lp_noise"]).contiguous()
+    stats = head.adv_stats(dd["adv"])
+    ref = head.head_call(_cabi.HEAD_PPO, dd["logits"], dd["loc"], dd["logstd"], dd["value"], adv=dd["adv"], lp_old=lp_old,
+                         adv_stats_t=stats, loss_scale=1.0 / B)
+    pin = lambda t: t.detach().cpu().contiguous().pin_memory()
+    pipe = HostHeadPipeline(B, A, P, cuda_dev, chunk=8192)
+    assert sum(hi - lo for lo, hi in pipe.bounds) == B and pipe.bounds[0][0] == 0
+    out = pipe.run(pin(d["logits"]), pin(d["loc"]), pin(d["logstd"]), pin(d["value"]), pin(d["adv"]), pin(lp_old))
+    assert torch.equal(out["lp"], ref["lp"].cpu())
+    assert torch.equal(out["ent"], ref["ent"].cpu())
+    assert torch.equal(out["dlogits"], ref["dlogits"].cpu())
+    assert rel(out["dloc"], ref["dloc"]) < 1e-5 and rel(out["dlogstd"], ref["dlogstd"]) < 1e-5
+    assert abs(float(out["loss"]) - float(ref["loss"])) <= 1e-5 * max(1.0, abs(float(ref["loss"])))
