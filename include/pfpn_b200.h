@@ -205,6 +205,9 @@ typedef struct pfpn_rsample_args {
   float* dlogstd;           /* [A, P]  bwd in/out (accumulated)                      */
   uint64_t seed, offset;
   int32_t B, A, P;
+  int32_t reserved;
+  const uint64_t* offset_dev; /* optional DEVICE word added to `offset` when the kernel starts (NULL = 0): a captured CUDA   */
+                              /* graph then draws fresh variates on every replay (the caller advances the word in-graph)     */
 } pfpn_rsample_args;
 int pfpn_head_rsample_fwd(const pfpn_rsample_args* args, pfpn_stream_t stream);
 /* (backward: dloc / dlogstd are ADDED to -- zero or pre-load them; the accumulation runs in per-lane registers and fixed-order
@@ -237,6 +240,8 @@ typedef struct pfpn_sac_head_args {
   float* dlogstd;           /* [A, P]  out, overwritten                                */
   uint64_t seed, offset;
   int32_t B, A, P;
+  int32_t reserved;
+  const uint64_t* offset_dev; /* optional device word added to `offset` (see pfpn_rsample_args)                         */
 } pfpn_sac_head_args;
 int pfpn_sac_head_workspace_bytes(int32_t A, int32_t P, size_t* bytes);
 int pfpn_sac_head_fwd_bwd(const pfpn_sac_head_args* args, void* workspace, size_t workspace_bytes, pfpn_stream_t stream);
@@ -414,6 +419,12 @@ int pfpn_clip_by_global_norm(float* grads, size_t n, float clip, float* norm_sca
  * Replaces: build_optimizer -> tf.train.AdamOptimizer  models/workers/base_worker.py:64-70 */
 int pfpn_adam_step(float* params, const float* grads, float* m, float* v, size_t n, float lr, float beta1,
                    float beta2, float eps, int64_t step, float grad_scale, pfpn_stream_t stream);
+/* Same with the step number read from DEVICE memory when the kernel runs: step = *step_counter + step_bias (>= 1), lr_t
+ * computed on the device -- nothing in the launch arguments changes between steps, so the call can be captured in a CUDA
+ * graph (the caller advances the counter in-graph, e.g. after the last Adam launch of the step). */
+int pfpn_adam_step_dev(float* params, const float* grads, float* m, float* v, size_t n, float lr, float beta1,
+                       float beta2, float eps, const int32_t* step_counter, int32_t step_bias, float grad_scale,
+                       pfpn_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * K7 fused with the data-parallel exchange: sum of the N ranks' clipped [gradient | statistics]

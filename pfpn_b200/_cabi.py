@@ -74,7 +74,7 @@ class SacHeadArgs(C.Structure):
         ("sample", _f32p), ("s_pre", _f32p), ("idx", C.c_void_p), ("logp", _f32p),
         ("dlogits", _f32p), ("dloc", _f32p), ("dlogstd", _f32p),
         ("seed", C.c_uint64), ("offset", C.c_uint64),
-        ("B", C.c_int32), ("A", C.c_int32), ("P", C.c_int32),
+        ("B", C.c_int32), ("A", C.c_int32), ("P", C.c_int32), ("reserved", C.c_int32), ("offset_dev", C.c_void_p),
     ]
 
 
@@ -144,7 +144,7 @@ class RSampleArgs(C.Structure):
         ("sample", _f32p), ("s_pre", _f32p), ("idx", C.c_void_p),
         ("g_sample", _f32p), ("g_s_pre", _f32p), ("dlogits", _f32p), ("dloc", _f32p), ("dlogstd", _f32p),
         ("seed", C.c_uint64), ("offset", C.c_uint64),
-        ("B", C.c_int32), ("A", C.c_int32), ("P", C.c_int32),
+        ("B", C.c_int32), ("A", C.c_int32), ("P", C.c_int32), ("reserved", C.c_int32), ("offset_dev", C.c_void_p),
     ]
 
 
@@ -203,6 +203,7 @@ pfpn_sac_losses = _sig("pfpn_sac_losses", C.c_int, [_vp] * 11 + [_f, _f, _f, _i3
 pfpn_axpby = _sig("pfpn_axpby", C.c_int, [_vp, _vp, C.c_size_t, _f, _f, _vp])
 pfpn_clip_by_global_norm = _sig("pfpn_clip_by_global_norm", C.c_int, [_vp, C.c_size_t, _f, _vp, _vp, C.c_size_t, _vp])
 pfpn_adam_step = _sig("pfpn_adam_step", C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _f, _f, _f, _f, C.c_int64, _f, _vp])
+pfpn_adam_step_dev = _sig("pfpn_adam_step_dev", C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _f, _f, _f, _f, _vp, _i32, _f, _vp])
 pfpn_tc_gemm_nt = _sig("pfpn_tc_gemm_nt", C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp])
 pfpn_tc_gemm_nn = _sig("pfpn_tc_gemm_nn", C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp])
 pfpn_tc_gemm_nt_lo = _sig("pfpn_tc_gemm_nt_lo", C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp])

@@ -257,6 +257,27 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// the same with the step number read from device memory (graph-capturable): lr_t as pfpn_adam_step computes it on the host
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                size_t n, float lr, float b1, float b2, float eps, float gscale,
+                                const int* __restrict__ step_counter, int step_bias) {
+  __shared__ float s_lr;
+  if (threadIdx.x == 0) {
+    const double t = (double)(*step_counter + step_bias);
+    s_lr = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+  }
+  __syncthreads();
+  const float lr_t = s_lr;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
 // out[c, r] = in[r, c]  (weights -> K-major operand of the tensor-core forward GEMM)
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc, int ldi, int ldo) {
   __shared__ float t[32][33];
@@ -415,6 +436,16 @@ extern "C" int pfpn_clip_by_global_norm(float* grads, size_t n, float clip, floa
     scale_kernel<<<kNormBlocks, 256, 0, st>>>(grads, n, norm_scale);
     PFPN_CUDA_OK(cudaGetLastError());
   }
+  return PFPN_OK;
+}
+
+extern "C" int pfpn_adam_step_dev(float* params, const float* grads, float* m, float* v, size_t n, float lr, float beta1,
+                                  float beta2, float eps, const int32_t* step_counter, int32_t step_bias, float grad_scale,
+                                  pfpn_stream_t stream_) {
+  if (!params || !grads || !m || !v || !step_counter || n == 0) return PFPN_ERR_ARG;
+  adam_dev_kernel<<<kNormBlocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(params, grads, m, v, n, lr, beta1, beta2, eps,
+                                                                                     grad_scale, step_counter, step_bias);
+  PFPN_CUDA_OK(cudaGetLastError());
   return PFPN_OK;
 }
 

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(BWD ? 384 : kRsWarps * 32) rsample_kernel(cons
   const long long nchunks = (rows + chunk_rows - 1) / chunk_rows;
   const int nw = blockDim.x >> 5;
   const Philox7 rng(ar.seed);
+  const uint64_t rng_off = ar.offset + (ar.offset_dev != nullptr ? *ar.offset_dev : 0ull);  // (device word: graph replays)
   // forward: c = chunk of consecutive rows per warp; backward: c = state per CTA, its rows split over the warps by a
   const long long c_begin = BWD ? (long long)blockIdx.x : (long long)blockIdx.x * nw + warp;
   const long long c_step = BWD ? (long long)gridDim.x : (long long)gridDim.x * nw;
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(BWD ? 384 : kRsWarps * 32) rsample_kernel(cons
         for (int e4 = 0; e4 < MAXE; e4 += 4) {
           const int k0 = lane + 32 * e4;
           if (k0 < P) {
-            const uint4 q = rng(ar.offset, (uint64_t)(r * P + k0));
+            const uint4 q = rng(rng_off, (uint64_t)(r * P + k0));
             const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(BWD ? 384 : kRsWarps * 32) rsample_kernel(cons
             const int k0 = lane + 32 * e4;
             if (k0 < P) {
               float n4[4];
-              normal4(rng(ar.offset, kNormalStream | (uint64_t)(r * P + k0)), n4);
+              normal4(rng(rng_off, kNormalStream | (uint64_t)(r * P + k0)), n4);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int k = k0 + 32 * i;
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(BWD ? 384 : kRsWarps * 32) rsample_kernel(cons
           // the forward only needs the winner's location draw: regenerate just that block
           const int es = my_arg >> 5;
           float n4[4];
-          normal4(rng(ar.offset, kNormalStream | (uint64_t)(r * P + (my_arg & 31) + 32 * (es & ~3))), n4);
+          normal4(rng(rng_off, kNormalStream | (uint64_t)(r * P + (my_arg & 31) + 32 * (es & ~3))), n4);
           eps = (es & 2) ? ((es & 1) ? n4[3] : n4[2]) : ((es & 1) ? n4[1] : n4[0]);
         } else {
           eps = ar.ext_normal[r * P + my_arg];

@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
     const float* cst_r = cst_s + a * P;
     float* acc_r = acc_s + (size_t)slot * 2 * AP + a * P;
     float2 acc1[NP], acc2[NP];
+    const uint64_t rng_off = kp.a.offset + (kp.a.offset_dev != nullptr ? *kp.a.offset_dev : 0ull);  // (device word: graph replays)
 #pragma unroll
     for (int i = 0; i < NP; ++i) acc1[i] = acc2[i] = make_float2(0.f, 0.f);
 
@@ -234,8 +235,8 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
         const int nj = u == 0 ? 4 : 3;  // particles >= 100: only slot (0, 3) exists
         float n4[4], nl4[4], ya4[4];
         if (FAST) {
-          const uint4 q = sac_philox(kp, kp.a.offset, (uint64_t)(r * P + kb));
-          sac_normal4(sac_philox(kp, kp.a.offset, kSacNormalStream | (uint64_t)(r * P + kb)), n4);
+          const uint4 q = sac_philox(kp, rng_off, (uint64_t)(r * P + kb));
+          sac_normal4(sac_philox(kp, rng_off, kSacNormalStream | (uint64_t)(r * P + kb)), n4);
           const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j)

@@ -86,24 +86,25 @@ class _RSampleFn(torch.autograd.Function):
     """(sample, s_) of utils.py:156-186 with the mask / mask2 custom gradients."""
 
     @staticmethod
-    def forward(ctx, logits, loc, logstd, seed, offset, ext_uniform, ext_normal):
+    def forward(ctx, logits, loc, logstd, seed, offset, ext_uniform, ext_normal, offset_dev=None):
         sample, s_pre, idx = _sampling.rsample_fwd(logits, loc, logstd, seed=seed, offset=offset,
-                                                   ext_uniform=ext_uniform, ext_normal=ext_normal)
+                                                   ext_uniform=ext_uniform, ext_normal=ext_normal, offset_dev=offset_dev)
         ctx.save_for_backward(logits, loc, logstd)
-        ctx.rng = (seed, offset, ext_uniform, ext_normal)
+        ctx.rng = (seed, offset, ext_uniform, ext_normal, offset_dev)
         ctx.mark_non_differentiable(idx)
         return sample, s_pre, idx
 
     @staticmethod
     def backward(ctx, g_sample, g_s_pre, _g_idx):
         logits, loc, logstd = ctx.saved_tensors
-        seed, offset, eu, en = ctx.rng
+        seed, offset, eu, en, odev = ctx.rng
         if g_sample is None:
             g_sample = torch.zeros(logits.shape[:2], dtype=torch.float32, device=logits.device)
         dlogits, dloc, dlogstd = _sampling.rsample_bwd(logits, loc, logstd, g_sample.contiguous(),
                                                        None if g_s_pre is None else g_s_pre.contiguous(),
-                                                       seed=seed, offset=offset, ext_uniform=eu, ext_normal=en)
-        return dlogits, dloc, dlogstd, None, None, None, None
+                                                       seed=seed, offset=offset, ext_uniform=eu, ext_normal=en,
+                                                       offset_dev=odev)  # (the word must not advance in between)
+        return dlogits, dloc, dlogstd, None, None, None, None, None
 
 
 class _DisDist:
@@ -160,15 +161,15 @@ class MixtureGaussianDistribution:
         return _EntropyFn.apply(self.logits, self.loc, self.logstd)
 
     # utils.py:153-200
-    def sample(self, n, *, seed: int = 0, offset: int = 0, ext_uniform=None, ext_normal=None):
+    def sample(self, n, *, seed: int = 0, offset: int = 0, ext_uniform=None, ext_normal=None, offset_dev=None):
         """``n`` must be 1 (utils.py:154).  Plain branch -> [1, B, A]; rsample branch
         (normalize_output) -> tuple (sample [1,B,A], value_before_tanh [1,B,A]).
-        Draws come from Philox(seed, offset) unless ext_* arrays are supplied."""
+        Draws come from Philox(seed, offset [+ the int64 device word ``offset_dev``]) unless ext_* arrays are supplied."""
         assert n == 1
         B, A, _ = self.logits.shape
         if self.normalize_output:
             sample, s_pre, idx = _RSampleFn.apply(self.logits, self.loc, self.logstd, seed, offset, ext_uniform,
-                                                  ext_normal)
+                                                  ext_normal, offset_dev)
             self.dis_action = idx
             return sample.reshape(n, B, A), s_pre.reshape(n, B, A)
         action, idx = _sampling.sample_plain(self.logits.detach(), self.loc.detach(), self.logstd.detach(), seed=seed,

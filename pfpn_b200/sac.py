@@ -21,6 +21,7 @@ autograd Functions of `distribution.py` call K1 / K3), exactly as a reference-si
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import List, Optional
 
 import numpy as np
@@ -34,6 +35,8 @@ from .network import ParticleFilteringClipPPONetwork, _Linear, _pad4
 
 
 class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
+    TRAIN_RNG_BASE = 1 << 40
+
     def __init__(self, trainable, state_shape, action_shape, alpha=0.2, tau=0.005, **kwargs):
         kwargs.setdefault("normalize_policy_output", True)  # sac.py:15-16
         kwargs.setdefault("gamma", 0.95)                    # deepmimic_base.py:12
@@ -122,6 +125,16 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
         if self.trainable:
             self.train_ops.append(self.sync_target_net)    # ... before the target sync is appended (sac.py:67-73)
         self._scratch = torch.empty(max(2 * S, 8), dtype=torch.float32, device=dev)
+        # Device-resident step state: nothing the training step's kernels are launched with changes between steps, so the
+        # whole step can be captured in a CUDA graph (GraphedSACUpdate).  `_train_rng` is added to the Philox offset of the
+        # training draws by the kernels themselves and advanced by 4 at the end of every compute_gradients; `_gstep_dev`
+        # mirrors global_step for the normaliser's decay (optim.cu).
+        self._train_rng = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._gstep_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._new_mean, self._new_std = self.state_mean.clone(), self.state_std.clone()
+        nb = C.c_size_t(0)
+        _cabi.check(_cabi.pfpn_normalizer_scratch_bytes(S, C.byref(nb)))
+        self._norm_scratch = torch.empty(nb.value, dtype=torch.uint8, device=dev)
         return self
 
     # ---------------------------------------------------------------------------- forward ----
@@ -181,14 +194,15 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
             dY, ldy = dX, dX.stride(0)
         return dY
 
-    def _policy(self, logits, B, requires_grad, seed_offset, ext):
+    def _policy(self, logits, B, requires_grad, seed_offset, ext, offset_dev=None):
         lg = logits.view(B, self.A, self.P)
         loc, ls = self.loc, self.logstd
         if requires_grad:
             lg = lg.detach().requires_grad_(True)
             loc, ls = loc.detach().requires_grad_(True), ls.detach().requires_grad_(True)
         dist = MixtureGaussianDistribution(lg, loc, torch.exp(ls.detach()), True, logstd=ls)
-        kw = dict(ext_uniform=ext[0], ext_normal=ext[1]) if ext is not None else dict(seed=self.sample_seed, offset=seed_offset)
+        kw = dict(ext_uniform=ext[0], ext_normal=ext[1]) if ext is not None else \
+            dict(seed=self.sample_seed, offset=seed_offset, offset_dev=offset_dev)
         smp, s_ = dist.sample(1, **kw)
         logp = dist.log_prob((smp[0], s_[0]))
         return smp[0], logp, (lg, loc, ls)
@@ -227,21 +241,22 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
         a_hist, r, nt = dv(action, B, self.A), dv(reward, B), dv(not_terminal, B)
         st = _stream_ptr()
         if self.normalize_state:  # LocalUpdateHookPre: statistics of this minibatch, applied by the optimizer
-            self._new_mean, self._new_std = self.state_mean.clone(), self.state_std.clone()
-            _cabi.check(_cabi.pfpn_normalizer_update(s.data_ptr(), self._new_mean.data_ptr(), self._new_std.data_ptr(), B,
-                                                     self.S, float(self.global_step), self._scratch.data_ptr(), st))
+            _cabi.check(_cabi.pfpn_normalizer_update_dev(s.data_ptr(), self.state_mean.data_ptr(), self.state_std.data_ptr(),
+                                                         self._new_mean.data_ptr(), self._new_std.data_ptr(), B, self.S,
+                                                         self._gstep_dev.data_ptr(), self._norm_scratch.data_ptr(),
+                                                         self._norm_scratch.numel(), st))
         x, x2 = self._normalize(s, "0"), self._normalize(s2, "1")
         logits, a_acts = self._actor_forward(x, "0")
-        off = self._rng_offset
-        self._rng_offset += 4
+        # training draws: Philox offsets TRAIN_RNG_BASE + {0 (s), 2 (s')} + the device word (rollouts count up from 0 on the host)
+        off, odev = self.TRAIN_RNG_BASE, (self._train_rng if draws is None else None)
         # K3f (A = 36, P = 100): the head's backward -- rsample backward + tanh log_prob forward/backward -- is ONE pass that
         # regenerates the forward's draws; the forward sample below then needs no autograd graph
         import os
         fused = (self.A, self.P) == (36, 100) and os.environ.get("PFPN_SAC_FUSED", "1") != "0"
-        smp, logp, leaves = self._policy(logits, B, not fused, off, None if draws is None else (draws[0], draws[1]))
+        smp, logp, leaves = self._policy(logits, B, not fused, off, None if draws is None else (draws[0], draws[1]), odev)
         logits2, _ = self._actor_forward(x2, "1")
         with torch.no_grad():
-            a2, logp2, _ = self._policy(logits2, B, False, off + 2, None if draws is None else (draws[2], draws[3]))
+            a2, logp2, _ = self._policy(logits2, B, False, off + 2, None if draws is None else (draws[2], draws[3]), odev)
         a_det = smp.detach()
         q_a = [self._q_forward(self.q[i], x, a_det, f"a{i}") for i in range(2)]
         q_r = [self._q_forward(self.q[i], x, a_hist, f"r{i}") for i in range(2)]
@@ -268,7 +283,7 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
             from . import sampling as _sampling
             ext = {} if draws is None else dict(ext_uniform=draws[0], ext_normal=draws[1])
             fo = _sampling.sac_head_fused(logits.view(B, self.A, self.P), self.loc, self.logstd, da.contiguous(), dlogp,
-                                          seed=self.sample_seed, offset=off, **ext)
+                                          seed=self.sample_seed, offset=off, offset_dev=odev, **ext)
             self._backward_stack(self.actor + [self.fc_policy], a_acts, fo["dlogits"].view(B, self.A * self.P))
             self.dloc.copy_(fo["dloc"])
             self.dlogstd.copy_(fo["dlogstd"])
@@ -279,6 +294,8 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
             self.dloc.copy_(loc_l.grad)
             self.dlogstd.copy_(ls_l.grad)
         self.dlog_alpha.copy_(out4[2:3])
+        if draws is None:
+            self._train_rng.add_(4)  # (after the backward: it regenerates the forward's draws from the same word)
         return out4[0] + out4[1], None, out4[1], out4[0]
 
     def train(self, sess, optimizer, ops, state, action, reward, not_terminal, state_):
@@ -310,11 +327,14 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
     def state_dict(self):
         sd = super().state_dict()
         sd["target_params"] = self.target_params.clone()
+        sd["train_rng"] = int(self._train_rng.item())
         return sd
 
     def load_state_dict(self, sd):
         super().load_state_dict(sd)
         self.target_params.copy_(sd["target_params"])
+        self._train_rng.fill_(int(sd.get("train_rng", 0)))
+        self._gstep_dev.fill_(int(self.global_step))
 
 
 class SACOptimizer:
@@ -331,12 +351,19 @@ class SACOptimizer:
         self.v: Optional[torch.Tensor] = None
 
     def apply_gradients(self, net: ParticleFilteringSACNetwork):
+        self._launch_step(net)
+        self._after_step(net)
+
+    # Split as SyncReplicasAdam's step: `_launch_step` only enqueues work whose launch arguments never change (the Adam
+    # step number lives in device memory), so GraphedSACUpdate can capture it; `_after_step` is host bookkeeping.
+    def _launch_step(self, net: ParticleFilteringSACNetwork):
         import torch.distributed as dist
         st = _stream_ptr()
         if self.m is None:
             self.m, self.v = torch.zeros_like(net.params), torch.zeros_like(net.params)
             self.norm_scale = torch.zeros(2, dtype=torch.float32, device=net.params.device)
             self._scratch = torch.empty(296, dtype=torch.float64, device=net.params.device)
+            self._step_dev = torch.full((1,), self.step, dtype=torch.int32, device=net.params.device)
             assert_replicas_identical(net.params, self.group)
         _cabi.check(_cabi.pfpn_clip_by_global_norm(net.grads.data_ptr(), net.n_params, self.norm_clip, self.norm_scale.data_ptr(),
                                                    self._scratch.data_ptr(), self._scratch.numel() * 8, st))
@@ -348,15 +375,71 @@ class SACOptimizer:
             dist.all_reduce(net.bucket, group=self.group)
             inv_n = 1.0 / dist.get_world_size(self.group)
         SyncReplicasAdam.unpack_stats(self, net, inv_n)
-        self.step += 1
         nc, n = net.n_critic, net.n_params
-        for lo, hi, lr in ((0, nc, self.lr_critic), (nc, n, self.lr_actor)):
-            _cabi.check(_cabi.pfpn_adam_step(net.params[lo:hi].data_ptr(), net.grads[lo:hi].data_ptr(), self.m[lo:hi].data_ptr(),
-                                             self.v[lo:hi].data_ptr(), hi - lo, lr, self.beta1, self.beta2, self.eps, self.step,
-                                             inv_n, st))
+        for lo, hi, lr in ((0, nc, self.lr_critic), (nc, n, self.lr_actor)):  # step = device counter + 1
+            _cabi.check(_cabi.pfpn_adam_step_dev(net.params[lo:hi].data_ptr(), net.grads[lo:hi].data_ptr(), self.m[lo:hi].data_ptr(),
+                                                 self.v[lo:hi].data_ptr(), hi - lo, lr, self.beta1, self.beta2, self.eps,
+                                                 self._step_dev.data_ptr(), 1, inv_n, st))
+        self._step_dev.add_(1)
+        net._gstep_dev.add_(1)
+        if net.trainable:
+            net.sync_target_net()  # (train_ops, sac.py:67-73; commutes with the particle resampling below)
+
+    def _after_step(self, net: ParticleFilteringSACNetwork):
+        self.step += 1
         net.global_step += 1
         for op in net.train_ops:
+            if getattr(op, "__func__", None) is ParticleFilteringSACNetwork.sync_target_net:
+                continue  # already enqueued by _launch_step
             op()
+
+
+class GraphedSACUpdate:
+    """One SAC learner step -- `net.compute_gradients(minibatch)` + `optimizer.apply_gradients(net)` -- captured ONCE in a
+    CUDA graph and replayed.  At the reference's batch size (256, deepmimic_sac_base.py:8) the step is ~150 launch-latency
+    sized kernels and copies: 2.5-2.9 ms eager, host-bound.  Capturable because the Philox offset of the training draws, the
+    Adam step number and the normaliser's step are device words the kernels read when they run (`_train_rng`, `_step_dev`,
+    `_gstep_dev`) and the graph itself advances.  The minibatch is copied into fixed input buffers (e.g. straight from
+    ``ReplayRing.sample``); the particle-resampling tick (host-side interval logic) runs eagerly after the replay.
+    Single-process use (with several ranks the NCCL all-reduce of the step stays eager: use apply_gradients)."""
+
+    KEYS = ("state", "action", "reward", "not_terminal", "state_")
+
+    def __init__(self, net: "ParticleFilteringSACNetwork", optimizer: "SACOptimizer", batch: int, warmup: int = 2):
+        dev = net.device
+        self.net, self.opt, self.B = net, optimizer, int(batch)
+        f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        self.inputs = dict(state=f(batch, net.S), action=f(batch, net.A), reward=f(batch), not_terminal=f(batch),
+                           state_=f(batch, net.S))
+        self.graph, self.losses, self._warm, self.replays = None, None, int(warmup), 0
+
+    def _set(self, *vals):
+        for k, v in zip(self.KEYS, vals):
+            if v is not None and v is not self.inputs[k]:
+                self.inputs[k].copy_(torch.as_tensor(v, dtype=torch.float32).reshape(self.inputs[k].shape), non_blocking=True)
+
+    def run(self, state=None, action=None, reward=None, not_terminal=None, state_=None):
+        """Arguments left None keep what is already in ``self.inputs``.  Returns device scalars
+        (loss, None, policy_loss, value_loss), valid until the next call."""
+        import os
+        self._set(state, action, reward, not_terminal, state_)
+        net, opt = self.net, self.opt
+        args = tuple(self.inputs[k] for k in self.KEYS)
+        if self._warm > 0 or os.environ.get("PFPN_GRAPH", "1") == "0":  # eager steps (also: allocate buffers and workspaces)
+            self._warm -= 1
+            self.losses = net.compute_gradients(*args)
+            opt.apply_gradients(net)
+            return self.losses
+        if self.graph is None:
+            torch.cuda.synchronize(net.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.losses = net.compute_gradients(*args)
+                opt._launch_step(net)
+        self.graph.replay()
+        self.replays += 1
+        opt._after_step(net)
+        return self.losses
 
 
 class ReplayRing:

@@ -44,7 +44,7 @@ def sample_plain(logits, loc, logstd, *, seed: int = 0, offset: int = 0, ext_uni
     return action, idx
 
 
-def _rsample_args(logits, loc, logstd, seed, offset, ext_uniform, ext_normal):
+def _rsample_args(logits, loc, logstd, seed, offset, ext_uniform, ext_normal, offset_dev=None):
     logits, loc, logstd = _f32c(logits, "logits"), _f32c(loc, "loc"), _f32c(logstd, "logstd")
     B, A, P = logits.shape
     a = _cabi.RSampleArgs()
@@ -57,12 +57,16 @@ def _rsample_args(logits, loc, logstd, seed, offset, ext_uniform, ext_normal):
         keep += [ext_uniform, ext_normal]
         a.ext_uniform, a.ext_normal = ext_uniform.data_ptr(), ext_normal.data_ptr()
     a.seed, a.offset, a.B, a.A, a.P = seed, offset, B, A, P
+    if offset_dev is not None:  # int64 device word added to `offset` by the kernel (graph replays draw fresh variates)
+        assert offset_dev.dtype == torch.int64 and offset_dev.is_cuda
+        a.offset_dev = offset_dev.data_ptr()
+        keep.append(offset_dev)
     return a, keep
 
 
-def rsample_fwd(logits, loc, logstd, *, seed=0, offset=0, ext_uniform=None, ext_normal=None):
+def rsample_fwd(logits, loc, logstd, *, seed=0, offset=0, ext_uniform=None, ext_normal=None, offset_dev=None):
     """utils.py:156-186 forward.  Returns (sample = tanh(s_), s_, idx)."""
-    a, keep = _rsample_args(logits, loc, logstd, seed, offset, ext_uniform, ext_normal)
+    a, keep = _rsample_args(logits, loc, logstd, seed, offset, ext_uniform, ext_normal, offset_dev)
     dev = logits.device
     sample = torch.empty(a.B, a.A, dtype=torch.float32, device=dev)
     s_pre = torch.empty_like(sample)
@@ -73,9 +77,10 @@ def rsample_fwd(logits, loc, logstd, *, seed=0, offset=0, ext_uniform=None, ext_
     return sample, s_pre, idx
 
 
-def rsample_bwd(logits, loc, logstd, g_sample, g_s_pre, *, seed=0, offset=0, ext_uniform=None, ext_normal=None):
+def rsample_bwd(logits, loc, logstd, g_sample, g_s_pre, *, seed=0, offset=0, ext_uniform=None, ext_normal=None,
+                offset_dev=None):
     """Straight-through backward (mask / mask2, utils.py:164-183).  Returns (dlogits, dloc, dlogstd)."""
-    a, keep = _rsample_args(logits, loc, logstd, seed, offset, ext_uniform, ext_normal)
+    a, keep = _rsample_args(logits, loc, logstd, seed, offset, ext_uniform, ext_normal, offset_dev)
     dev = logits.device
     g_sample = _f32c(g_sample, "g_sample")
     a.g_sample = g_sample.data_ptr()
@@ -146,7 +151,7 @@ def rollout_fused(logits, loc, logstd, *, seed=0, offset=0, ext_uniform=None, ex
 
 
 def sac_head_fused(logits, loc, logstd, g_sample, g_lp, *, seed=0, offset=0, ext_uniform=None, ext_normal=None,
-                   out: Optional[dict] = None, dlogits_out=None):
+                   out: Optional[dict] = None, dlogits_out=None, offset_dev=None):
     """K3f: rsample forward + tanh log_prob forward + the backward of both in one pass (utils.py:108-144,156-186).
     Returns dict(sample, s_pre, idx, logp, dlogits, dloc, dlogstd).  A = 36, P = 100 only (PfpnError -3 otherwise)."""
     logits, loc, logstd = _f32c(logits, "logits"), _f32c(loc, "loc"), _f32c(logstd, "logstd")
@@ -175,6 +180,10 @@ def sac_head_fused(logits, loc, logstd, g_sample, g_lp, *, seed=0, offset=0, ext
     a.sample, a.s_pre, a.idx, a.logp = (out[k].data_ptr() for k in ("sample", "s_pre", "idx", "logp"))
     a.dlogits, a.dloc, a.dlogstd = (out[k].data_ptr() for k in ("dlogits", "dloc", "dlogstd"))
     a.seed, a.offset, a.B, a.A, a.P = seed, offset, B, A, P
+    if offset_dev is not None:
+        assert offset_dev.dtype == torch.int64 and offset_dev.is_cuda
+        a.offset_dev = offset_dev.data_ptr()
+        keep.append(offset_dev)
     n = C.c_size_t(0)
     _cabi.check(_cabi.pfpn_sac_head_workspace_bytes(A, P, C.byref(n)))
     key = (dev, "sacf", n.value)

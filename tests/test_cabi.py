@@ -49,7 +49,10 @@ def test_every_header_function_has_a_ctypes_signature():
 
 
 def test_other_struct_layouts_match_the_static_asserts_of_capi_cu():
-    assert C.sizeof(_cabi.SampleArgs) == 88 and C.sizeof(_cabi.RSampleArgs) == 136 and C.sizeof(_cabi.ResampleArgs) == 200
+    assert C.sizeof(_cabi.SampleArgs) == 88 and C.sizeof(_cabi.RSampleArgs) == 144 and C.sizeof(_cabi.ResampleArgs) == 200
+    assert _cabi.RSampleArgs.offset_dev.offset == 136
+    assert C.sizeof(_cabi.SacHeadArgs) == 152 and _cabi.SacHeadArgs.offset_dev.offset == 144
+    assert C.sizeof(_cabi.HeadPush) == 176 and _cabi.HeadPush.consume_rows.offset == 152 and _cabi.HeadPush.consume_scale.offset == 168
 
 
 def test_argument_errors_of_the_widened_entry_points_without_gpu():

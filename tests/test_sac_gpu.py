@@ -132,3 +132,43 @@ def test_sac_step_with_the_fused_head_kernel_equals_the_autograd_composition(cud
             os.environ.pop("PFPN_SAC_FUSED", None)
     assert rel(grads["1"][0], grads["0"][0]) < 2 * TOL
     assert np.allclose(grads["1"][1], grads["0"][1], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("P", [35, 100])
+def test_sac_step_replayed_as_a_cuda_graph_equals_the_eager_steps(cuda_dev, P):
+    """GraphedSACUpdate: the whole learner step (two actor forwards, six critic evaluations, head forward / backward,
+    losses, joint clip, two Adams, target sync) captured once and replayed must leave the network bit-identical to the same
+    steps issued eagerly -- including the Philox offsets of the training draws, the Adam step number and the normaliser's
+    step, which the kernels read from device memory.  P = 35: autograd composition; P = 100: fused K3f."""
+    from pfpn_b200.sac import GraphedSACUpdate, ParticleFilteringSACNetwork, SACOptimizer
+    S, A, B = 197, 36, 256
+    mk = lambda: ParticleFilteringSACNetwork(True, [S], [A], action_lower_bound=[-1.0] * A, action_upper_bound=[1.0] * A,
+                                             particles=P, resample=-1, resample_interval=12000, normalize_state=True,
+                                             clip_state=5.0, device=cuda_dev, seed=5).init()
+    g = torch.Generator().manual_seed(11)
+    batches = [(torch.randn(B, S, generator=g), torch.rand(B, A, generator=g) * 1.8 - 0.9, torch.randn(B, generator=g),
+                (torch.rand(B, generator=g) > 0.1).float(), torch.randn(B, S, generator=g)) for _ in range(6)]
+    batches = [tuple(t.to(cuda_dev) for t in b) for b in batches]
+    net_e, opt_e = mk(), SACOptimizer()
+    losses_e = []
+    for b in batches:
+        out = net_e.compute_gradients(*b)
+        opt_e.apply_gradients(net_e)
+        losses_e.append(float(out[0]))
+    net_g, opt_g = mk(), SACOptimizer()
+    gu = GraphedSACUpdate(net_g, opt_g, B, warmup=2)
+    losses_g = []
+    for b in batches:
+        out = gu.run(*b)
+        losses_g.append(float(out[0]))
+    torch.cuda.synchronize()
+    assert gu.replays == 4
+    assert losses_e == losses_g
+    assert torch.equal(net_e.params, net_g.params)
+    assert torch.equal(net_e.target_params, net_g.target_params)
+    assert torch.equal(net_e.state_mean, net_g.state_mean) and torch.equal(net_e.state_std, net_g.state_std)
+    assert torch.equal(opt_e.m, opt_g.m) and torch.equal(opt_e.v, opt_g.v)
+    assert net_e.global_step == net_g.global_step == 6 and int(net_g._gstep_dev.item()) == 6 and int(opt_g._step_dev.item()) == 6
+    assert int(net_g._train_rng.item()) == 24
+    # different steps draw different variates (the device word advances inside the graph)
+    assert len(set(losses_g)) == len(losses_g)

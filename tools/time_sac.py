@@ -2,7 +2,7 @@
 import os, sys, json, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from pfpn_b200.sac import ParticleFilteringSACNetwork, SACOptimizer, ReplayRing
+from pfpn_b200.sac import ParticleFilteringSACNetwork, SACOptimizer, ReplayRing, GraphedSACUpdate
 dev = torch.device("cuda:0")
 S, A = 197, 36
 res = []
@@ -25,8 +25,20 @@ for P, B in ((35, 256), (100, 256), (100, 4096), (100, 65536)):
     w0 = time.perf_counter(); e0.record()
     for _ in range(n): step()
     e1.record(); torch.cuda.synchronize(); w1 = time.perf_counter()
-    res.append({"P": P, "batch": B, "ms_per_step_device": round(e0.elapsed_time(e1) / n, 3), "ms_per_step_wall": round((w1 - w0) * 1e3 / n, 3),
-                "samples_per_s": round(B / (e0.elapsed_time(e1) / n) * 1e3)})
+    row = {"P": P, "batch": B, "ms_per_step_device": round(e0.elapsed_time(e1) / n, 3), "ms_per_step_wall": round((w1 - w0) * 1e3 / n, 3),
+           "samples_per_s": round(B / (e0.elapsed_time(e1) / n) * 1e3)}
+    if B <= 4096:  # the same step replayed as one CUDA graph (replay sample eager: a gather into the graph's input buffers)
+        gu = GraphedSACUpdate(net, opt, B, warmup=1)
+        def gstep():
+            gu.run(*ring.sample(B))
+        for _ in range(4): gstep()
+        torch.cuda.synchronize()
+        w0 = time.perf_counter(); e0.record()
+        for _ in range(n): gstep()
+        e1.record(); torch.cuda.synchronize(); w1 = time.perf_counter()
+        row.update(graph_ms_per_step_device=round(e0.elapsed_time(e1) / n, 3), graph_ms_per_step_wall=round((w1 - w0) * 1e3 / n, 3),
+                   graph_samples_per_s=round(B / (e0.elapsed_time(e1) / n) * 1e3), graph_replays=gu.replays)
+    res.append(row)
     del net, opt, ring
     torch.cuda.empty_cache()
 print(json.dumps({"sac_learner_step": res, "note": "B=256 is the reference's batch_size (deepmimic_sac_base.py:8): launch/host-bound"}))
