@@ -194,6 +194,33 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
             dY, ldy = dX, dX.stride(0)
         return dY
 
+    def _parallel(self, thunks):
+        """Run independent pieces of the step on side streams (fork after the current stream, join back into it).  At the
+        reference's batch of 256 the step is a chain of ~150 kernels of 5-10 us each: the six critic evaluations, the two
+        critic backward stacks and the two action-gradient chains have no data dependence on each other, so as parallel
+        branches (of the eager streams and of the captured graph alike) they shorten the critical path."""
+        import os
+        if len(thunks) < 2 or self.device.type != "cuda" or os.environ.get("PFPN_SAC_STREAMS", "1") == "0":
+            return [t() for t in thunks]
+        if not torch.cuda.is_current_stream_capturing() and not getattr(self, "_wide", False):
+            return [t() for t in thunks]  # (eager small batches are host-bound: the extra stream switches only cost time)
+        cur = torch.cuda.current_stream(self.device)
+        if not hasattr(self, "_pstreams"):
+            self._pstreams = [torch.cuda.Stream(self.device) for _ in range(6)]
+            self._pdone = [torch.cuda.Event() for _ in range(6)]
+            self._pfork = torch.cuda.Event()
+        self._pfork.record(cur)
+        outs = []
+        for k, t in enumerate(thunks):
+            s = self._pstreams[k % len(self._pstreams)]
+            s.wait_event(self._pfork)
+            with torch.cuda.stream(s):
+                outs.append(t())
+        for k in range(min(len(thunks), len(self._pstreams))):
+            self._pdone[k].record(self._pstreams[k])
+            cur.wait_event(self._pdone[k])
+        return outs
+
     def _policy(self, logits, B, requires_grad, seed_offset, ext, offset_dev=None):
         lg = logits.view(B, self.A, self.P)
         loc, ls = self.loc, self.logstd
@@ -238,6 +265,7 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
             self.device, dtype=torch.float32).reshape(*shape).contiguous()
         s, s2 = self._dev_state(state), self._dev_state(state_)
         B = s.shape[0]
+        self._wide = B >= 2048  # (eager: side streams only where the kernels are long enough to overlap)
         a_hist, r, nt = dv(action, B, self.A), dv(reward, B), dv(not_terminal, B)
         st = _stream_ptr()
         if self.normalize_state:  # LocalUpdateHookPre: statistics of this minibatch, applied by the optimizer
@@ -258,9 +286,10 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
         with torch.no_grad():
             a2, logp2, _ = self._policy(logits2, B, False, off + 2, None if draws is None else (draws[2], draws[3]), odev)
         a_det = smp.detach()
-        q_a = [self._q_forward(self.q[i], x, a_det, f"a{i}") for i in range(2)]
-        q_r = [self._q_forward(self.q[i], x, a_hist, f"r{i}") for i in range(2)]
-        q_t = [self._q_forward(self.qt[i], x2, a2, f"t{i}") for i in range(2)]
+        qs = self._parallel([lambda i=i: self._q_forward(self.q[i], x, a_det, f"a{i}") for i in range(2)] +
+                            [lambda i=i: self._q_forward(self.q[i], x, a_hist, f"r{i}") for i in range(2)] +
+                            [lambda i=i: self._q_forward(self.qt[i], x2, a2, f"t{i}") for i in range(2)])
+        q_a, q_r, q_t = qs[0:2], qs[2:4], qs[4:6]
         f = lambda name: self._buf(name, B)
         dq_a, dq_r, dlogp, out4 = [f("dq1a"), f("dq2a")], [f("dq1r"), f("dq2r")], f("dlogp"), self._buf("sac_out", 4)
         _cabi.check(_cabi.pfpn_sac_losses(q_a[0][0].data_ptr(), q_a[1][0].data_ptr(), q_r[0][0].data_ptr(), q_r[1][0].data_ptr(),
@@ -270,15 +299,11 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
                                           dq_a[0].data_ptr(), dq_a[1].data_ptr(), dq_r[0].data_ptr(), dq_r[1].data_ptr(),
                                           dlogp.data_ptr(), out4.data_ptr(), st))
         self.grads.zero_()
-        # value loss -> critic variables
-        for i in range(2):
-            self._backward_stack(self.q[i], q_r[i][1], dq_r[i])
-        # policy loss: through the critics into the action (no critic weight gradients), then the head, then the actor
-        da = None
-        for i in range(2):
-            dxin = self._input_grad(self.q[i], q_a[i][1], dq_a[i], f"a{i}")
-            part = dxin[:, self.S:self.S + self.A]
-            da = part.clone() if da is None else da + part
+        # value loss -> critic variables; policy loss: through the critics into the action (no critic weight gradients),
+        # then the head, then the actor.  Four independent chains (disjoint gradient segments / scratch buffers).
+        res = self._parallel([lambda i=i: self._backward_stack(self.q[i], q_r[i][1], dq_r[i], f"q{i}") for i in range(2)] +
+                             [lambda i=i: self._input_grad(self.q[i], q_a[i][1], dq_a[i], f"a{i}") for i in range(2)])
+        da = res[2][:, self.S:self.S + self.A] + res[3][:, self.S:self.S + self.A]
         if fused:
             from . import sampling as _sampling
             ext = {} if draws is None else dict(ext_uniform=draws[0], ext_normal=draws[1])
