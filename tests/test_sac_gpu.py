@@ -134,28 +134,32 @@ def test_sac_step_with_the_fused_head_kernel_equals_the_autograd_composition(cud
     assert np.allclose(grads["1"][1], grads["0"][1], rtol=1e-6, atol=1e-7)
 
 
-@pytest.mark.parametrize("P", [35, 100])
-def test_sac_step_replayed_as_a_cuda_graph_equals_the_eager_steps(cuda_dev, P):
+@pytest.mark.parametrize("P,interval", [(35, 12000), (100, 12000), (35, 3)])
+def test_sac_step_replayed_as_a_cuda_graph_equals_the_eager_steps(cuda_dev, P, interval):
     """GraphedSACUpdate: the whole learner step (two actor forwards, six critic evaluations, head forward / backward,
     losses, joint clip, two Adams, target sync) captured once and replayed must leave the network bit-identical to the same
     steps issued eagerly -- including the Philox offsets of the training draws, the Adam step number and the normaliser's
-    step, which the kernels read from device memory.  P = 35: autograd composition; P = 100: fused K3f."""
+    step, which the kernels read from device memory.  P = 35: autograd composition; P = 100: fused K3f; interval = 3: the
+    particle-resampling tick (host-side interval logic, eager, rewires fc_policy in place) falls between replays."""
     from pfpn_b200.sac import GraphedSACUpdate, ParticleFilteringSACNetwork, SACOptimizer
     S, A, B = 197, 36, 256
     mk = lambda: ParticleFilteringSACNetwork(True, [S], [A], action_lower_bound=[-1.0] * A, action_upper_bound=[1.0] * A,
-                                             particles=P, resample=-1, resample_interval=12000, normalize_state=True,
+                                             particles=P, resample=-1, resample_interval=interval, normalize_state=True,
                                              clip_state=5.0, device=cuda_dev, seed=5).init()
     g = torch.Generator().manual_seed(11)
+    roll = torch.randn(512, S, generator=g).to(cuda_dev)
     batches = [(torch.randn(B, S, generator=g), torch.rand(B, A, generator=g) * 1.8 - 0.9, torch.randn(B, generator=g),
                 (torch.rand(B, generator=g) > 0.1).float(), torch.randn(B, S, generator=g)) for _ in range(6)]
     batches = [tuple(t.to(cuda_dev) for t in b) for b in batches]
     net_e, opt_e = mk(), SACOptimizer()
+    net_e.run_batch(roll)  # activity statistics for the resampler
     losses_e = []
     for b in batches:
         out = net_e.compute_gradients(*b)
         opt_e.apply_gradients(net_e)
         losses_e.append(float(out[0]))
     net_g, opt_g = mk(), SACOptimizer()
+    net_g.run_batch(roll)
     gu = GraphedSACUpdate(net_g, opt_g, B, warmup=2)
     losses_g = []
     for b in batches:
