@@ -702,13 +702,19 @@ def run_extra(dev, rank, world, stream, maxr):
     del logits5, buf5
     torch.cuda.empty_cache()
     # ---- SAC-PFPN learner step at the reference's batch size (deepmimic_sac_base.py:8), eager and as one replayed graph ----
-    try:
+    t_e = t_g = -1.0
+    sac_err, sac_replays = None, 0
+    # every rank its own learner: a one-rank group each (new_group is collective: all ranks create all groups, same order)
+    solo = None
+    if world > 1:
+        solo = [torch.distributed.new_group([r]) for r in range(world)][rank]
+    try:  # (local work only inside the try: the collectives below must run on every rank whatever happens here)
         from pfpn_b200.sac import GraphedSACUpdate, ParticleFilteringSACNetwork, SACOptimizer, ReplayRing
         Ss, Bs_ = 197, 256
         snet = ParticleFilteringSACNetwork(True, [Ss], [A], action_lower_bound=[-1.0] * A, action_upper_bound=[1.0] * A,
                                            particles=35, resample=-1, resample_interval=12000, normalize_state=True,
                                            clip_state=5.0, device=dev, seed=SEED).init()
-        sopt = SACOptimizer()
+        sopt = SACOptimizer(group=solo)
         ring = ReplayRing(200_000, Ss, A, device=dev, seed=SEED + rank)
         n0 = 50_000
         ring.append(torch.randn(n0, Ss, device=dev, generator=gr), torch.rand(n0, A, device=dev, generator=gr) * 2 - 1,
@@ -720,13 +726,15 @@ def run_extra(dev, rank, world, stream, maxr):
         t_e, _ = timed(sac_eager, 20, stream)
         sgu = GraphedSACUpdate(snet, sopt, Bs_, warmup=1)
         t_g, _ = timed(lambda: sgu.run(*ring.sample(Bs_)), 20, stream, warm=4)
-        out["sac_step_B256_P35"] = {"eager_ms": maxr(t_e), "graph_ms": maxr(t_g), "graph_replays": sgu.replays,
-                                    "samples_s_per_gpu_graph": Bs_ / (maxr(t_g) * 1e-3),
-                                    "note": "replicas only (every rank its own learner); replay sample -> two actor forwards, six "
-                                            "critic evaluations, head fwd/bwd, joint clip, two Adams, target sync"}
+        sac_replays = sgu.replays
         del snet, sopt, ring, sgu
     except Exception as e:  # noqa: BLE001 -- an extra must never take the headline down
-        out["sac_step_B256_P35"] = {"error": repr(e)[:200]}
+        sac_err = repr(e)[:200]
+    t_e, t_g = maxr(t_e), maxr(t_g)
+    out["sac_step_B256_P35"] = {"eager_ms": t_e, "graph_ms": t_g, "graph_replays": sac_replays,
+                                "samples_s_per_gpu_graph": (256 / (t_g * 1e-3)) if t_g > 0 else None, "error": sac_err,
+                                "note": "replicas only (every rank its own independent learner); replay sample -> two actor "
+                                        "forwards, six critic evaluations, head fwd/bwd, joint clip, two Adams, target sync"}
     # ---- K6: the trunk's tensor-core GEMM at the headline batch, against the MEASURED tensor peak -------------------
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
