@@ -138,9 +138,9 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
         return self
 
     # ---------------------------------------------------------------------------- forward ----
-    def _normalize(self, state, tag):
+    def _normalize(self, state, tag, out=None):
         B = state.shape[0]
-        x = self._buf(f"x{tag}", B, self.Sp)
+        x = self._buf(f"x{tag}", B, self.Sp) if out is None else out
         _cabi.check(_cabi.pfpn_state_normalize(state.data_ptr(), self.state_mean.data_ptr(), self.state_std.data_ptr(),
                                                x.data_ptr(), B, self.S, self.Sp, self.clip_state,
                                                1 if self.normalize_state else 0, _stream_ptr()))
@@ -273,8 +273,13 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
                                                          self._new_mean.data_ptr(), self._new_std.data_ptr(), B, self.S,
                                                          self._gstep_dev.data_ptr(), self._norm_scratch.data_ptr(),
                                                          self._norm_scratch.numel(), st))
-        x, x2 = self._normalize(s, "0"), self._normalize(s2, "1")
-        logits, a_acts = self._actor_forward(x, "0")
+        # the actor sees s and s' through the SAME weights: one forward over 2B rows (half the launches of this part of the
+        # step, and from batch 256 on the stacked rows reach the tensor-core GEMM path)
+        xx = self._buf("xx", 2 * B, self.Sp)
+        x, x2 = self._normalize(s, "0", out=xx[:B]), self._normalize(s2, "1", out=xx[B:])
+        logits_all, acts_all = self._actor_forward(xx, "01")
+        logits, logits2 = logits_all[:B], logits_all[B:]
+        a_acts = [t[:B] for t in acts_all]
         # training draws: Philox offsets TRAIN_RNG_BASE + {0 (s), 2 (s')} + the device word (rollouts count up from 0 on the host)
         off, odev = self.TRAIN_RNG_BASE, (self._train_rng if draws is None else None)
         # K3f (A = 36, P = 100): the head's backward -- rsample backward + tanh log_prob forward/backward -- is ONE pass that
@@ -282,7 +287,6 @@ class ParticleFilteringSACNetwork(ParticleFilteringClipPPONetwork):
         import os
         fused = (self.A, self.P) == (36, 100) and os.environ.get("PFPN_SAC_FUSED", "1") != "0"
         smp, logp, leaves = self._policy(logits, B, not fused, off, None if draws is None else (draws[0], draws[1]), odev)
-        logits2, _ = self._actor_forward(x2, "1")
         with torch.no_grad():
             a2, logp2, _ = self._policy(logits2, B, False, off + 2, None if draws is None else (draws[2], draws[3]), odev)
         a_det = smp.detach()
@@ -395,11 +399,14 @@ class SACOptimizer:
         # statistics pushed through the same accumulators as the gradients (normaliser moments of this minibatch and the
         # activity statistics: sync_model.py:37-45), then the mean over workers
         inv_n = 1.0
-        SyncReplicasAdam.pack_stats(self, net)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            SyncReplicasAdam.pack_stats(self, net)
             dist.all_reduce(net.bucket, group=self.group)
             inv_n = 1.0 / dist.get_world_size(self.group)
-        SyncReplicasAdam.unpack_stats(self, net, inv_n)
+            SyncReplicasAdam.unpack_stats(self, net, inv_n)
+        elif net.normalize_state:  # one worker: the "mean over workers" of the pushed statistics is the statistics
+            net.state_mean.copy_(net._new_mean)
+            net.state_std.copy_(net._new_std)
         nc, n = net.n_critic, net.n_params
         for lo, hi, lr in ((0, nc, self.lr_critic), (nc, n, self.lr_actor)):  # step = device counter + 1
             _cabi.check(_cabi.pfpn_adam_step_dev(net.params[lo:hi].data_ptr(), net.grads[lo:hi].data_ptr(), self.m[lo:hi].data_ptr(),
