@@ -73,3 +73,17 @@ def test_gae_kernel_on_the_golden_vectors(cuda_dev):
                                    float(c["gae_gamma"]), _stream_ptr()))
         assert np.array_equal(adv.cpu().numpy().astype(np.float64), c["adv"])
         assert np.array_equal(tgt.cpu().numpy().astype(np.float64), c["target"])
+
+
+def test_host_pipeline_chunk_schedule_covers_the_batch_and_ramps():
+    """HostHeadPipeline._schedule (pure host logic): contiguous cover of [0, B), no chunk above the slot size, small first
+    and last chunks when the batch is large enough (pipeline fill / drain), plain equal chunks otherwise."""
+    from pfpn_b200.host import HostHeadPipeline
+    for B, chunk in [(65536, 8192), (65537, 8192), (30000, 8192), (20000, 8192), (8192, 8192), (1000, 1000), (5, 5), (100000, 4096)]:
+        b = HostHeadPipeline._schedule(B, chunk)
+        assert b[0][0] == 0 and b[-1][1] == B
+        assert all(lo < hi and hi - lo <= chunk for lo, hi in b)
+        assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+    big = [hi - lo for lo, hi in HostHeadPipeline._schedule(65536, 8192)]
+    assert big[0] == 1024 and big[-1] == 1024 and max(big) == 8192
+    assert [hi - lo for lo, hi in HostHeadPipeline._schedule(20000, 8192)] == [8192, 8192, 3616]
