@@ -25,7 +25,9 @@
 extern "C" {
 #endif
 
-#define PFPN_ABI_VERSION 1
+/* 2: round 2 -- pfpn_rsample_args / pfpn_sac_head_args gained `offset_dev`, pfpn_head_push the packet protocol,
+ *    pfpn_sync_args `params_lo`; new entry points are additive. */
+#define PFPN_ABI_VERSION 2
 
 typedef void* pfpn_stream_t;
 

@@ -13,7 +13,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_abi_version_and_status_strings():
-    assert _cabi.pfpn_abi_version() == 1
+    assert _cabi.pfpn_abi_version() == 2
     assert _cabi.pfpn_status_string(0) == b"ok"
     for code in (-1, -2, -3, -4):
         assert _cabi.pfpn_status_string(code).startswith(b"pfpn:")
