@@ -10,7 +10,7 @@ pin = lambda t: t.contiguous().pin_memory()
 g = torch.Generator().manual_seed(1)
 logits = pin(torch.randn(B, A, P, generator=g) * 2); loc, logstd = synth.particle_grid(A, P, g); loc, logstd = pin(loc), pin(logstd)
 value = pin(torch.rand(B, A, generator=g) * 2 - 1); adv = pin(torch.randn(B, generator=g)); lp_old = pin(torch.randn(B, generator=g) * 0.1 - 20)
-for chunk, ns in [(8192, 3), (4096, 3), (2048, 3), (2048, 4), (1024, 4), (4096, 4), (16384, 2)]:
+for chunk, ns in [(8192, 3), (6144, 3), (12288, 3), (16384, 3), (8192, 4), (4096, 4), (16384, 2)]:
     pipe = HostHeadPipeline(B, A, P, dev, chunk=chunk, n_streams=ns)
     for _ in range(2): pipe.run(logits, loc, logstd, value, adv, lp_old)
     t0 = time.perf_counter(); n = 6
