@@ -186,6 +186,16 @@ __device__ __forceinline__ float u32_to_unit_open(uint32_t x) {
   float u = ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);  // 24-bit, strictly inside (0,1)
   return u;
 }
+// One standard normal from two 24-bit uniforms (Box-Muller, cosine branch) on the MUFU pipe: sqrt.approx(-2 ln u1)
+// cos.approx(2 pi u2).  Shared by K2 (csrc/sample.cu) and K2f (csrc/rollout.cu) so that both produce the same bits for the
+// same Philox block; absolute error ~1e-6, far below the resolution of the 24-bit uniforms it is fed.
+__device__ __forceinline__ float normal_from_bits(uint32_t x, uint32_t y) {
+  const float u1 = u32_to_unit_open(x), u2 = u32_to_unit_open(y);
+  float l, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u1));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.f * 0.6931471805599453f * l));
+  return r * __cosf(6.283185307179586f * u2);
+}
 __device__ __forceinline__ double u64_to_unit_double(uint32_t hi, uint32_t lo) {
   // 53-bit mantissa in [0,1)
   uint64_t x = ((uint64_t)hi << 32) | lo;

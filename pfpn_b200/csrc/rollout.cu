@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(SLOTS * 72 + 32, 2) rollout_kernel(const Rollo
       vsum[i] = 0.f;
     }
     asm volatile("bar.sync 1, %0;" ::"r"(NTHR) : "memory");  // constants visible to every slot
-    const Philox rng(kp.a.seed);
+    const Philox7 rng(kp.a.seed);  // (as K2)
     const float delta = 4e-6f + (float)P * 6e-8f;  // error budget of the fp32 CDF relative to the total (as K2)
 
     for (int it = 0; it < my_tiles; ++it) {
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(SLOTS * 72 + 32, 2) rollout_kernel(const Rollo
       if (kp.a.ext_normal != nullptr) {
         eps = __ldg(&kp.a.ext_normal[r * P + idx]);
       } else {
-        eps = __fsqrt_rn(-2.f * logf(u32_to_unit_open(qnx))) * cospif(2.f * u32_to_unit_open(qny));  // (= K2's sqrtf)
+        eps = normal_from_bits(qnx, qny);  // (the function K2 uses: same bits)
       }
       const float2 ms_ = musd[a * P + idx];  // (shared-memory table: a dependent global load here was 5 % of all stall samples)
       const float v = __fadd_rn(__fmul_rn(eps, ms_.y), ms_.x);
