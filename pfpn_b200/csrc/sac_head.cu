@@ -210,15 +210,19 @@ __global__ void __launch_bounds__(SLOTS* AT * 8 + 32, 1) sac_head_kernel(const S
       if (!is_tail) {
         mbar_wait(smem_u32(&full_bar[st]), ph);
       } else {
+        // (the slots past the batch end are zero-filled: their threads run the row math on their OWN slot -- finite inputs,
+        //  results discarded -- instead of re-reading slot 0's row, which slot 0's threads overwrite with the gradient in the
+        //  same phase: a benign but real read-after-write race compute-sanitizer's racecheck reported)
         const int nvalid = (B - b0) * AP;
-        for (int i = tid; i < nvalid; i += NTHR) sbuf[i] = __ldg(&g_logits[(size_t)b0 * AP + i]);
-        for (int i = tid; i < (B - b0) * A; i += NTHR) sbuf[TILE_F + i] = __ldg(&kp.a.g_sample[(size_t)b0 * A + i]);
+        for (int i = tid; i < TILE_F; i += NTHR) sbuf[i] = i < nvalid ? __ldg(&g_logits[(size_t)b0 * AP + i]) : 0.f;
+        for (int i = tid; i < SLOTS * A; i += NTHR)
+          sbuf[TILE_F + i] = i < (B - b0) * A ? __ldg(&kp.a.g_sample[(size_t)b0 * A + i]) : 0.f;
         asm volatile("bar.sync 1, %0;" ::"r"(NTHR) : "memory");  // compute threads only; the last tile only
       }
       const int b = b0 + slot;
       const bool row_ok = b < B;
-      const long long r = (long long)(row_ok ? b : b0) * A + a;  // (masked rows recompute state b0, results discarded)
-      float* lg = sbuf + (row_ok ? rowoff_p : a * P);
+      const long long r = (long long)(row_ok ? b : b0) * A + a;  // (masked rows: zero logits, draws of state b0, results discarded)
+      float* lg = sbuf + rowoff_p;
 
       // ---- step 1: draws, noisy logits (log2 domain), locations -----------------------------------------------
       // Slots are kept as register PAIRS (slot e -> pair e / 2, half e % 2) so that steps 3 / 4 run on packed fp32x2
