@@ -233,3 +233,42 @@ def test_sync_replicas_adam_apply_gradients_two_ranks_gloo():
             assert torch.allclose(out[key], want, rtol=1e-6, atol=1e-7), key
         assert out["step"] == 1 and out["gstep"] == 1 and out["ticks"] == 1
     assert torch.equal(res[0][1]["params"], res[1][1]["params"])  # replicas bit-identical
+
+
+def test_peer_gather_bookkeeping_without_a_gpu(monkeypatch):
+    """PeerGather's host-side protocol (exchange numbering, rotating slots, one-exchange lag, who consumes what) with the
+    device calls stubbed: push v may carry the sum of v-1 (consume_into), never more than one exchange lags, reduce()
+    consumes the oldest, and slot(v) = v mod 4 so that v+3 never lands on an unconsumed slot."""
+    import ctypes as C
+    from pfpn_b200 import _cabi, peer
+
+    calls = []
+    monkeypatch.setattr(_cabi, "pfpn_peer_gather_sum_packets",
+                        lambda rows, nr, value, n, out, scale, st: calls.append((rows, nr, value, n)) or 0)
+    pg = object.__new__(peer.PeerGather)
+    pg.rank, pg.world, pg.n, pg.dev = 1, 4, 2520, torch.device("cpu")
+    pg.pushed = pg.consumed = 0
+    pg._gather_ptr = 1 << 20
+    pg._gather_ptrs = [(r + 1) << 24 for r in range(4)]
+    pg._push = [pg._make_push(s) for s in range(pg.NBUF)]
+    out = torch.zeros(2520)
+    p1 = pg.push_args(consume_into=out)            # nothing to consume yet
+    assert (p1.value, p1.consume_value, p1.protocol, p1.nranks) == (1, 0, 1, 4) and pg.pending == 1
+    assert p1.out[2] == pg._gather_ptrs[2] + ((1 * 4 + 1) * 2520) * 8   # slot 1, my row (rank 1), 8-byte packets
+    p2 = pg.push_args(consume_into=out, scale=0.25)
+    assert (p2.value, p2.consume_value) == (2, 1) and pg.pending == 1
+    assert p2.consume_rows == pg._gather_ptr + 1 * 4 * 2520 * 8 and p2.consume_out == out.data_ptr()
+    assert abs(p2.consume_scale - 0.25) < 1e-9
+    p3 = pg.push_args()                             # producer only: exchange 2 stays pending
+    assert (p3.value, p3.consume_value) == (3, 0) and pg.pending == 2
+    with pytest.raises(RuntimeError):
+        pg.push_args()                              # a third unconsumed exchange would overwrite a live slot
+    pg.reduce(out)
+    pg.reduce(out)
+    assert [c[2] for c in calls] == [2, 3] and pg.pending == 0
+    assert calls[0][0] == pg._gather_ptr + 2 * 4 * 2520 * 8 and calls[1][0] == pg._gather_ptr + 3 * 4 * 2520 * 8
+    with pytest.raises(RuntimeError):
+        pg.reduce(out)
+    for v in range(4, 12):                          # steady state: slots rotate 0,1,2,3,...
+        p = pg.push_args(consume_into=out)
+        assert p.value == v and pg.slot_of(v) == v % 4 and (p.consume_value == v - 1 or v == 4)
